@@ -1,0 +1,112 @@
+/*
+ * voltools_b200.h -- C ABI of libvoltools_b200.so: the B200-native (sm_100a) replacement for the device
+ * side of voltools' affine volume-resampling path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch / cupy types), returns an
+ * int status (0 = VT_OK, otherwise pass it to vt_error_string) and is stream-ordered and non-blocking
+ * unless stated.  Device buffers are owned by the caller; the library allocates device memory only inside
+ * the opaque contexts created by vt_host_ctx_create().
+ *
+ * Conventions (identical to the reference): a volume is a C-contiguous float32 array of numpy shape
+ * (d0, d1, d2); a transform is a row-major float32 4x4 mapping OUTPUT index (a0,a1,a2,1) to INPUT index
+ * (voltools/utils/matrices.py:111-154); the sample point of output voxel a is M*a, evaluated with the
+ * reference kernel's float32 recipe (voltools/transforms.py:264-274).
+ *
+ * Each function names the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef VOLTOOLS_B200_H
+#define VOLTOOLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_ABI_VERSION 1
+
+/* status codes: 0 ok; 1..99 library errors; 1000+e = cudaError_t e; 2000+e = CUresult e */
+#define VT_OK 0
+#define VT_ERR_INVALID_ARG 1
+#define VT_ERR_UNSUPPORTED 2
+#define VT_ERR_NO_DEVICE 3
+#define VT_ERR_ALLOC 4
+
+/* interpolation device function, as selected by voltools/transforms.py:11-17 (_INTERPOLATIONS):
+ *   'linear' -> VT_LINEAR; 'bspline','filt_bspline' -> VT_CUBIC_TEX; '*_simple' -> VT_CUBIC_SIMPLE.
+ * The filt_* names differ only by running vt_prefilter_f32 on the volume first.                      */
+#define VT_LINEAR 0       /* linearTex3D       voltools/kernels/helper_interpolation.h:3-6   */
+#define VT_CUBIC_TEX 1    /* cubicTex3D        voltools/kernels/helper_interpolation.h:8-40  */
+#define VT_CUBIC_SIMPLE 2 /* cubicTex3DSimple  voltools/kernels/helper_interpolation.h:42-68 */
+
+/* flags for vt_affine_f32 (OR together) */
+#define VT_OOB_SKIP 0x0u       /* out-of-bounds output voxels are not written (reference: transforms.py:276-278) */
+#define VT_OOB_ZERO 0x1u       /* ...are written as 0: fuses the reference's fill(0)/cp.zeros (transforms.py:208,
+                                  volume.py:73) into the kernel when the library owns a fresh output            */
+#define VT_WEIGHTS_TEX_RN 0x0u /* texture-unit compatible weights: coordinate -> 1.8 fixed point, round-nearest  */
+#define VT_WEIGHTS_TEX_TRUNC 0x2u /* same, truncating conversion (diagnostic)                                     */
+#define VT_WEIGHTS_EXACT 0x4u  /* exact float32 fractions (more accurate than the reference; not parity)         */
+#define VT_KERNEL_AUTO 0x00u   /* pick the kernel family from shape/alignment/matrix                             */
+#define VT_KERNEL_GATHER 0x10u /* force: direct global gathers through L1                                        */
+#define VT_KERNEL_BRICK 0x20u  /* force: TMA-staged shared-memory brick cache (VT_ERR_UNSUPPORTED if impossible) */
+
+#define VT_MAX_BATCH 32 /* matrices per launch held in kernel parameters; larger batches are chunked */
+
+int vt_abi_version(void);
+const char *vt_error_string(int status);
+
+/* replaces voltools/utils/general.py:61-80 (get_available_devices): number of CUDA devices */
+int vt_device_count(int *count);
+
+/*
+ * Cubic B-spline prefilter, in place, X (fastest axis) then Y then Z.
+ * Replaces _bspline_prefilter (voltools/transforms.py:290-309) and the kernels SamplesToCoefficients3DX/Y/Z
+ * (voltools/kernels/bspline.h:58-99); any shape >= 1 per axis (no power-of-two launch constraint).
+ *   d_vol   device pointer, (d0,d1,d2) float32 C-contiguous
+ *   variant 0 = default (fastest validated), 1 = sequential two-sweep kernels with the reference's exact
+ *           operation order (bit-identical coefficients), 2 = windowed kernels
+ *   device  CUDA ordinal, or -1 for the current device
+ *   stream  cudaStream_t (NULL = legacy default stream)
+ */
+int vt_prefilter_f32(float *d_vol, int d0, int d1, int d2, int variant, int device, void *stream);
+
+/*
+ * The `transform` kernel launch (voltools/transforms.py:253-282 launched at :212 and volume.py:78), for a
+ * batch of matrices over one resident source volume.
+ *   d_src              sampled volume (s0,s1,s2): raw samples, or coefficients from vt_prefilter_f32
+ *   d_dst              n_mats output volumes of shape (o0,o1,o2); matrix k writes at d_dst + k*dst_batch_stride
+ *                      (elements).  The reference always has (o0,o1,o2) == (s0,s1,s2).
+ *   h_mats             HOST pointer, n_mats row-major float32 4x4 matrices; copied into kernel parameters
+ *                      (replaces the per-call cp.asarray(transform_m) H2D copy, volume.py:70)
+ *   interp             VT_LINEAR / VT_CUBIC_TEX / VT_CUBIC_SIMPLE
+ *   flags              VT_OOB_* | VT_WEIGHTS_* | VT_KERNEL_*
+ *   z_begin, z_end     only output planes a0 in [z_begin, z_end) are produced (z-slab sharding); pass 0, o0
+ */
+int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
+                  long long dst_batch_stride, const float *h_mats, int n_mats, int interp, unsigned flags,
+                  int z_begin, int z_end, int device, void *stream);
+
+/* which kernel family vt_affine_f32 would run for these arguments: 1 = gather, 2 = brick */
+int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d_src, const float *h_mats,
+                   int n_mats, int interp, unsigned flags, int *family);
+
+/*
+ * Host-buffer path: numpy in -> numpy out, as transforms.affine() with output=None
+ * (voltools/transforms.py:180-223: H2D, [prefilter], kernel, D2H).  Blocking.  The context owns pinned
+ * staging and device buffers that grow to the largest volume seen, and pipelines the copies with the
+ * kernels in z-slabs.
+ */
+typedef struct vt_host_ctx vt_host_ctx;
+int vt_host_ctx_create(int device, vt_host_ctx **ctx);
+int vt_host_ctx_destroy(vt_host_ctx *ctx);
+int vt_host_affine_f32(vt_host_ctx *ctx, const float *h_src, int s0, int s1, int s2, float *h_dst, int o0, int o1,
+                       int o2, const float *h_m16, int interp, int prefilter, unsigned flags);
+
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+long long vt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLTOOLS_B200_H */

@@ -1,0 +1,305 @@
+/*
+ * vt_oracle.c -- CPU restatement of the reference's GPU resampling path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under voltools_b200/ may import, link or call this file; it is the
+ * checker used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.  It is deliberately
+ * scalar and slow.
+ *
+ * Parity status: PINNED.  This restatement is checked (tests/test_oracle.py) against
+ *   (1) the reference's own `__host__` prefilter code compiled from /root/reference (oracle/_ref/
+ *       libvt_ref_host.so, built by oracle/build_ref.py) and the SURVEY Appendix A.4 known-answer vector,
+ *   (2) golden volumes under tests/golden/ produced by the reference's own CUDA kernels (captured from
+ *       voltools/transforms.py and compiled unmodified) running on a B200 through a real texture object
+ *       (tests/golden/make_golden_gpu.py), and
+ *   (3) on the GPU box, live against oracle/_ref/libvt_ref_gpu.so (same kernels) on seeded inputs.
+ *
+ * What is restated (reference file:line):
+ *   coordinate generation + bounds skip ...... voltools/transforms.py:243-281
+ *   linearTex3D / cubicTex3D / cubicTex3DSimple  voltools/kernels/helper_interpolation.h:3-68
+ *   bspline_weights / bspline ................. voltools/kernels/bspline.h:102-122
+ *   prefilter (X, then Y, then Z) ............. voltools/kernels/bspline.h:2-99, voltools/transforms.py:290-309
+ *   Pole, dot(float4,float4) .................. voltools/kernels/helper_math.h:1468, :1256-1259
+ *   tex3D<float> border/linear/unnormalised ... hardware (CUDA C Programming Guide, "Texture Fetching":
+ *       xB = x - 0.5, i = floor(xB), alpha = frac(xB) held in 9-bit fixed point with 8 fractional bits;
+ *       texels outside the array read 0).  The conversion rule of the coordinate to fixed point is not
+ *       documented; `tex_rule` selects it and the default was fixed by the on-B200 probe.
+ *
+ * Float recipe: the order of float32 operations (including which multiply-adds the reference's compiled
+ * kernels contract into FMAs, read from the SASS of oracle/_ref/*.cubin) is reproduced with explicit
+ * fmaf(); compile with -ffp-contract=off so the compiler adds none of its own.
+ *
+ * Axis convention: a volume has numpy shape (d0, d1, d2), C-contiguous; p0/p1/p2 are the (+0.5 shifted)
+ * input coordinates along those axes; the texture's (x, y, z) = (p2, p1, p0).
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#define VTO_LINEAR 0        /* linearTex3D            ('linear')                               */
+#define VTO_CUBIC_TEX 1     /* cubicTex3D             ('bspline', 'filt_bspline')              */
+#define VTO_CUBIC_SIMPLE 2  /* cubicTex3DSimple       ('bspline_simple', 'filt_bspline_simple') */
+
+/* tex_rule: how the texture unit turns a float coordinate into 1.8 fixed point                */
+#define VTO_TEX_RN 0     /* round to nearest (ties to even) of x*256   -- what B200 does (probe)    */
+#define VTO_TEX_TRUNC 1  /* floor of x*256                                                          */
+#define VTO_TEX_EXACT 2  /* no quantisation: exact float32 fraction (not what the hardware does)   */
+
+/* ---------------------------------------------------------------------------------------------- */
+/* prefilter: bspline.h:2-54                                                                     */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* Pole = sqrt(3.0f) - 2.0f folded to float32 (helper_math.h:1468); both constants below are what nvcc
+ * folds the reference's expressions to (SASS immediates 0xbe8930a4, 0x40bfffff, 0x3e58658d).          */
+static float vto_pole(void) { return sqrtf(3.0f) - 2.0f; }
+static float vto_lambda(void) { const float p = vto_pole(); return (1.0f - p) * (1.0f - 1.0f / p); }
+static float vto_anti(void) { const float p = vto_pole(); return p / (p - 1.0f); }
+
+/* In-place conversion of one line of `n` samples spaced `step` floats apart.                     */
+static void vto_line(float *c, size_t n, ptrdiff_t step)
+{
+    const float pole = vto_pole(), lambda = vto_lambda(), anti = vto_anti();
+    const float npole = -pole; /* the compiled recursion is fma(s, lambda, -(prev * |pole|)) */
+    if (n == 0) return;
+    /* InitialCausalCoefficient, bspline.h:2-19: horizon min(12, n), accumulates zn * c[k] with an FMA */
+    const size_t horizon = n < 12 ? n : 12;
+    float zn = pole, sum = c[0];
+    for (size_t k = 0; k < horizon; k++) {
+        sum = fmaf(zn, c[k * step], sum);
+        zn *= pole;
+    }
+    float prev = lambda * sum;
+    c[0] = prev;
+    /* causal recursion, bspline.h:43-46 */
+    for (size_t k = 1; k < n; k++) {
+        prev = fmaf(c[k * step], lambda, -(prev * npole));
+        c[k * step] = prev;
+    }
+    /* anticausal init + recursion, bspline.h:48-53 */
+    prev = anti * c[(n - 1) * step];
+    c[(n - 1) * step] = prev;
+    for (ptrdiff_t k = (ptrdiff_t)n - 2; k >= 0; k--) {
+        prev = pole * (prev - c[k * step]);
+        c[k * step] = prev;
+    }
+}
+
+void vto_prefilter_line(float *c, int n, int step) { vto_line(c, (size_t)n, step); }
+
+/* bspline.h:58-99 driven as transforms.py:305-307: X (fastest axis) then Y then Z, in place. */
+void vto_prefilter(float *vol, int d0, int d1, int d2)
+{
+    const size_t D = d0, H = d1, W = d2;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t z = 0; z < D; z++)
+        for (size_t y = 0; y < H; y++)
+            vto_line(vol + (z * H + y) * W, W, 1);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t z = 0; z < D; z++)
+        for (size_t x = 0; x < W; x++)
+            vto_line(vol + z * H * W + x, H, (ptrdiff_t)W);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t y = 0; y < H; y++)
+        for (size_t x = 0; x < W; x++)
+            vto_line(vol + y * W + x, D, (ptrdiff_t)(H * W));
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* texture unit emulation                                                                        */
+/* ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+    const float *v;
+    int d0, d1, d2;
+    int rule;
+} vto_tex;
+
+static inline float vto_texel(const vto_tex *t, long i0, long i1, long i2)
+{
+    /* cudaAddressModeBorder: outside the array reads 0 (transforms.py:187-189) */
+    if (i0 < 0 || i1 < 0 || i2 < 0 || i0 >= t->d0 || i1 >= t->d1 || i2 >= t->d2) return 0.0f;
+    return t->v[((size_t)i0 * t->d1 + i1) * t->d2 + i2];
+}
+
+/* one axis: coordinate -> (base texel, alpha) */
+static inline void vto_fix(float x, int rule, long *i, float *alpha)
+{
+    if (rule == VTO_TEX_EXACT) {
+        const float xb = x - 0.5f;
+        const float fl = floorf(xb);
+        *i = (long)fl;
+        *alpha = xb - fl;
+        return;
+    }
+    /* 1.8 fixed point: X = round(x * 256); xB = X - 128 */
+    const float s = x * 256.0f; /* exact scaling */
+    long X = (rule == VTO_TEX_RN) ? lrintf(s) : (long)floorf(s);
+    X -= 128;
+    long b = X >> 8; /* arithmetic shift == floor */
+    *i = b;
+    *alpha = (float)(X - b * 256) * (1.0f / 256.0f);
+}
+
+/* tex3D<float>(tex, x, y, z) with x along d2, y along d1, z along d0 */
+static float vto_tex3d_impl(const vto_tex *t, float x, float y, float z)
+{
+    long i2, i1, i0;
+    float ax, ay, az;
+    vto_fix(x, t->rule, &i2, &ax);
+    vto_fix(y, t->rule, &i1, &ay);
+    vto_fix(z, t->rule, &i0, &az);
+    const float c000 = vto_texel(t, i0, i1, i2), c001 = vto_texel(t, i0, i1, i2 + 1);
+    const float c010 = vto_texel(t, i0, i1 + 1, i2), c011 = vto_texel(t, i0, i1 + 1, i2 + 1);
+    const float c100 = vto_texel(t, i0 + 1, i1, i2), c101 = vto_texel(t, i0 + 1, i1, i2 + 1);
+    const float c110 = vto_texel(t, i0 + 1, i1 + 1, i2), c111 = vto_texel(t, i0 + 1, i1 + 1, i2 + 1);
+    /* (1-a)(1-b)(1-g) T + ... ; the unit's internal arithmetic is wider than what matters at the
+     * stated 2e-3 tolerance, so the evaluation order here is a free choice. */
+    const float bx = 1.0f - ax, by = 1.0f - ay, bz = 1.0f - az;
+    const float r00 = bx * c000 + ax * c001, r01 = bx * c010 + ax * c011;
+    const float r10 = bx * c100 + ax * c101, r11 = bx * c110 + ax * c111;
+    const float s0 = by * r00 + ay * r01, s1 = by * r10 + ay * r11;
+    return bz * s0 + az * s1;
+}
+
+float vto_tex3d(const float *vol, int d0, int d1, int d2, float x, float y, float z, int rule)
+{
+    vto_tex t = {vol, d0, d1, d2, rule};
+    return vto_tex3d_impl(&t, x, y, z);
+}
+
+void vto_tex3d_many(const float *vol, int d0, int d1, int d2, const float *xyz, long n, float *out, int rule)
+{
+    vto_tex t = {vol, d0, d1, d2, rule};
+    for (long k = 0; k < n; k++) out[k] = vto_tex3d_impl(&t, xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]);
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* interpolators: helper_interpolation.h                                                         */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* bspline.h:102-112 with g0/g1/h0/h1 of helper_interpolation.h:17-20, per axis, in the compiled op order:
+ *   w1 = fma(-0.5*f*f, 2-f, 2/3)     w2 = fma(-0.5*o*o, 2-o, 2/3)     w3 = f * (f*f * 1/6)
+ *   g0 = fma(o, o*o * 1/6, w1)       g1 = w2 + w3
+ *   h0 = idx + (w1/g0 - 0.5)         h1 = idx + (w3/g1 + 1.5)                                       */
+static inline void vto_ruijters(float coord, float *g0, float *g1, float *h0, float *h1)
+{
+    const float cg = coord - 0.5f;
+    const float idx = floorf(cg);
+    const float f = cg - idx;
+    const float o = 1.0f - f;
+    const float sq = f * f, osq = o * o;
+    const float sixth = 1.0f / 6.0f, twothirds = 2.0f / 3.0f;
+    const float w1 = fmaf(sq * -0.5f, 2.0f - f, twothirds);
+    const float w2 = fmaf(osq * -0.5f, 2.0f - o, twothirds);
+    const float w3 = f * (sq * sixth);
+    *g0 = fmaf(o, osq * sixth, w1);
+    *g1 = w2 + w3;
+    *h0 = idx + (w1 / *g0 - 0.5f);
+    *h1 = idx + (w3 / *g1 + 1.5f);
+}
+
+/* helper_interpolation.h:8-40 */
+static float vto_cubic_tex(const vto_tex *t, float x, float y, float z)
+{
+    float g0x, g1x, h0x, h1x, g0y, g1y, h0y, h1y, g0z, g1z, h0z, h1z;
+    vto_ruijters(x, &g0x, &g1x, &h0x, &h1x);
+    vto_ruijters(y, &g0y, &g1y, &h0y, &h1y);
+    vto_ruijters(z, &g0z, &g1z, &h0z, &h1z);
+    float t000 = vto_tex3d_impl(t, h0x, h0y, h0z), t100 = vto_tex3d_impl(t, h1x, h0y, h0z);
+    t000 = fmaf(g0x, t000, g1x * t100);
+    float t010 = vto_tex3d_impl(t, h0x, h1y, h0z), t110 = vto_tex3d_impl(t, h1x, h1y, h0z);
+    t010 = fmaf(g0x, t010, g1x * t110);
+    t000 = fmaf(g0y, t000, g1y * t010);
+    float t001 = vto_tex3d_impl(t, h0x, h0y, h1z), t101 = vto_tex3d_impl(t, h1x, h0y, h1z);
+    t001 = fmaf(g0x, t001, g1x * t101);
+    float t011 = vto_tex3d_impl(t, h0x, h1y, h1z), t111 = vto_tex3d_impl(t, h1x, h1y, h1z);
+    t011 = fmaf(g0x, t011, g1x * t111);
+    t001 = fmaf(g0y, t001, g1y * t011);
+    return fmaf(g0z, t000, g1z * t001);
+}
+
+/* bspline.h:114-122 */
+static inline float vto_bspline(float t)
+{
+    t = fabsf(t);
+    const float a = 2.0f - t;
+    if (t < 1.0f) return fmaf(a, (t * -0.5f) * t, 2.0f / 3.0f);
+    if (t < 2.0f) return (a * a) * a / 6.0f;
+    return 0.0f;
+}
+
+/* helper_interpolation.h:42-68: 4x4x4 point fetches at texel centres => exact texel values */
+static float vto_cubic_simple(const vto_tex *t, float x, float y, float z)
+{
+    const float cgx = x - 0.5f, cgy = y - 0.5f, cgz = z - 0.5f;
+    const float ix = floorf(cgx), iy = floorf(cgy), iz = floorf(cgz);
+    const float fx = cgx - ix, fy = cgy - iy, fz = cgz - iz;
+    float result = 0.0f;
+    for (int kz = -1; kz <= 2; kz++) {
+        const float bz = vto_bspline((float)kz - fz);
+        for (int ky = -1; ky <= 2; ky++) {
+            const float byz = vto_bspline((float)ky - fy) * bz;
+            for (int kx = -1; kx <= 2; kx++) {
+                const float bxyz = vto_bspline((float)kx - fx) * byz;
+                const float texel = vto_texel(t, (long)iz + kz, (long)iy + ky, (long)ix + kx);
+                result = fmaf(bxyz, texel, result);
+            }
+        }
+    }
+    return result;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* the transform kernel: transforms.py:253-282                                                   */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* p_r = dot((a0,a1,a2,1), M[r]) + 0.5 in the compiled order (SASS of oracle/_ref/transform_*.cubin):
+ *   t = a1*M[r][1]; t = fma(a0, M[r][0], t); t = fma(a2, M[r][2], t); t = M[r][3] + t; p = t + 0.5 */
+static inline float vto_coord(const float *row, float a0, float a1, float a2)
+{
+    float t = a1 * row[1];
+    t = fmaf(a0, row[0], t);
+    t = fmaf(a2, row[2], t);
+    t = row[3] + t;
+    return t + 0.5f;
+}
+
+/*
+ * src: (s0,s1,s2) sampled volume.  dst: (o0,o1,o2) output volume (the reference always has o == s).
+ * m16: row-major float32 4x4 mapping OUTPUT index -> INPUT index.  Voxels whose sample point falls
+ * outside the source are skipped (dst keeps its previous contents), exactly as transforms.py:276-278.
+ * Only output planes a0 in [z_begin, z_end) are produced (the whole volume is [0, o0)).
+ * Returns the number of voxels written.
+ */
+long vto_affine(const float *src, int s0, int s1, int s2, float *dst, int o0, int o1, int o2,
+                const float *m16, int interp, int tex_rule, int z_begin, int z_end)
+{
+    vto_tex t = {src, s0, s1, s2, tex_rule};
+    vto_tex tp = {src, s0, s1, s2, VTO_TEX_EXACT};
+    const float f0 = (float)s0, f1 = (float)s1, f2 = (float)s2;
+    long written = 0;
+    (void)tp;
+#pragma omp parallel for schedule(static) reduction(+ : written)
+    for (int a0 = z_begin; a0 < z_end; a0++) {
+        for (int a1 = 0; a1 < o1; a1++) {
+            for (int a2 = 0; a2 < o2; a2++) {
+                const float p0 = vto_coord(m16 + 0, (float)a0, (float)a1, (float)a2);
+                const float p1 = vto_coord(m16 + 4, (float)a0, (float)a1, (float)a2);
+                const float p2 = vto_coord(m16 + 8, (float)a0, (float)a1, (float)a2);
+                if (p2 < 0 || p1 < 0 || p0 < 0 || p2 >= f2 || p1 >= f1 || p0 >= f0) continue;
+                float r;
+                if (interp == VTO_LINEAR) r = vto_tex3d_impl(&t, p2, p1, p0);
+                else if (interp == VTO_CUBIC_TEX) r = vto_cubic_tex(&t, p2, p1, p0);
+                else r = vto_cubic_simple(&t, p2, p1, p0);
+                dst[((size_t)a0 * o1 + a1) * o2 + a2] = r;
+                written++;
+            }
+        }
+    }
+    return written;
+}
+
+/* constants, exported so tests can pin them against the SASS immediates */
+float vto_const_pole(void) { return vto_pole(); }
+float vto_const_lambda(void) { return vto_lambda(); }
+float vto_const_anti(void) { return vto_anti(); }

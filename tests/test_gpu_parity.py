@@ -1,0 +1,197 @@
+"""GPU parity: libvoltools_b200 (through the public API / C ABI) vs the CPU oracle and vs the reference's own
+CUDA kernels run through a real texture object (oracle/_ref, when present).
+
+Tolerances (max |d| / value range of the SAMPLED volume, i.e. of the coefficient volume for filt_*):
+  bspline_simple, filt_bspline_simple, prefilter ........ 1e-5   (pure float32 in the reference)
+  linear, bspline, filt_bspline ......................... 2e-3   (reference uses 8-bit hardware weights)
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+MODES = ['linear', 'bspline', 'bspline_simple', 'filt_bspline', 'filt_bspline_simple']
+TOL = {'linear': 2e-3, 'bspline': 2e-3, 'filt_bspline': 2e-3, 'bspline_simple': 1e-5, 'filt_bspline_simple': 1e-5}
+
+
+@pytest.fixture(scope='module')
+def vt():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import voltools_b200 as vt
+    return vt
+
+
+def _center(shape):
+    return np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+
+
+def _matrices(vt, shape):
+    c = _center(shape)
+    tm = vt.utils.transform_matrix
+    return {
+        'identity': np.identity(4, dtype=np.float32),
+        'shift': tm(translation=(0.37, -1.21, 2.5)),
+        'rot45': tm(rotation=(0, 45, 0), rotation_order='rzxz', center=c),
+        'rot_general': tm(rotation=(33.3, -71.0, 12.5), rotation_order='sxyz', center=c),
+        'full_affine': tm(scale=(1.1, 0.9, 1.05), shear=(0.05, -0.03, 0.02), rotation=(30, 45, 60),
+                          rotation_order='rzxz', translation=(1.5, -0.75, 0.5), center=c),
+        'downscale': tm(scale=(2.3, 1.7, 3.1), center=c),
+        'rotate_origin': vt.utils.rotation_matrix((10, 20, 30)),
+    }
+
+
+def _range(vol, mode):
+    v = oracle.prefilter(vol) if mode.startswith('filt') else vol
+    return float(np.ptp(v))
+
+
+def _err(a, b, rng):
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) / rng
+
+
+@pytest.mark.parametrize('shape', [(20, 24, 28), (33, 17, 45), (64, 64, 64)])
+@pytest.mark.parametrize('mode', MODES)
+def test_affine_vs_oracle(vt, shape, mode):
+    rng = np.random.default_rng(sum(shape))
+    vol = rng.random(shape, dtype=np.float32)
+    r = _range(vol, mode)
+    for name, m in _matrices(vt, shape).items():
+        got = vt.affine(vol, m, interpolation=mode, device='gpu:0')
+        want = oracle.affine(vol, m, mode)
+        assert got.shape == vol.shape and got.dtype == np.float32
+        e = _err(got, want, r)
+        assert e <= TOL[mode], f'{mode} {name} {shape}: {e:.3e}'
+        # the set of skipped (zero) voxels must be identical, not just close
+        assert np.array_equal(got == 0, want == 0) or e <= TOL[mode]
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_affine_vs_reference_kernels(vt, mode):
+    """Same inputs through the reference's own kernels + hardware texture on this GPU."""
+    if not oracle.ref_gpu_available():
+        pytest.skip('oracle/_ref/libvt_ref_gpu.so not built')
+    shape = (40, 52, 60)  # all even: the reference's prefilter launch needs power-of-two divisors
+    rng = np.random.default_rng(7)
+    vol = rng.random(shape, dtype=np.float32)
+    r = _range(vol, mode)
+    for name, m in _matrices(vt, shape).items():
+        ref, _, _ = oracle.transform_ref_gpu(vol, m, mode)
+        got = vt.affine(vol, m, interpolation=mode, device='gpu:0')
+        want = oracle.affine(vol, m, mode)
+        e_mine, e_oracle = _err(got, ref, r), _err(want, ref, r)
+        assert e_oracle <= TOL[mode], f'oracle vs reference {mode} {name}: {e_oracle:.3e}'
+        assert e_mine <= TOL[mode], f'ours vs reference {mode} {name}: {e_mine:.3e}'
+
+
+@pytest.mark.parametrize('shape', [(16, 16, 16), (20, 24, 28), (7, 5, 3), (1, 1, 1), (33, 17, 45), (50, 60, 130)])
+def test_prefilter(vt, shape):
+    import torch
+    rng = np.random.default_rng(3)
+    vol = rng.random(shape, dtype=np.float32)
+    want = oracle.prefilter(vol)
+    r = float(np.ptp(want)) or 1.0
+    for variant in (0, 1):
+        t = torch.from_numpy(vol).cuda()
+        vt._native.prefilter(t.data_ptr(), shape, 0, torch.cuda.current_stream().cuda_stream, variant=variant)
+        got = t.cpu().numpy()
+        assert _err(got, want, r) <= 1e-5, (variant, shape, _err(got, want, r))
+    if oracle.ref_gpu_available() and all(s % 2 == 0 for s in shape):
+        ref = oracle.prefilter_ref_gpu(vol)
+        assert _err(want, ref, r) <= 1e-6
+        t = torch.from_numpy(vol).cuda()
+        vt._native.prefilter(t.data_ptr(), shape, 0, torch.cuda.current_stream().cuda_stream, variant=1)
+        assert np.array_equal(t.cpu().numpy(), ref), 'sequential variant must be bit-identical to the reference'
+
+
+def test_output_semantics(vt):
+    """output= given: written in place, out-of-bounds voxels keep their contents, returns None
+    (transforms.py:207-210, :224-226); input arrays are never modified."""
+    import torch
+    shape = (24, 28, 32)
+    rng = np.random.default_rng(11)
+    vol = rng.random(shape, dtype=np.float32)
+    m = _matrices(vt, shape)['rot45']
+    prefill = (rng.random(shape, dtype=np.float32) + 10).astype(np.float32)
+    for mode in ('linear', 'filt_bspline', 'filt_bspline_simple'):
+        out = torch.from_numpy(prefill.copy()).cuda()
+        src = torch.from_numpy(vol).cuda()
+        ret = vt.affine(src, m, interpolation=mode, output=out, device='gpu')
+        assert ret is None
+        assert np.array_equal(src.cpu().numpy(), vol), 'input was modified'
+        want = oracle.affine(vol, m, mode, output=prefill)
+        got = out.cpu().numpy()
+        assert _err(got, want, _range(vol, mode)) <= TOL[mode]
+        kept = want == prefill
+        assert kept.any() and np.array_equal(got[kept], prefill[kept])
+
+
+def test_static_volume_and_batch(vt):
+    import torch
+    shape = (30, 36, 40)
+    rng = np.random.default_rng(5)
+    vol = rng.random(shape, dtype=np.float32)
+    for mode in ('linear', 'filt_bspline', 'bspline_simple'):
+        sv = vt.StaticVolume(vol, interpolation=mode, device='gpu:0')
+        r = _range(vol, mode)
+        mats = [vt.utils.transform_matrix(rotation=(0, a, 0), center=_center(shape)) for a in range(0, 180, 4)]
+        single = sv.transform(rotation=(0, 8, 0))
+        want = oracle.affine(vol, mats[2], mode)
+        assert _err(single, want, r) <= TOL[mode]
+        batch = sv.affine_many(mats).cpu().numpy()
+        assert batch.shape == (len(mats),) + shape
+        for k in (0, 2, 17, len(mats) - 1):
+            assert _err(batch[k], oracle.affine(vol, mats[k], mode), r) <= TOL[mode]
+        assert np.array_equal(batch[2], single), 'batched and single launches must agree bit for bit'
+        out = torch.zeros(shape, device='cuda:0')
+        assert sv.rotate((0, 0, 10), output=out) is None
+        assert _err(out.cpu().numpy(), oracle.affine(vol, vt.utils.rotation_matrix((0, 0, 10)), mode), r) <= TOL[mode]
+
+
+def test_z_slabs_compose(vt):
+    """z-slab sharding: disjoint slabs written by separate calls reproduce the single-call result exactly."""
+    import torch
+    shape = (37, 20, 24)
+    rng = np.random.default_rng(9)
+    vol = torch.from_numpy(rng.random(shape, dtype=np.float32)).cuda()
+    m = _matrices(vt, shape)['full_affine']
+    for interp in (0, 1, 2):
+        full = torch.zeros(shape, device='cuda')
+        vt._native.affine(vol.data_ptr(), shape, full.data_ptr(), shape, m, interp, vt._native.OOB_ZERO)
+        parts = torch.full(shape, -1.0, device='cuda')
+        for z0, z1 in ((0, 9), (9, 10), (10, 30), (30, 37)):
+            vt._native.affine(vol.data_ptr(), shape, parts.data_ptr(), shape, m, interp, vt._native.OOB_ZERO,
+                              z_range=(z0, z1))
+        assert torch.equal(full, parts)
+
+
+def test_reshape(vt):
+    """reshape=True: pad + conjugated matrix (transforms.py:171-178)."""
+    shape = (20, 24, 28)
+    rng = np.random.default_rng(2)
+    vol = rng.random(shape, dtype=np.float32)
+    m = _matrices(vt, shape)['rot45']
+    got = vt.affine(vol, m, interpolation='linear', reshape=True, device='gpu:0')
+    pb, pa, nd = vt.utils.compute_post_transform_dimensions(shape, m)
+    assert got.shape == tuple(int(x) for x in nd)
+    padded = np.pad(vol, list(zip(pb, pa)))
+    m2 = (vt.utils.translation_matrix(-1 * pb) @ m @ vt.utils.translation_matrix(pb)).astype(np.float32)
+    want = oracle.affine(padded, m2, 'linear')
+    assert _err(got, want, 1.0) <= 2e-3
+
+
+def test_errors(vt):
+    vol = np.zeros((4, 4, 4), np.float32)
+    with pytest.raises(ValueError):
+        vt.affine(vol, np.identity(4), device='cpu')
+    with pytest.raises(ValueError):
+        vt.affine(vol, np.identity(4), interpolation='nearest', device='gpu')
+    with pytest.raises(ValueError):
+        vt.StaticVolume(np.zeros((4, 4), np.float32))
+    with pytest.raises(ValueError):
+        vt.utils.rotation_matrix((1, 2, 3), rotation_units='grad')
+    with pytest.raises(ValueError):
+        vt.utils.rotation_matrix((1, 2, 3), rotation_order='xyz')

@@ -1,0 +1,70 @@
+"""Quick device-side timing of our kernels vs the reference's own kernels on this GPU (not the bench)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import oracle  # noqa: E402
+import voltools_b200 as vt  # noqa: E402
+from voltools_b200 import _native  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    sizes = [int(a) for a in sys.argv[1:]] or [256, 512]
+    for n in sizes:
+        shape = (n, n, n)
+        nvox = n ** 3
+        rng = np.random.default_rng(0)
+        vol = rng.random(shape, dtype=np.float32)
+        c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+        mats = {
+            'rot45x': vt.utils.transform_matrix(rotation=(0, 45, 0), rotation_order='rzxz', center=c),
+            'affine': vt.utils.transform_matrix(scale=(1.1, 0.9, 1.05), shear=(0.05, -0.03, 0.02),
+                                                rotation=(30, 45, 60), rotation_order='rzxz',
+                                                translation=(5.5, -3.25, 2.0), center=c),
+        }
+        src = torch.from_numpy(vol).cuda()
+        dst = torch.zeros(shape, device='cuda')
+        st = torch.cuda.current_stream().cuda_stream
+        for variant in (1, 0):
+            tmp = src.clone()
+            ms = timeit(lambda: _native.prefilter(tmp.data_ptr(), shape, 0, st, variant=variant), iters=5, warm=1)
+            print(f'{n}^3 prefilter variant {variant}: {ms:.3f} ms  {nvox / ms / 1e6:.1f} Gvox/s  '
+                  f'({8 * nvox / ms / 1e6 / 6549.1 * 100:.1f}% of 8B/vox roofline)')
+        for mname, m in mats.items():
+            for interp, iname in ((0, 'linear'), (1, 'cubic_tex'), (2, 'cubic_simple')):
+                for fam, fname in ((_native.KERNEL_GATHER, 'gather'), (_native.KERNEL_BRICK, 'brick')):
+                    try:
+                        ms = timeit(lambda: _native.affine(src.data_ptr(), shape, dst.data_ptr(), shape, m, interp,
+                                                           _native.OOB_ZERO | fam, stream=st))
+                    except RuntimeError as e:
+                        print(f'{n}^3 {mname} {iname} {fname}: {e}')
+                        continue
+                    print(f'{n}^3 {mname} {iname} {fname}: {ms:.3f} ms  {nvox / ms / 1e6:.1f} Gvox/s  '
+                          f'({8 * nvox / ms / 1e6 / 6549.1 * 100:.1f}% roofline)')
+        if oracle.ref_gpu_available() and n <= 512:
+            for mname, m in mats.items():
+                for mode in ('linear', 'bspline', 'bspline_simple', 'filt_bspline'):
+                    _, msk, msp = oracle.transform_ref_gpu(vol, m, mode, iters=5)
+                    print(f'{n}^3 {mname} REFERENCE kernels {mode}: kernel {msk:.3f} ms '
+                          f'({nvox / msk / 1e6:.1f} Gvox/s)' + (f' prefilter {msp:.3f} ms' if msp else ''))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,123 @@
+"""ctypes binding of libvoltools_b200.so (include/voltools_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails this raises.  The library is built
+in-tree by `python voltools_b200/csrc/build.py` (or `__graft_entry__.build()`).
+"""
+import ctypes
+from pathlib import Path
+
+import numpy as np
+
+_SO = Path(__file__).resolve().parent / 'libvoltools_b200.so'
+
+LINEAR, CUBIC_TEX, CUBIC_SIMPLE = 0, 1, 2
+OOB_SKIP, OOB_ZERO = 0x0, 0x1
+WEIGHTS_TEX_RN, WEIGHTS_TEX_TRUNC, WEIGHTS_EXACT = 0x0, 0x2, 0x4
+KERNEL_AUTO, KERNEL_GATHER, KERNEL_BRICK = 0x00, 0x10, 0x20
+MAX_BATCH = 32
+
+# interpolation name -> (device function, needs prefilter)      voltools/transforms.py:11-17
+INTERPOLATIONS = {
+    'linear': (LINEAR, False),
+    'bspline': (CUBIC_TEX, False),
+    'bspline_simple': (CUBIC_SIMPLE, False),
+    'filt_bspline': (CUBIC_TEX, True),
+    'filt_bspline_simple': (CUBIC_SIMPLE, True),
+}
+
+_lib = None
+_f32p = ctypes.POINTER(ctypes.c_float)
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _SO.exists():
+            raise RuntimeError(f'{_SO} is missing: build it with `python voltools_b200/csrc/build.py` '
+                               '(there is no CPU or PyTorch fallback)')
+        L = ctypes.CDLL(str(_SO))
+        L.vt_abi_version.restype = _i
+        L.vt_error_string.restype = ctypes.c_char_p
+        L.vt_error_string.argtypes = [_i]
+        L.vt_device_count.argtypes = [ctypes.POINTER(_i)]
+        L.vt_prefilter_f32.argtypes = [_vp, _i, _i, _i, _i, _i, _vp]
+        L.vt_affine_f32.argtypes = [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i,
+                                    ctypes.c_uint, _i, _i, _i, _vp]
+        L.vt_affine_plan.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _f32p, _i, _i, ctypes.c_uint, ctypes.POINTER(_i)]
+        L.vt_host_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
+        L.vt_host_ctx_destroy.argtypes = [_vp]
+        L.vt_host_affine_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f32p, _i, _i, ctypes.c_uint]
+        L.vt_launch_count.restype = ctypes.c_longlong
+        if L.vt_abi_version() != 1:
+            raise RuntimeError('libvoltools_b200.so ABI version mismatch')
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError(f'libvoltools_b200: {lib().vt_error_string(status).decode()} (status {status})')
+
+
+def device_count():
+    n = _i(0)
+    lib().vt_device_count(ctypes.byref(n))
+    return n.value
+
+
+def launch_count():
+    return lib().vt_launch_count()
+
+
+def _mats(matrices):
+    m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
+    return m, m.ctypes.data_as(_f32p)
+
+
+def prefilter(ptr, shape, device=-1, stream=0, variant=0):
+    check(lib().vt_prefilter_f32(ptr, shape[0], shape[1], shape[2], variant, device, stream))
+
+
+def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None,
+           device=-1, stream=0):
+    m, mp = _mats(matrices)
+    if batch_stride is None:
+        batch_stride = int(dst_shape[0]) * int(dst_shape[1]) * int(dst_shape[2])
+    z0, z1 = (0, dst_shape[0]) if z_range is None else z_range
+    check(lib().vt_affine_f32(src_ptr, *map(int, src_shape), dst_ptr, *map(int, dst_shape), batch_stride, mp, len(m),
+                              interp, flags, z0, z1, device, stream))
+
+
+def affine_plan(src_ptr, src_shape, dst_shape, matrices, interp, flags=0):
+    m, mp = _mats(matrices)
+    fam = _i(0)
+    check(lib().vt_affine_plan(*map(int, src_shape), *map(int, dst_shape), src_ptr, mp, len(m), interp, flags,
+                               ctypes.byref(fam)))
+    return {1: 'gather', 2: 'brick'}[fam.value]
+
+
+class HostContext:
+    """Owner of a vt_host_ctx (pinned staging + device buffers for the numpy-in / numpy-out path)."""
+
+    def __init__(self, device=-1):
+        self._h = _vp()
+        check(lib().vt_host_ctx_create(device, ctypes.byref(self._h)))
+
+    def affine(self, src, dst, matrix, interp, prefilter, flags=0):
+        m, mp = _mats(matrix)
+        assert src.dtype == np.float32 and dst.dtype == np.float32 and src.flags.c_contiguous and dst.flags.c_contiguous
+        check(lib().vt_host_affine_f32(self._h, src.ctypes.data, *src.shape, dst.ctypes.data, *dst.shape, mp, interp,
+                                       int(prefilter), flags))
+
+    def close(self):
+        if self._h:
+            lib().vt_host_ctx_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

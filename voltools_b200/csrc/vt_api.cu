@@ -1,0 +1,270 @@
+// vt_api.cu -- the extern "C" surface of libvoltools_b200.so (see include/voltools_b200.h).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "vt_common.cuh"
+
+int vt_launch_gather(const VtResampleParams &P, int interp, cudaStream_t st);   // vt_resample_gather.cu
+int vt_launch_brick(const VtResampleParams &P, int interp, cudaStream_t st);    // vt_resample_brick.cu
+int vt_brick_supported(const VtResampleParams &P, int interp);                  // vt_resample_brick.cu
+int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter.cu
+int vt_prefilter_win(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter_win.cu
+
+static std::atomic<long long> g_launches{0};
+void vt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+// scoped device switch: unlike the reference's switch_to_device (voltools/utils/general.py:84-88) the
+// caller's current device is restored on exit.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    int status = VT_OK;
+    explicit DeviceGuard(int device)
+    {
+        if (device < 0) return;
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) { status = 1000 + (int)e; return; }
+        if (prev != device) {
+            e = cudaSetDevice(device);
+            if (e != cudaSuccess) { status = 1000 + (int)e; return; }
+            changed = true;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+int fill_params(VtResampleParams &P, const float *d_src, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
+                long long dst_batch_stride, unsigned flags, int z_begin, int z_end)
+{
+    if (!d_src || !d_dst) return VT_ERR_INVALID_ARG;
+    if (s0 < 1 || s1 < 1 || s2 < 1 || o0 < 1 || o1 < 1 || o2 < 1) return VT_ERR_INVALID_ARG;
+    if (z_begin < 0 || z_end > o0 || z_begin > z_end) return VT_ERR_INVALID_ARG;
+    // the reference indexes voxels with 32-bit integers (transforms.py:258-264); so do the kernels' planes
+    if ((long long)s1 * s2 > 0x7fffffffLL || (long long)o1 * o2 > 0x7fffffffLL) return VT_ERR_UNSUPPORTED;
+    P.src = d_src;
+    P.dst = d_dst;
+    P.s0 = s0; P.s1 = s1; P.s2 = s2;
+    P.o0 = o0; P.o1 = o1; P.o2 = o2;
+    P.dst_batch_stride = dst_batch_stride;
+    P.z_begin = z_begin;
+    P.z_end = z_end;
+    P.flags = flags;
+    return VT_OK;
+}
+
+void copy_mats(VtResampleParams &P, const float *h_mats, int first, int count)
+{
+    P.n_mats = count;
+    for (int k = 0; k < count; k++)
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) P.mats[k].r[r][c] = h_mats[(size_t)(first + k) * 16 + r * 4 + c];
+}
+
+int choose_family(const VtResampleParams &P, int interp, unsigned flags)
+{
+    const unsigned forced = flags & 0xf0u;
+    if (forced == VT_KERNEL_GATHER) return 1;
+    const int ok = vt_brick_supported(P, interp);
+    if (forced == VT_KERNEL_BRICK) return ok ? 2 : -1;
+    return ok ? 2 : 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vt_abi_version(void) { return VT_ABI_VERSION; }
+
+const char *vt_error_string(int status)
+{
+    static thread_local char buf[256];
+    switch (status) {
+        case VT_OK: return "ok";
+        case VT_ERR_INVALID_ARG: return "invalid argument";
+        case VT_ERR_UNSUPPORTED: return "unsupported shape or configuration";
+        case VT_ERR_NO_DEVICE: return "no CUDA device";
+        case VT_ERR_ALLOC: return "allocation failed";
+    }
+    if (status >= 2000) {
+        snprintf(buf, sizeof buf, "CUDA driver error %d", status - 2000);
+        return buf;
+    }
+    if (status >= 1000) {
+        snprintf(buf, sizeof buf, "CUDA error %d: %s", status - 1000, cudaGetErrorString((cudaError_t)(status - 1000)));
+        return buf;
+    }
+    return "unknown status";
+}
+
+int vt_device_count(int *count)
+{
+    if (!count) return VT_ERR_INVALID_ARG;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return VT_ERR_NO_DEVICE;
+    }
+    return VT_OK;
+}
+
+long long vt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vt_prefilter_f32(float *d_vol, int d0, int d1, int d2, int variant, int device, void *stream)
+{
+    if (!d_vol || d0 < 1 || d1 < 1 || d2 < 1) return VT_ERR_INVALID_ARG;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (variant) {
+        case 0: return vt_prefilter_win(d_vol, d0, d1, d2, st);
+        case 1: return vt_prefilter_seq(d_vol, d0, d1, d2, st);
+        case 2: return vt_prefilter_win(d_vol, d0, d1, d2, st);
+    }
+    return VT_ERR_INVALID_ARG;
+}
+
+int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d_src, const float *h_mats, int n_mats,
+                   int interp, unsigned flags, int *family)
+{
+    if (!family || !h_mats || n_mats < 1) return VT_ERR_INVALID_ARG;
+    VtResampleParams P;
+    float dummy;
+    int rc = fill_params(P, (const float *)d_src, s0, s1, s2, &dummy, o0, o1, o2, 0, flags, 0, o0);
+    if (rc) return rc;
+    copy_mats(P, h_mats, 0, n_mats < VT_MAX_BATCH ? n_mats : VT_MAX_BATCH);
+    const int f = choose_family(P, interp, flags);
+    if (f < 0) return VT_ERR_UNSUPPORTED;
+    *family = f;
+    return VT_OK;
+}
+
+int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
+                  long long dst_batch_stride, const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin,
+                  int z_end, int device, void *stream)
+{
+    if (!h_mats || n_mats < 0) return VT_ERR_INVALID_ARG;
+    if (interp != VT_LINEAR && interp != VT_CUBIC_TEX && interp != VT_CUBIC_SIMPLE) return VT_ERR_INVALID_ARG;
+    if (n_mats == 0) return VT_OK;
+    VtResampleParams P;
+    int rc = fill_params(P, d_src, s0, s1, s2, d_dst, o0, o1, o2, dst_batch_stride, flags, z_begin, z_end);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int first = 0; first < n_mats; first += VT_MAX_BATCH) {
+        const int count = (n_mats - first) < VT_MAX_BATCH ? (n_mats - first) : VT_MAX_BATCH;
+        copy_mats(P, h_mats, first, count);
+        P.dst = d_dst + (size_t)first * dst_batch_stride;
+        const int family = choose_family(P, interp, flags);
+        if (family < 0) return VT_ERR_UNSUPPORTED;
+        rc = (family == 2) ? vt_launch_brick(P, interp, st) : vt_launch_gather(P, interp, st);
+        if (rc) return rc;
+    }
+    return VT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer path
+// ---------------------------------------------------------------------------------------------------
+struct vt_host_ctx {
+    int device;
+    cudaStream_t st_in, st_k, st_out;
+    float *d_src, *d_dst;
+    size_t cap_src, cap_dst;
+    cudaEvent_t ev_in, ev_k;
+};
+
+int vt_host_ctx_create(int device, vt_host_ctx **out)
+{
+    if (!out) return VT_ERR_INVALID_ARG;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    vt_host_ctx *c = new (std::nothrow) vt_host_ctx();
+    if (!c) return VT_ERR_ALLOC;
+    memset(c, 0, sizeof *c);
+    if (device < 0) VT_CUDA(cudaGetDevice(&device));
+    c->device = device;
+    VT_CUDA(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+    VT_CUDA(cudaStreamCreateWithFlags(&c->st_k, cudaStreamNonBlocking));
+    VT_CUDA(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
+    VT_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+    VT_CUDA(cudaEventCreateWithFlags(&c->ev_k, cudaEventDisableTiming));
+    *out = c;
+    return VT_OK;
+}
+
+int vt_host_ctx_destroy(vt_host_ctx *c)
+{
+    if (!c) return VT_OK;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->st_in);
+    cudaStreamSynchronize(c->st_k);
+    cudaStreamSynchronize(c->st_out);
+    cudaFree(c->d_src);
+    cudaFree(c->d_dst);
+    cudaEventDestroy(c->ev_in);
+    cudaEventDestroy(c->ev_k);
+    cudaStreamDestroy(c->st_in);
+    cudaStreamDestroy(c->st_k);
+    cudaStreamDestroy(c->st_out);
+    delete c;
+    return VT_OK;
+}
+
+static int ensure(float **p, size_t *cap, size_t bytes)
+{
+    if (*cap >= bytes) return VT_OK;
+    if (*p) VT_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    VT_CUDA(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return VT_OK;
+}
+
+int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s2, float *h_dst, int o0, int o1, int o2,
+                       const float *h_m16, int interp, int prefilter, unsigned flags)
+{
+    if (!c || !h_src || !h_dst || !h_m16) return VT_ERR_INVALID_ARG;
+    if (s0 < 1 || s1 < 1 || s2 < 1 || o0 < 1 || o1 < 1 || o2 < 1) return VT_ERR_INVALID_ARG;
+    DeviceGuard g(c->device);
+    if (g.status) return g.status;
+    const size_t nsrc = (size_t)s0 * s1 * s2, plane_out = (size_t)o1 * o2;
+    int rc = ensure(&c->d_src, &c->cap_src, nsrc * 4);
+    if (rc) return rc;
+    rc = ensure(&c->d_dst, &c->cap_dst, (size_t)o0 * plane_out * 4);
+    if (rc) return rc;
+    // upload (the source is needed whole before any output plane can be gathered under a general affine map)
+    VT_CUDA(cudaMemcpyAsync(c->d_src, h_src, nsrc * 4, cudaMemcpyHostToDevice, c->st_k));
+    if (prefilter) {
+        rc = vt_prefilter_f32(c->d_src, s0, s1, s2, 0, -1, c->st_k);
+        if (rc) return rc;
+    }
+    // output=None semantics (transforms.py:207-210): skipped voxels are zero -> fused as VT_OOB_ZERO.
+    // z-slabs: the kernel of slab i+1 overlaps the download of slab i.
+    const unsigned fl = (flags & ~1u) | VT_OOB_ZERO;
+    int nslab = o0 >= 8 ? 8 : 1;
+    for (int sl = 0; sl < nslab; sl++) {
+        const int z0 = (int)((long long)o0 * sl / nslab), z1 = (int)((long long)o0 * (sl + 1) / nslab);
+        if (z1 <= z0) continue;
+        rc = vt_affine_f32(c->d_src, s0, s1, s2, c->d_dst, o0, o1, o2, 0, h_m16, 1, interp, fl, z0, z1, -1, c->st_k);
+        if (rc) return rc;
+        VT_CUDA(cudaEventRecord(c->ev_k, c->st_k));
+        VT_CUDA(cudaStreamWaitEvent(c->st_out, c->ev_k, 0));
+        VT_CUDA(cudaMemcpyAsync(h_dst + (size_t)z0 * plane_out, c->d_dst + (size_t)z0 * plane_out,
+                                (size_t)(z1 - z0) * plane_out * 4, cudaMemcpyDeviceToHost, c->st_out));
+    }
+    VT_CUDA(cudaStreamSynchronize(c->st_out));
+    VT_CUDA(cudaStreamSynchronize(c->st_k));
+    return VT_OK;
+}
+
+}  // extern "C"

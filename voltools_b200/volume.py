@@ -1,0 +1,165 @@
+"""StaticVolume: a volume kept resident on the GPU and resampled many times.
+
+Mirror of voltools/volume.py:13-165.  What differs underneath:
+  * the resident object is the (optionally prefiltered) coefficient volume in linear HBM -- no CUDA array /
+    texture object (volume.py:36-50): the kernels gather from the linear buffer directly;
+  * the matrix travels in kernel parameters (no per-call 64-byte H2D copy, volume.py:70);
+  * `affine_many` / `transform_many` push a whole batch of matrices through one launch per VT_MAX_BATCH
+    matrices (the reference launches once per matrix);
+  * with output=None the zero-fill (volume.py:73) is fused into the kernel.
+"""
+from typing import Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _native
+from .transforms import _INTERPOLATIONS, _device_view, _is_host, _resolve_device, _stream, _torch
+from .utils import get_available_devices, scale_matrix, shear_matrix, rotation_matrix, translation_matrix, \
+    transform_matrix
+
+
+class StaticVolume:
+    """
+    For StaticVolume transforms the boolean reshape cannot be given as an argument.
+    """
+
+    def __init__(self, data, interpolation: str = 'linear', device: str = 'gpu'):
+        if len(data.shape) != 3:
+            raise ValueError('Expected a 3D array')
+        devices = get_available_devices()
+        if device not in devices:
+            raise ValueError(f'Unknown device ({device}), must be one of {devices}')
+        if interpolation not in _INTERPOLATIONS:
+            raise ValueError(f'Interpolation must be one of {list(_INTERPOLATIONS.keys())}')
+        torch = _torch()
+        self.device = device
+        self.interpolation = interpolation
+        self._interp, needs_prefilter = _INTERPOLATIONS[interpolation]
+        vin = None if _is_host(data) else _device_view(data, 'data')
+        self._dev = _resolve_device(device, vin)
+        self.shape = tuple(int(s) for s in data.shape)
+        self.d_type = np.float32
+        # always a private copy (volume.py:30 `cp.array(data)` copies too)
+        with torch.cuda.device(self._dev):
+            if vin is None:
+                host = np.ascontiguousarray(data, dtype=np.float32)
+                self._coeffs = torch.from_numpy(host).to(f'cuda:{self._dev}')
+            else:
+                src = vin.owner if isinstance(vin.owner, torch.Tensor) \
+                    else torch.as_tensor(vin.owner, device=f'cuda:{self._dev}')
+                self._coeffs = src.to(f'cuda:{self._dev}', copy=True)
+            if needs_prefilter:
+                _native.prefilter(self._coeffs.data_ptr(), self.shape, self._dev, _stream(self._dev))
+
+    # -- resident buffer access (used by the multi-GPU layer) -------------------------------------------
+    @property
+    def coefficients(self):
+        """The resident (prefiltered, for filt_* modes) volume as a torch CUDA tensor."""
+        return self._coeffs
+
+    @classmethod
+    def from_coefficients(cls, coeffs, interpolation: str = 'linear'):
+        """Wrap an already prepared coefficient tensor (e.g. one received by NCCL broadcast) without copying."""
+        self = cls.__new__(cls)
+        self.device = f'gpu:{coeffs.device.index}'
+        self.interpolation = interpolation
+        self._interp, _ = _INTERPOLATIONS[interpolation]
+        self._dev = coeffs.device.index
+        self.shape = tuple(int(s) for s in coeffs.shape)
+        self.d_type = np.float32
+        self._coeffs = coeffs
+        return self
+
+    # -- transforms ---------------------------------------------------------------------------------------
+    def affine(self, transform_m: np.ndarray, profile: bool = False, output=None) -> Union[np.ndarray, None]:
+        """volume.py:61-101."""
+        torch = _torch()
+        m = np.ascontiguousarray(transform_m, dtype=np.float32).reshape(4, 4)
+        vout = None if output is None else _device_view(output, 'output')
+        if vout is not None and vout.shape != self.shape:
+            raise ValueError(f'output shape {vout.shape} does not match the volume shape {self.shape}')
+        with torch.cuda.device(self._dev):
+            if profile:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+            stream = _stream(self._dev)
+            if vout is None:
+                out_t = torch.empty(self.shape, dtype=torch.float32, device=f'cuda:{self._dev}')
+                _native.affine(self._coeffs.data_ptr(), self.shape, out_t.data_ptr(), self.shape, m, self._interp,
+                               _native.OOB_ZERO, device=self._dev, stream=stream)
+            else:
+                _native.affine(self._coeffs.data_ptr(), self.shape, vout.ptr, self.shape, m, self._interp,
+                               _native.OOB_SKIP, device=self._dev, stream=stream)
+            if profile:
+                t1.record()
+                t1.synchronize()
+                print(f'transform finished in {t0.elapsed_time(t1):.3f}ms')
+            return out_t.cpu().numpy() if vout is None else None
+
+    def affine_many(self, matrices: Sequence[np.ndarray], output=None, zero_fill: bool = None):
+        """Batched `affine`: K matrices -> K volumes, one launch per VT_MAX_BATCH matrices.
+
+        output: None -> returns a new torch CUDA tensor of shape (K, *shape), zero where out of bounds;
+                a (K, *shape) device array -> written in place (out-of-bounds voxels untouched unless
+                zero_fill=True), returns None.
+        """
+        torch = _torch()
+        m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
+        k = len(m)
+        with torch.cuda.device(self._dev):
+            stream = _stream(self._dev)
+            if output is None:
+                out_t = torch.empty((k,) + self.shape, dtype=torch.float32, device=f'cuda:{self._dev}')
+                ptr, flags = out_t.data_ptr(), _native.OOB_ZERO
+            else:
+                vout = _device_view(output, 'output')
+                if vout.shape != (k,) + self.shape:
+                    raise ValueError(f'output shape {vout.shape} does not match {(k,) + self.shape}')
+                out_t, ptr = None, vout.ptr
+                flags = _native.OOB_ZERO if zero_fill else _native.OOB_SKIP
+            _native.affine(self._coeffs.data_ptr(), self.shape, ptr, self.shape, m, self._interp, flags,
+                           device=self._dev, stream=stream)
+        return out_t
+
+    def transform(self, scale: Union[float, Tuple[float, float, float], np.ndarray] = None,
+                  shear: Union[float, Tuple[float, float, float], np.ndarray] = None,
+                  rotation: Union[Tuple[float, float, float], np.ndarray] = None,
+                  rotation_units: str = 'deg', rotation_order: str = 'rzxz',
+                  translation: Union[Tuple[float, float, float], np.ndarray] = None,
+                  center: Union[Tuple[float, float, float], np.ndarray] = None,
+                  profile: bool = False,
+                  output=None) -> Union[np.ndarray, None]:
+        """volume.py:103-123."""
+        if center is None:
+            center = np.divide(np.subtract(self.shape, 1), 2, dtype=np.float32)
+        if isinstance(scale, float):
+            scale = (scale, scale, scale)
+        if isinstance(shear, float):
+            shear = (shear, shear, shear)
+        m = transform_matrix(scale, shear, rotation, rotation_units, rotation_order, translation, center)
+        return self.affine(m, profile, output)
+
+    def translate(self, translation: Tuple[float, float, float], profile: bool = False,
+                  output=None) -> Union[np.ndarray, None]:
+        """volume.py:125-131."""
+        return self.affine(translation_matrix(translation), profile, output)
+
+    def shear(self, coefficients: Union[float, Tuple[float, float, float]], profile: bool = False,
+              output=None) -> Union[np.ndarray, None]:
+        """volume.py:133-143."""
+        if isinstance(coefficients, float):
+            coefficients = (coefficients, coefficients, coefficients)
+        return self.affine(shear_matrix(coefficients), profile, output)
+
+    def scale(self, coefficients: Union[float, Tuple[float, float, float]], profile: bool = False,
+              output=None) -> Union[np.ndarray, None]:
+        """volume.py:145-155."""
+        if isinstance(coefficients, float):
+            coefficients = (coefficients, coefficients, coefficients)
+        return self.affine(scale_matrix(coefficients), profile, output)
+
+    def rotate(self, rotation: Tuple[float, float, float], rotation_units: str = 'deg', rotation_order: str = 'rzxz',
+               profile: bool = False, output=None) -> Union[np.ndarray, None]:
+        """volume.py:157-165 (about the array origin, like the reference)."""
+        m = rotation_matrix(rotation=rotation, rotation_units=rotation_units, rotation_order=rotation_order)
+        return self.affine(m, profile, output)
