@@ -1,0 +1,130 @@
+"""CPU suite: host-side logic (matrix builders, shape helpers, API surface) and the C-ABI library's exports."""
+import ctypes
+import re
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _utils():
+    import voltools_b200.utils as u
+    return u
+
+
+# golden host matrices generated from the reference
+G1 = np.array([[0.7712806, 0.6337184, 0.059391174, 0], [-0.613092, 0.71461016, 0.3368241, 0],
+               [0.17101008, -0.29619813, 0.9396926, 0], [0, 0, 0, 1]], np.float32)
+G2 = np.array([[0.81379765, 0.54383814, -0.20487413, 0], [-0.4698463, 0.8231729, 0.31879577, 0],
+               [0.34202015, -0.16317591, 0.9254166, 0], [0, 0, 0, 1]], np.float32)
+G6 = np.array([[1.3950913e-01, 8.3980620e-01, 3.8669834e-01, -9.9016479e+01],
+               [-8.5836309e-01, -1.4925867e-01, 6.6490811e-01, 3.4631332e+02],
+               [6.7360973e-01, -2.9064128e-01, 7.1574771e-01, -2.7221985e+01], [0, 0, 0, 1]], np.float32)
+
+
+def test_golden_matrices():
+    u = _utils()
+    np.testing.assert_allclose(u.rotation_matrix((10, 20, 30), 'deg', 'rzxz'), G1, atol=1e-6)
+    np.testing.assert_allclose(u.rotation_matrix((10, 20, 30), 'deg', 'sxyz'), G2, atol=1e-6)
+    t = u.translation_matrix((1, 2, 3))
+    assert np.array_equal(t[:3, 3], [-1, -2, -3]) and np.array_equal(t[:3, :3], np.identity(3))
+    s = u.shear_matrix((0.1, 0.2, 0.3))
+    assert s[0, 1] == np.float32(0.1) and s[0, 2] == np.float32(0.2) and s[1, 2] == np.float32(0.3)
+    assert np.array_equal(np.diag(u.scale_matrix((2, 3, 4))), [2, 3, 4, 1])
+    g6 = u.transform_matrix(scale=(1.1, 0.9, 1.05), shear=(0.05, -0.03, 0.02), rotation=(30, 45, 60),
+                            rotation_order='rzxz', translation=(5.5, -3.25, 2.0), center=(255.5,) * 3)
+    np.testing.assert_allclose(g6, G6, rtol=1e-6, atol=1e-5)
+    g7 = u.transform_matrix(rotation=(0, 45, 0), rotation_order='rzxz', center=(49.5,) * 3)
+    np.testing.assert_allclose(g7, [[1, 0, 0, 0], [0, 0.70710677, 0.70710677, -20.50357],
+                                    [0, -0.70710677, 0.70710677, 49.5], [0, 0, 0, 1]], atol=1e-5)
+    assert g7.dtype == np.float32
+    pb, pa, nd = u.compute_post_transform_dimensions((100,) * 3, g7)
+    assert tuple(pb) == (0, 21, 21) and tuple(pa) == (0, 20, 21) and tuple(nd) == (100, 141, 142)
+
+
+def test_matrices_vs_imported_reference():
+    """Every builder against the unmodified reference package, where it can be imported."""
+    path = oracle.ref_python_path()
+    if path is None:
+        pytest.skip('reference python package not staged')
+    saved = list(sys.path)
+    sys.path.insert(0, path)
+    try:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            import voltools.utils as ru
+    finally:
+        sys.path[:] = saved
+    u = _utils()
+    assert sorted(u.AVAILABLE_ROTATIONS) == sorted(ru.AVAILABLE_ROTATIONS)
+    assert u.AVAILABLE_UNITS == ru.AVAILABLE_UNITS
+    rng = np.random.default_rng(0)
+    for order in ru.AVAILABLE_ROTATIONS:
+        for units in ('deg', 'rad'):
+            ang = rng.uniform(-180, 180, 3) if units == 'deg' else rng.uniform(-np.pi, np.pi, 3)
+            np.testing.assert_allclose(u.rotation_matrix(ang, units, order), ru.rotation_matrix(ang, units, order),
+                                       atol=1e-6)
+            kw = dict(scale=rng.uniform(0.5, 2, 3), shear=rng.uniform(-0.2, 0.2, 3), rotation=ang,
+                      rotation_units=units, rotation_order=order, translation=rng.uniform(-9, 9, 3),
+                      center=rng.uniform(0, 200, 3))
+            a, b = u.transform_matrix(**kw), ru.transform_matrix(**kw)
+            assert a.dtype == b.dtype == np.float32
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-4)
+    for shape in ((100, 100, 100), (30, 50, 70)):
+        for _ in range(10):
+            m = ru.transform_matrix(rotation=rng.uniform(-180, 180, 3), scale=rng.uniform(0.7, 1.5, 3),
+                                    center=np.divide(shape, 2))
+            for x, y in zip(u.compute_post_transform_dimensions(shape, m),
+                            ru.compute_post_transform_dimensions(shape, m)):
+                assert np.array_equal(x, y)
+
+
+def test_api_surface():
+    import voltools_b200 as vt
+    for name in ('transform', 'affine', 'rotate', 'scale', 'shear', 'translate', 'StaticVolume',
+                 'AVAILABLE_INTERPOLATIONS', 'AVAILABLE_DEVICES', 'utils'):
+        assert hasattr(vt, name), name
+    assert vt.AVAILABLE_INTERPOLATIONS == ['linear', 'bspline', 'bspline_simple', 'filt_bspline',
+                                           'filt_bspline_simple']
+    for name in ('transform_matrix', 'rotation_matrix', 'translation_matrix', 'shear_matrix', 'scale_matrix',
+                 'AVAILABLE_ROTATIONS', 'AVAILABLE_UNITS', 'get_available_devices', 'switch_to_device',
+                 'compute_post_transform_dimensions'):
+        assert hasattr(vt.utils, name), name
+    assert 'cpu' not in vt.AVAILABLE_DEVICES  # no CPU fallback in the product
+    with pytest.raises(ValueError):
+        vt.affine(np.zeros((4, 4, 4), np.float32), np.identity(4), device='cpu')
+    with pytest.raises(ValueError):
+        vt.utils.rotation_matrix((1, 2, 3), rotation_order='zxz')
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads and exports everything include/voltools_b200.h declares (no compute calls)."""
+    header = (ROOT / 'include' / 'voltools_b200.h').read_text()
+    declared = set(re.findall(r'\b(vt_[a-z0-9_]+)\s*\(', header))
+    declared -= {'vt_host_ctx'}
+    assert {'vt_prefilter_f32', 'vt_affine_f32', 'vt_host_affine_f32', 'vt_error_string'} <= declared
+    so = ROOT / 'voltools_b200' / 'libvoltools_b200.so'
+    assert so.exists(), 'run python voltools_b200/csrc/build.py (or __graft_entry__.build())'
+    lib = ctypes.CDLL(str(so))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    lib.vt_abi_version.restype = ctypes.c_int
+    assert lib.vt_abi_version() == 1
+    lib.vt_error_string.restype = ctypes.c_char_p
+    assert lib.vt_error_string(0) == b'ok'
+    assert lib.vt_error_string(2) != b'ok'
+
+
+def test_product_does_not_touch_the_oracle():
+    """No file of the product package may import/link/execute anything under oracle/."""
+    for p in (ROOT / 'voltools_b200').rglob('*'):
+        if p.suffix in ('.py', '.cu', '.cuh', '.h', '.cpp'):
+            text = p.read_text()
+            assert 'import oracle' not in text and 'from oracle' not in text and 'vt_oracle' not in text, p
+            assert 'import scipy' not in text and 'from scipy' not in text, f'{p}: CPU fallback dependency'
