@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- Gvoxels/s of the affine volume-resampling hot path on N B200s (one JSON line on stdout).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workloads (BASELINE.json `configs`, inputs per SURVEY.md section 8d):
+  cfg1    (default) configs[1]: transform() of 250^3 float32 volumes, interpolation='filt_bspline' (prefilter +
+          8-fetch cubic), rotation=(0,45,0) 'rzxz' about the centre.  One step = one pass over a batch of 8
+          independent volumes (500 MB in + 500 MB out, larger than the 126 MB L2), each through the public
+          voltools_b200.transform(...).  N > 1: every rank owns its own batch (independent objects, no
+          collective) -> weak scaling.
+  affine512  configs[3]: 512^3 bspline_simple, full affine G6, output= device array.
+  sweep   configs[2]: StaticVolume 256^3 filt_bspline, 180-angle sweep; rank 0 prefilters, one NCCL broadcast of
+          the coefficient volume, the angles are split across ranks (strong scaling).
+  modes   all five interpolation modes at 512^3 (rot45 and full affine) -> reported under "modes" (1 GPU).
+
+`value` is device-resident throughput (inputs already in HBM, CUDA events); `e2e` is the same batch through the
+same public call with pinned HOST arrays in and out (H2D + kernels + D2H inside the timed region).
+`roofline` is for the kernel with the largest share of the step, from per-launch CUDA events recorded by the
+library (vt_profile_*), against MEASURED_PEAKS.json.  `cpu_baseline` times the unmodified reference package's
+CPU path (voltools.transform(device='cpu') -> scipy.ndimage.affine_transform), staged under oracle/_ref/py, on
+this host.  `--impl reference` runs that CPU path alone as the reference arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = 'Gvoxels/s'
+ROT45 = dict(rotation=(0, 45, 0), rotation_order='rzxz')
+FULL_AFFINE = dict(scale=(1.1, 0.9, 1.05), shear=(0.05, -0.03, 0.02), rotation=(30, 45, 60), rotation_order='rzxz',
+                   translation=(5.5, -3.25, 2.0))
+CFG1 = dict(n=250, batch=8, interpolation='filt_bspline', kw=ROT45,
+            name="configs[1]: transform() 250^3 float32 interpolation='filt_bspline' rotation=(0,45,0) rzxz; "
+                 "step = batch of 8 independent volumes")
+
+
+def peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        return float(json.loads(p.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def dist_env():
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, uuid):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', uuid, f'--query-gpu={self.Q}',
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(',') for r in Path(self.f.name).read_text().strip().splitlines() if r.count(',') >= 6]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.strip().lower().startswith('active'):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference CPU path (the unmodified reference package, staged by oracle/build_ref.py under oracle/_ref/py)
+# ------------------------------------------------------------------------------------------------------------
+def _ref_voltools():
+    import contextlib
+    import io
+    import oracle
+    path = oracle.ref_python_path()
+    if path is None:
+        return None
+    sys.path.insert(0, path)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints a cupy-missing warning on import
+            import voltools as ref_vt
+    finally:
+        sys.path.remove(path)
+    return ref_vt
+
+
+def _ref_worker(job):
+    seed, shape, interpolation, kw = job
+    ref_vt = _ref_voltools()
+    vol = np.random.default_rng(seed).random(shape, dtype=np.float32)
+    t0 = time.perf_counter()
+    out = ref_vt.transform(vol, interpolation=interpolation, device='cpu', **kw)
+    dt = time.perf_counter() - t0
+    return dt, float(out[shape[0] // 2, shape[1] // 2, shape[2] // 2])
+
+
+def cpu_baseline_leg(cfg):
+    """Reference CPU path on ONE full volume of the workload, one core (scipy.ndimage is single-threaded)."""
+    ref_vt = _ref_voltools()
+    if ref_vt is None:
+        return {'value': None, 'unit': METRIC, 'cores': 0, 'kind': 'reference', 'sample': 'reference package not staged'}
+    n = cfg['n']
+    dt, _ = _ref_worker((0, (n, n, n), cfg['interpolation'], cfg['kw']))
+    out = {'value': n ** 3 / dt / 1e9, 'unit': METRIC, 'cores': 1, 'kind': 'reference',
+           'sample': f"1 of the step's {cfg['batch']} volumes ({n}^3) through the unmodified reference "
+                     f"voltools.transform(device='cpu') = scipy.ndimage.affine_transform(order=3, prefilter=True); "
+                     f'{dt:.2f} s on 1 of {os.cpu_count()} host cores'}
+    # scipy.ndimage.affine_transform directly (tests/benchmark.py:60), order 1 and 3, 100^3 (BASELINE configs[0] shape)
+    try:
+        from scipy import ndimage
+        from voltools_b200.utils import transform_matrix
+        v = np.random.default_rng(0).random((100, 100, 100), dtype=np.float32)
+        m = transform_matrix(center=(49.5, 49.5, 49.5), **ROT45)
+        extra = {}
+        for order in (1, 3):
+            t0 = time.perf_counter()
+            ndimage.affine_transform(v, m, order=order)
+            extra[f'scipy_affine_transform_order{order}_100^3_gvox_s'] = 1e6 / (time.perf_counter() - t0) / 1e9
+        t0 = time.perf_counter()
+        ref_vt.transform(v, interpolation='linear', device='cpu', **ROT45)
+        extra['reference_cpu_linear_100^3_gvox_s (BASELINE configs[0])'] = 1e6 / (time.perf_counter() - t0) / 1e9
+        out['extra'] = extra
+    except Exception as e:  # informational only
+        out['extra'] = {'error': repr(e)}
+    return out
+
+
+def reference_arm(args, cfg):
+    """--impl reference: the reference's own CPU implementation, all the host parallelism it can use (one process
+    per independent volume of the batch; each call is single-threaded inside SciPy)."""
+    import multiprocessing as mp
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    if _ref_voltools() is None:
+        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref/py (reference package) not staged'}))
+        return
+    n = cfg['n']
+    procs = max(1, min(os.cpu_count() or 1, cfg['batch']))
+    # bounded sample: a z-slab of `planes` planes of each volume (in-plane rotation about axis 0: every output
+    # plane costs the same), sized so that (steps + warmup) steps fit in ~150 s
+    t_probe, _ = _ref_worker((0, (16, n, n), cfg['interpolation'], cfg['kw']))
+    per_plane = t_probe / 16
+    budget = 150.0 / (args.steps + args.warmup)
+    planes = int(max(8, min(n, budget / per_plane)))
+    shape = (planes, n, n)
+    jobs = [(1000 + i, shape, cfg['interpolation'], cfg['kw']) for i in range(procs)]
+    with mp.get_context('fork').Pool(procs) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_worker, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_worker, jobs)
+        dt = time.perf_counter() - t0
+    vox = procs * planes * n * n * args.steps
+    value = vox / dt / 1e9
+    sample = (f'{procs} processes x one {planes}x{n}x{n} z-slab of a {n}^3 volume per step, unmodified reference '
+              f"voltools.transform(interpolation='{cfg['interpolation']}', device='cpu')")
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['name'], 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': METRIC, 'cores': procs, 'kind': 'reference', 'sample': sample},
+        'e2e': {'value': value, 'unit': METRIC, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def timed(torch, fn, steps, warmup, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / 1e3
+
+
+def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
+    from voltools_b200 import _native
+    n, batch, interp, kw = cfg['n'], cfg['batch'], cfg['interpolation'], cfg['kw']
+    shape = (n, n, n)
+    device = f'gpu:{dev}'
+    rank, _, world = dist_env()
+    gen = torch.Generator(device=f'cuda:{dev}').manual_seed(1234 + rank)
+    vols = [torch.rand(shape, generator=gen, device=f'cuda:{dev}', dtype=torch.float32) for _ in range(batch)]
+    outs = [torch.zeros(shape, device=f'cuda:{dev}', dtype=torch.float32) for _ in range(batch)]
+
+    def step():
+        for v, o in zip(vols, outs):
+            vt.transform(v, interpolation=interp, output=o, device=device, **kw)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    uuid = str(getattr(torch.cuda.get_device_properties(dev), 'uuid', dev))
+    clocks = ClockSampler(uuid if uuid.startswith('GPU-') or uuid.isdigit() else 'GPU-' + uuid)
+    l0 = _native.launch_count()
+    sec = timed(torch, step, args.steps, 0, barrier)
+    launches = _native.launch_count() - l0
+    clk = clocks.stop()
+    sec = reduce_max(sec)
+    vox_step = batch * n ** 3
+    value = world * vox_step * args.steps / sec / 1e9
+
+    # per-kernel durations over the same K steps (CUDA events inside the library, on the launch stream)
+    _native.profile_enable(True)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    prof = _native.profile_read()
+    _native.profile_enable(False)
+    peak, peak_src = peaks()
+    kernels = {}
+    total_ms = sum(ms for ms, _ in prof.values()) or 1.0
+    for name, (ms, cnt) in prof.items():
+        avg = ms / cnt
+        ach = 8.0 * n ** 3 / (avg * 1e-3) / 1e9
+        kernels[name] = {'launches_per_step': cnt / args.steps, 'avg_ms': avg, 'share': ms / total_ms,
+                         'achieved_gbs': ach, 'frac': ach / peak}
+    dom = max(prof, key=lambda k: prof[k][0]) if prof else None
+    traffic = None
+    tfile = ROOT / 'profiles' / 'traffic.json'
+    if dom and tfile.exists():
+        traffic = json.loads(tfile.read_text()).get(dom, {}).get('dram_bytes_per_launch')
+    roofline = None
+    if dom:
+        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom]['achieved_gbs'], 'peak': peak,
+                    'unit': 'GB/s', 'frac': kernels[dom]['frac'], 'traffic': traffic, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': 8 * n ** 3,
+                    'step_frac': 16.0 * vox_step * args.steps / sec / 1e9 / peak,
+                    'note': 'achieved = 8 B/voxel x 250^3 voxels / average launch duration; step_frac = 16 B/voxel '
+                            '(prefilter 8 + resample 8) x voxels per step / step time / peak',
+                    'kernels': kernels}
+
+    # end to end: pinned host arrays in and out through the same public call
+    h_vols = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(batch)]
+    h_outs = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(batch)]
+    for h, v in zip(h_vols, vols):
+        h.copy_(v)
+    np_vols, np_outs = [h.numpy() for h in h_vols], [h.numpy() for h in h_outs]
+
+    def step_e2e():
+        for v, o in zip(np_vols, np_outs):
+            vt.transform(v, interpolation=interp, output=o, device=device, **kw)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_sec = reduce_max(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * vox_step * e2e_steps / e2e_sec / 1e9
+    # the host path must agree with the device path
+    err = float((torch.from_numpy(np_outs[0]).to(f'cuda:{dev}') - outs[0]).abs().max())
+    assert err <= 1e-5 * 16, f'host path differs from device path: {err}'
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+        'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['name'], 'voxels_per_step_per_gpu': vox_step, 'parallelism': f'dp{world}',
+                   'l2': 'inputs larger than L2: 8 distinct volumes per step (500 MB in + 500 MB out per GPU)',
+                   'call': "voltools_b200.transform(vol, rotation=(0,45,0), rotation_order='rzxz', "
+                           "interpolation='filt_bspline', output=out, device='gpu:X')"},
+        'clocks': {'sm_mhz': clk['sm_mhz'], 'sm_max_mhz': clk['sm_max_mhz'], 'reasons': clk['reasons'],
+                   'samples': clk['samples']},
+        'e2e': {'value': e2e_value, 'unit': METRIC, 'h2d_bytes_per_step': vox_step * 4, 'd2h_bytes_per_step': vox_step * 4,
+                'steps': e2e_steps, 'ms_per_step': e2e_sec / e2e_steps * 1e3,
+                'call': 'same call with pinned numpy arrays for volume and output'},
+        'gpu_launches': int(launches),
+        'roofline': roofline,
+    }
+    return line
+
+
+def run_modes(args, torch, vt, dev):
+    """All five modes at 512^3 (north-star target shape): kernel-only Gvox/s, rot45 and full affine."""
+    from voltools_b200 import _native
+    n = args.size
+    shape = (n, n, n)
+    peak, _ = peaks()
+    c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+    mats = {'rot45': vt.utils.transform_matrix(center=c, **ROT45),
+            'full_affine': vt.utils.transform_matrix(center=c, **FULL_AFFINE)}
+    src = torch.rand(shape, device=f'cuda:{dev}')
+    dst = torch.zeros(shape, device=f'cuda:{dev}')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f'cuda:{dev}')
+    res = {}
+    for mode in vt.AVAILABLE_INTERPOLATIONS:
+        for mname, m in mats.items():
+            ts = []
+            for it in range(args.warmup + args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                vt.affine(src, m, interpolation=mode, output=dst, device=f'gpu:{dev}')
+                e1.record()
+                e1.synchronize()
+                if it >= args.warmup:
+                    ts.append(e0.elapsed_time(e1))
+            ms = statistics.median(ts)
+            bytes_per_vox = 16 if mode.startswith('filt') else 8
+            res[f'{mode}/{mname}'] = {'ms': ms, 'gvox_s': n ** 3 / ms / 1e6,
+                                      'roofline_frac': bytes_per_vox * n ** 3 / (ms * 1e-3) / 1e9 / peak}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes'])
+    ap.add_argument('--size', type=int, default=512)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--batch', type=int, default=None, help='volumes per step (default 8; smaller only for profiling)')
+    args = ap.parse_args()
+    cfg = dict(CFG1)
+    if args.batch:
+        cfg['batch'] = args.batch
+        cfg['name'] = cfg['name'].replace('batch of 8', f'batch of {args.batch}')
+    if args.impl == 'reference':
+        reference_arm(args, cfg)
+        return
+    import torch
+    import voltools_b200 as vt
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback)')
+    dev = local_rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{dev}'))
+
+        def barrier():
+            dist.barrier()
+
+        def reduce_max(x):
+            t = torch.tensor([x], dtype=torch.float64, device=f'cuda:{dev}')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+    else:
+        def barrier():
+            pass
+
+        def reduce_max(x):
+            return x
+
+    if args.workload == 'modes':
+        res = run_modes(args, torch, vt, dev)
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'workload': f'modes {args.size}^3', 'modes': res}))
+        return
+    line = run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline_leg(cfg)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

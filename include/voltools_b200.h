@@ -44,9 +44,10 @@ extern "C" {
 #define VT_OOB_SKIP 0x0u       /* out-of-bounds output voxels are not written (reference: transforms.py:276-278) */
 #define VT_OOB_ZERO 0x1u       /* ...are written as 0: fuses the reference's fill(0)/cp.zeros (transforms.py:208,
                                   volume.py:73) into the kernel when the library owns a fresh output            */
-#define VT_WEIGHTS_TEX_RN 0x0u /* texture-unit compatible weights: coordinate -> 1.8 fixed point, round-nearest  */
-#define VT_WEIGHTS_TEX_TRUNC 0x2u /* same, truncating conversion (diagnostic)                                     */
-#define VT_WEIGHTS_EXACT 0x4u  /* exact float32 fractions (more accurate than the reference; not parity)         */
+#define VT_WEIGHTS_TEX_HW 0x0u /* texture-unit compatible filter weights for VT_LINEAR / VT_CUBIC_TEX: the B200 unit's
+                                  1.8 fixed-point coordinates and 8-bit integer texel weights, reproduced in
+                                  software (DESIGN.md "texture unit model") -- the parity policy, default         */
+#define VT_WEIGHTS_EXACT 0x4u  /* exact float32 fractions (more accurate than the reference; NOT parity)         */
 #define VT_KERNEL_AUTO 0x00u   /* pick the kernel family from shape/alignment/matrix                             */
 #define VT_KERNEL_GATHER 0x10u /* force: direct global gathers through L1                                        */
 #define VT_KERNEL_BRICK 0x20u  /* force: TMA-staged shared-memory brick cache (VT_ERR_UNSUPPORTED if impossible) */
@@ -105,6 +106,18 @@ int vt_host_affine_f32(vt_host_ctx *ctx, const float *h_src, int s0, int s1, int
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 long long vt_launch_count(void);
+
+/*
+ * Per-kernel device timing, for roofline reporting (replaces the reference's `profile=` event pair around
+ * the whole call, voltools/transforms.py:167-169, :214-219, at kernel granularity).  While enabled every
+ * kernel launch of the library is bracketed by CUDA events on its own stream.  vt_profile_read blocks until
+ * the recorded launches of that kernel have finished and returns their summed duration and their count
+ * since the last vt_profile_enable(1).
+ */
+int vt_profile_enable(int on);
+int vt_profile_kernel_count(void);
+const char *vt_profile_kernel_name(int kernel);
+int vt_profile_read(int kernel, double *ms_total, long long *launches);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ _SO = HERE / 'libvt_oracle.so'
 
 # interpolation name -> which of the reference's three device functions it selects (transforms.py:11-17)
 INTERP_FN = {'linear': 0, 'bspline': 1, 'bspline_simple': 2, 'filt_bspline': 1, 'filt_bspline_simple': 2}
-TEX_RN, TEX_TRUNC, TEX_EXACT = 0, 1, 2
+TEX_RN, TEX_TRUNC, TEX_EXACT, TEX_HW = 0, 1, 2, 3
 
 _lib = None
 _f32p = ctypes.POINTER(ctypes.c_float)
@@ -77,7 +77,7 @@ def prefilter_line(line):
     return v
 
 
-def affine(volume, matrix, interpolation='linear', output=None, tex_rule=TEX_RN, out_shape=None, z_range=None):
+def affine(volume, matrix, interpolation='linear', output=None, tex_rule=TEX_HW, out_shape=None, z_range=None):
     """Restatement of the reference GPU branch of affine(): returns the output volume.
 
     `volume` is the array the texture would hold; for filt_* names it is prefiltered here first
@@ -95,7 +95,7 @@ def affine(volume, matrix, interpolation='linear', output=None, tex_rule=TEX_RN,
     return out
 
 
-def tex3d_many(volume, xyz, tex_rule=TEX_RN):
+def tex3d_many(volume, xyz, tex_rule=TEX_HW):
     v = _c32(volume)
     c = _c32(xyz).reshape(-1, 3)
     out = np.empty(len(c), np.float32)

@@ -12,7 +12,7 @@ _SO = Path(__file__).resolve().parent / 'libvoltools_b200.so'
 
 LINEAR, CUBIC_TEX, CUBIC_SIMPLE = 0, 1, 2
 OOB_SKIP, OOB_ZERO = 0x0, 0x1
-WEIGHTS_TEX_RN, WEIGHTS_TEX_TRUNC, WEIGHTS_EXACT = 0x0, 0x2, 0x4
+WEIGHTS_TEX_HW, WEIGHTS_EXACT = 0x0, 0x4
 KERNEL_AUTO, KERNEL_GATHER, KERNEL_BRICK = 0x00, 0x10, 0x20
 MAX_BATCH = 32
 
@@ -50,6 +50,10 @@ def lib():
         L.vt_host_ctx_destroy.argtypes = [_vp]
         L.vt_host_affine_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f32p, _i, _i, ctypes.c_uint]
         L.vt_launch_count.restype = ctypes.c_longlong
+        L.vt_profile_enable.argtypes = [_i]
+        L.vt_profile_kernel_name.restype = ctypes.c_char_p
+        L.vt_profile_kernel_name.argtypes = [_i]
+        L.vt_profile_read.argtypes = [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
         if L.vt_abi_version() != 1:
             raise RuntimeError('libvoltools_b200.so ABI version mismatch')
         _lib = L
@@ -69,6 +73,21 @@ def device_count():
 
 def launch_count():
     return lib().vt_launch_count()
+
+
+def profile_enable(on=True):
+    check(lib().vt_profile_enable(int(bool(on))))
+
+
+def profile_read():
+    """{kernel name: (total ms, launches)} for every kernel launched since profile_enable(True)."""
+    out = {}
+    for k in range(lib().vt_profile_kernel_count()):
+        ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
+        check(lib().vt_profile_read(k, ctypes.byref(ms), ctypes.byref(n)))
+        if n.value:
+            out[lib().vt_profile_kernel_name(k).decode()] = (ms.value, n.value)
+    return out
 
 
 def _mats(matrices):

@@ -2,7 +2,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "vt_common.cuh"
 
@@ -14,6 +16,63 @@ int vt_prefilter_win(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    
 
 static std::atomic<long long> g_launches{0};
 void vt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------------------
+// per-kernel device timing
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct ProfRec {
+    int id;
+    cudaEvent_t e0, e1;
+};
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+std::vector<ProfRec *> g_prof_recs;
+double g_prof_ms[VT_K_COUNT];
+long long g_prof_n[VT_K_COUNT];
+const char *const g_prof_names[VT_K_COUNT] = {
+    "prefilter_x", "prefilter_y", "prefilter_z", "prefilter_fused", "gather_linear", "gather_cubic_tex",
+    "gather_cubic_simple", "brick_linear", "brick_cubic_tex", "brick_cubic_simple", "slice_linear",
+    "slice_cubic_tex", "slice_cubic_simple"};
+
+void prof_drain_locked()
+{
+    for (ProfRec *r : g_prof_recs) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(r->e1) == cudaSuccess && cudaEventElapsedTime(&ms, r->e0, r->e1) == cudaSuccess) {
+            g_prof_ms[r->id] += ms;
+            g_prof_n[r->id] += 1;
+        }
+        cudaEventDestroy(r->e0);
+        cudaEventDestroy(r->e1);
+        delete r;
+    }
+    g_prof_recs.clear();
+}
+}  // namespace
+
+VtProf::VtProf(int id_, cudaStream_t st_) : id(id_), st(st_), rec(nullptr)
+{
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec *r = new (std::nothrow) ProfRec();
+    if (!r) return;
+    r->id = id;
+    if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess) {
+        delete r;
+        return;
+    }
+    cudaEventRecord(r->e0, st);
+    rec = r;
+}
+
+VtProf::~VtProf()
+{
+    if (!rec) return;
+    ProfRec *r = (ProfRec *)rec;
+    cudaEventRecord(r->e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
+}
 
 namespace {
 
@@ -116,6 +175,37 @@ int vt_device_count(int *count)
 }
 
 long long vt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vt_profile_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_drain_locked();
+    if (on) {
+        for (int i = 0; i < VT_K_COUNT; i++) {
+            g_prof_ms[i] = 0.0;
+            g_prof_n[i] = 0;
+        }
+    }
+    g_prof_on.store(on ? 1 : 0);
+    return VT_OK;
+}
+
+int vt_profile_kernel_count(void) { return VT_K_COUNT; }
+
+const char *vt_profile_kernel_name(int kernel)
+{
+    return (kernel >= 0 && kernel < VT_K_COUNT) ? g_prof_names[kernel] : "";
+}
+
+int vt_profile_read(int kernel, double *ms_total, long long *launches)
+{
+    if (kernel < 0 || kernel >= VT_K_COUNT || !ms_total || !launches) return VT_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_drain_locked();
+    *ms_total = g_prof_ms[kernel];
+    *launches = g_prof_n[kernel];
+    return VT_OK;
+}
 
 int vt_prefilter_f32(float *d_vol, int d0, int d1, int d2, int variant, int device, void *stream)
 {

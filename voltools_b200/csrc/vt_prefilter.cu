@@ -144,6 +144,7 @@ int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st)
         const size_t n_rows = D * H;
         const size_t blocks = (n_rows + 32 * XW - 1) / (32 * XW);
         if (blocks > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
+        VtProf prof(VT_K_PREFILTER_X, st);
         prefilter_x_seq<<<(unsigned)blocks, dim3(32, XW), 0, st>>>(d_vol, d2, n_rows);
         vt_count_launch();
     }
@@ -151,6 +152,7 @@ int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st)
     {
         dim3 grid((unsigned)((W + 255) / 256), (unsigned)D);
         if (D > 65535) return VT_ERR_UNSUPPORTED;
+        VtProf prof(VT_K_PREFILTER_Y, st);
         prefilter_strided_seq<<<grid, 256, 0, st>>>(d_vol, d1, W, d2, d0, H * W);
         vt_count_launch();
     }
@@ -160,6 +162,7 @@ int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st)
         const size_t bx = (cols + 255) / 256;
         if (bx > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
         // inner index runs over the whole (y, x) plane: treat the plane as one row of H*W columns
+        VtProf prof(VT_K_PREFILTER_Z, st);
         prefilter_strided_seq<<<dim3((unsigned)bx, 1), 256, 0, st>>>(d_vol, d0, cols, (int)cols, 1, 0);
         vt_count_launch();
     }

@@ -8,7 +8,8 @@
 //   * 3-D output tiles (32 x 8 x TZ) instead of a 1-D grid-stride loop: neighbouring threads sample
 //     neighbouring input voxels in all three axes, and index decomposition needs no division;
 //   * the matrix (and a whole batch of them) lives in kernel parameters (constant bank), not in global memory;
-//   * the texture unit is emulated in software (1.8 fixed-point weights, border = 0), so the source is the
+//   * the texture unit is reproduced in software (vt_common.cuh: 1.8 fixed-point coordinates, 8-bit integer
+//     texel weights, border = 0), so the source is the
 //     plain linear buffer: no CUDA-array copy (transforms.py:197-199) is needed.
 #include "vt_common.cuh"
 
@@ -36,11 +37,18 @@ template <int RULE>
 __device__ __forceinline__ float tex3d_emul(const SrcView &s, float x, float y, float z)
 {
     int i2, i1, i0;
-    float ax, ay, az;
-    vt_tex_fix<RULE>(x, i2, ax);
-    vt_tex_fix<RULE>(y, i1, ay);
-    vt_tex_fix<RULE>(z, i0, az);
     float c000, c001, c010, c011, c100, c101, c110, c111;
+    int a, b, c;
+    float ax, ay, az;
+    if (RULE == 0) {
+        vt_tex_fix_hw(x, i2, a);
+        vt_tex_fix_hw(y, i1, b);
+        vt_tex_fix_hw(z, i0, c);
+    } else {
+        vt_tex_fix<2>(x, i2, ax);
+        vt_tex_fix<2>(y, i1, ay);
+        vt_tex_fix<2>(z, i0, az);
+    }
     const bool interior = i0 >= 0 && i1 >= 0 && i2 >= 0 && i0 + 1 < s.s0 && i1 + 1 < s.s1 && i2 + 1 < s.s2;
     if (interior) {
         const float *q = s.p + ((size_t)i0 * s.s1 + i1) * s.s2 + i2;
@@ -54,6 +62,20 @@ __device__ __forceinline__ float tex3d_emul(const SrcView &s, float x, float y, 
         c010 = s.at(i0, i1 + 1, i2);     c011 = s.at(i0, i1 + 1, i2 + 1);
         c100 = s.at(i0 + 1, i1, i2);     c101 = s.at(i0 + 1, i1, i2 + 1);
         c110 = s.at(i0 + 1, i1 + 1, i2); c111 = s.at(i0 + 1, i1 + 1, i2 + 1);
+    }
+    if (RULE == 0) {
+        int wn[4], wf[4];
+        vt_tex_hw_side(a, b, 256 - c, wn);
+        vt_tex_hw_side(a, b, c, wf);
+        float r = __fmul_rn(vt_u2f(wn[0]), c000);
+        r = __fmaf_rn(vt_u2f(wn[1]), c001, r);
+        r = __fmaf_rn(vt_u2f(wn[2]), c010, r);
+        r = __fmaf_rn(vt_u2f(wn[3]), c011, r);
+        r = __fmaf_rn(vt_u2f(wf[0]), c100, r);
+        r = __fmaf_rn(vt_u2f(wf[1]), c101, r);
+        r = __fmaf_rn(vt_u2f(wf[2]), c110, r);
+        r = __fmaf_rn(vt_u2f(wf[3]), c111, r);
+        return __fmul_rn(r, 1.0f / 256.0f);
     }
     const float bx = 1.0f - ax, by = 1.0f - ay, bz = 1.0f - az;
     const float r00 = bx * c000 + ax * c001, r01 = bx * c010 + ax * c011;
@@ -172,8 +194,11 @@ int launch2(const VtResampleParams &P, cudaStream_t st)
     dim3 grid((P.o2 + TX - 1) / TX, (P.o1 + TY - 1) / TY, nzt * P.n_mats);
     dim3 block(TX, TY, 1);
     if (grid.y > 65535u || grid.z > 65535u) return VT_ERR_UNSUPPORTED;
-    if (P.flags & VT_OOB_ZERO) vt_gather_kernel<INTERP, RULE, true><<<grid, block, 0, st>>>(P);
-    else vt_gather_kernel<INTERP, RULE, false><<<grid, block, 0, st>>>(P);
+    {
+        VtProf prof(VT_K_GATHER_LINEAR + INTERP, st);
+        if (P.flags & VT_OOB_ZERO) vt_gather_kernel<INTERP, RULE, true><<<grid, block, 0, st>>>(P);
+        else vt_gather_kernel<INTERP, RULE, false><<<grid, block, 0, st>>>(P);
+    }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
     return VT_OK;
@@ -184,7 +209,6 @@ int launch1(const VtResampleParams &P, cudaStream_t st)
 {
     if (INTERP == VT_CUBIC_SIMPLE) return launch2<INTERP, 0>(P, st);  // no texture weights involved
     if (P.flags & VT_WEIGHTS_EXACT) return launch2<INTERP, 2>(P, st);
-    if (P.flags & VT_WEIGHTS_TEX_TRUNC) return launch2<INTERP, 1>(P, st);
     return launch2<INTERP, 0>(P, st);
 }
 

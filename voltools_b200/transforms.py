@@ -9,6 +9,9 @@ Inputs may be numpy arrays, torch CUDA tensors or any object exposing __cuda_arr
 `output=` may be a torch CUDA tensor or a __cuda_array_interface__ object and is written in place:
 out-of-bounds voxels keep their previous contents and the function returns None (transforms.py:224-226).
 With output=None the result is returned as a numpy array (transforms.py:221-223).
+Extension: with a numpy `volume`, `output=` may also be a float32 C-contiguous numpy array (ideally pinned); it is
+then completely overwritten (out-of-bounds voxels = 0, like output=None) straight from the device and the function
+returns None -- this saves the host-side copy of the result.
 """
 from typing import Tuple, Union
 
@@ -156,8 +159,14 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
     m = np.ascontiguousarray(transform_m, dtype=np.float32).reshape(4, 4)
 
     host_in = _is_host(volume)
+    host_out = output is not None and _is_host(output)
+    if host_out:
+        if not host_in:
+            raise ValueError('a numpy `output` needs a numpy `volume`')
+        if output.dtype != np.float32 or not output.flags.c_contiguous:
+            raise ValueError('output: expected a C-contiguous float32 numpy array')
     vin = None if host_in else _device_view(volume, 'volume')
-    vout = None if output is None else _device_view(output, 'output')
+    vout = None if (output is None or host_out) else _device_view(output, 'output')
     dev = _resolve_device(device, vin, vout)
 
     if reshape:
@@ -178,6 +187,8 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
     shape = tuple(int(s) for s in volume.shape)
     if vout is not None and vout.shape != shape:
         raise ValueError(f'output shape {vout.shape} does not match the volume shape {shape}')
+    if host_out and tuple(output.shape) != shape:
+        raise ValueError(f'output shape {tuple(output.shape)} does not match the volume shape {shape}')
 
     with torch.cuda.device(dev):
         if profile:
@@ -187,11 +198,13 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
         if host_in and vout is None:
             # numpy in -> numpy out (transforms.py:180-223): pipelined host path inside the library
             src = np.ascontiguousarray(volume, dtype=np.float32)
-            result = np.empty(shape, dtype=np.float32)
+            result = output if host_out else np.empty(shape, dtype=np.float32)
             ctx = _host_ctx.get(dev)
             if ctx is None:
                 ctx = _host_ctx[dev] = _native.HostContext(dev)
             ctx.affine(src, result, m, interp, needs_prefilter)
+            if host_out:
+                result = None
         else:
             stream = _stream(dev)
             if host_in:
