@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 1
+#define VT_ABI_VERSION 2
 
 /* status codes: 0 ok; 1..99 library errors; 1000+e = cudaError_t e; 2000+e = CUresult e */
 #define VT_OK 0
@@ -50,7 +50,8 @@ extern "C" {
 #define VT_WEIGHTS_EXACT 0x4u  /* exact float32 fractions (more accurate than the reference; NOT parity)         */
 #define VT_KERNEL_AUTO 0x00u   /* pick the kernel family from shape/alignment/matrix                             */
 #define VT_KERNEL_GATHER 0x10u /* force: direct global gathers through L1                                        */
-#define VT_KERNEL_BRICK 0x20u  /* force: TMA-staged shared-memory brick cache (VT_ERR_UNSUPPORTED if impossible) */
+#define VT_KERNEL_BRICK 0x20u  /* force: shared-memory brick cache, general matrices (VT_ERR_UNSUPPORTED if impossible) */
+#define VT_KERNEL_SLICE 0x30u  /* force: plane-marching kernels for matrices that leave axis 0 alone (ditto)         */
 
 #define VT_MAX_BATCH 32 /* matrices per launch held in kernel parameters; larger batches are chunked */
 
@@ -61,16 +62,20 @@ const char *vt_error_string(int status);
 int vt_device_count(int *count);
 
 /*
- * Cubic B-spline prefilter, in place, X (fastest axis) then Y then Z.
+ * Cubic B-spline prefilter: samples d_src -> interpolation coefficients d_dst, X (fastest axis) then Y then Z.
  * Replaces _bspline_prefilter (voltools/transforms.py:290-309) and the kernels SamplesToCoefficients3DX/Y/Z
  * (voltools/kernels/bspline.h:58-99); any shape >= 1 per axis (no power-of-two launch constraint).
- *   d_vol   device pointer, (d0,d1,d2) float32 C-contiguous
- *   variant 0 = default (fastest validated), 1 = sequential two-sweep kernels with the reference's exact
- *           operation order (bit-identical coefficients), 2 = windowed kernels
+ *   d_src, d_dst  device pointers, (d0,d1,d2) float32 C-contiguous.  d_dst == d_src filters in place (what the
+ *           reference does); a distinct d_dst leaves the samples untouched, saves the caller a copy and enables
+ *           the fast windowed kernels.
+ *   variant 0 = default: windowed kernels when d_dst != d_src (16 B/voxel of traffic, coefficients within ~3e-7
+ *           of the range of variant 1), otherwise variant 1;
+ *           1 = sequential two-sweep kernels with the reference's exact operation order (bit-identical
+ *           coefficients), in place or out of place
  *   device  CUDA ordinal, or -1 for the current device
  *   stream  cudaStream_t (NULL = legacy default stream)
  */
-int vt_prefilter_f32(float *d_vol, int d0, int d1, int d2, int variant, int device, void *stream);
+int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, int variant, int device, void *stream);
 
 /*
  * The `transform` kernel launch (voltools/transforms.py:253-282 launched at :212 and volume.py:78), for a
@@ -88,7 +93,7 @@ int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int 
                   long long dst_batch_stride, const float *h_mats, int n_mats, int interp, unsigned flags,
                   int z_begin, int z_end, int device, void *stream);
 
-/* which kernel family vt_affine_f32 would run for these arguments: 1 = gather, 2 = brick */
+/* which kernel family vt_affine_f32 would run for these arguments: 1 = gather, 2 = brick, 3 = slice */
 int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d_src, const float *h_mats,
                    int n_mats, int interp, unsigned flags, int *family);
 

@@ -87,24 +87,106 @@ def test_affine_vs_reference_kernels(vt, mode):
         assert e_mine <= TOL[mode], f'ours vs reference {mode} {name}: {e_mine:.3e}'
 
 
-@pytest.mark.parametrize('shape', [(16, 16, 16), (20, 24, 28), (7, 5, 3), (1, 1, 1), (33, 17, 45), (50, 60, 130)])
+@pytest.mark.parametrize('shape', [(16, 16, 16), (20, 24, 28), (7, 5, 3), (1, 1, 1), (33, 17, 45), (50, 60, 130),
+                                   (3, 200, 11), (70, 9, 300), (40, 130, 33)])
 def test_prefilter(vt, shape):
     import torch
     rng = np.random.default_rng(3)
     vol = rng.random(shape, dtype=np.float32)
     want = oracle.prefilter(vol)
     r = float(np.ptp(want)) or 1.0
-    for variant in (0, 1):
-        t = torch.from_numpy(vol).cuda()
-        vt._native.prefilter(t.data_ptr(), shape, 0, torch.cuda.current_stream().cuda_stream, variant=variant)
-        got = t.cpu().numpy()
-        assert _err(got, want, r) <= 1e-5, (variant, shape, _err(got, want, r))
+    st = torch.cuda.current_stream().cuda_stream
+    # variant 1 (sequential, reference operation order), in place and out of place
+    t = torch.from_numpy(vol).cuda()
+    vt._native.prefilter(t.data_ptr(), shape, 0, st, variant=1)
+    seq = t.cpu().numpy()
+    assert _err(seq, want, r) <= 1e-6, (shape, _err(seq, want, r))
+    src = torch.from_numpy(vol).cuda()
+    dst = torch.full(shape, np.nan, device='cuda')
+    vt._native.prefilter(src.data_ptr(), shape, 0, st, variant=1, dst_ptr=dst.data_ptr())
+    assert np.array_equal(dst.cpu().numpy(), seq) and np.array_equal(src.cpu().numpy(), vol)
+    # variant 0 out of place: windowed kernels (truncated warm-up, |pole|^12 = 1.4e-7)
+    dst = torch.full(shape, np.nan, device='cuda')
+    vt._native.prefilter(src.data_ptr(), shape, 0, st, variant=0, dst_ptr=dst.data_ptr())
+    got = dst.cpu().numpy()
+    assert np.array_equal(src.cpu().numpy(), vol), 'source modified'
+    assert _err(got, want, r) <= 1e-6, ('windowed', shape, _err(got, want, r))
+    # variant 0 in place falls back to the sequential kernels
+    t = torch.from_numpy(vol).cuda()
+    vt._native.prefilter(t.data_ptr(), shape, 0, st, variant=0)
+    assert np.array_equal(t.cpu().numpy(), seq)
     if oracle.ref_gpu_available() and all(s % 2 == 0 for s in shape):
         ref = oracle.prefilter_ref_gpu(vol)
         assert _err(want, ref, r) <= 1e-6
-        t = torch.from_numpy(vol).cuda()
-        vt._native.prefilter(t.data_ptr(), shape, 0, torch.cuda.current_stream().cuda_stream, variant=1)
-        assert np.array_equal(t.cpu().numpy(), ref), 'sequential variant must be bit-identical to the reference'
+        assert np.array_equal(seq, ref), 'sequential variant must be bit-identical to the reference'
+
+
+def test_prefilter_windows_large(vt):
+    """Sizes at which the windowed kernels really cut lines into strips / steps (several y-strips, many z steps)."""
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    for shape in ((100, 300, 250), (64, 120, 512)):
+        src = torch.rand(shape, device='cuda', generator=torch.Generator('cuda').manual_seed(5))
+        a = src.clone()
+        vt._native.prefilter(a.data_ptr(), shape, 0, st, variant=1)
+        b = torch.empty_like(src)
+        vt._native.prefilter(src.data_ptr(), shape, 0, st, variant=0, dst_ptr=b.data_ptr())
+        r = float(a.max() - a.min())
+        assert float((a - b).abs().max()) / r <= 1e-6, shape
+        # interior reconstruction: (c[i-1] + 4 c[i] + c[i+1]) / 6 == s[i] along every axis
+        rec = b
+        for ax in range(3):
+            rec = (rec.roll(1, ax) + 4 * rec + rec.roll(-1, ax)) / 6
+        inner = (slice(16, -16),) * 3
+        assert float((rec[inner] - src[inner]).abs().max()) <= 2e-5
+
+
+def _slice_matrices(vt, shape):
+    c = _center(shape)
+    tm = vt.utils.transform_matrix
+    mats = {f'rot{a}': tm(rotation=(0, a, 0), rotation_order='rzxz', center=c) for a in (0, 1, 45, 90, 133.7, 180, -60)}
+    mats['rot30_shift'] = tm(rotation=(0, 30, 0), rotation_order='rzxz', center=c, translation=(3, 1.25, -2.5))
+    mats['rot30_shift_neg'] = tm(rotation=(0, -30, 0), rotation_order='rzxz', center=c, translation=(-5, 0.5, 0.75))
+    mats['inplane_scale'] = tm(scale=(1.0, 1.15, 0.9), center=c)
+    mats['origin_rotate'] = vt.utils.rotation_matrix((0, 20, 0), rotation_order='rzxz')
+    return mats
+
+
+@pytest.mark.parametrize('shape', [(20, 24, 28), (33, 47, 45), (9, 70, 130)])
+@pytest.mark.parametrize('interp', [0, 1, 2])
+def test_slice_family(vt, shape, interp):
+    """Matrices that leave axis 0 alone run on the plane-marching kernels: same results as the general gather
+    kernels (float32 summation order aside) and as the oracle."""
+    import torch
+    N = vt._native
+    rng = np.random.default_rng(17)
+    vol_np = rng.random(shape, dtype=np.float32)
+    vol = torch.from_numpy(vol_np).cuda()
+    mode = ['linear', 'bspline', 'bspline_simple'][interp]
+    for name, m in _slice_matrices(vt, shape).items():
+        assert N.affine_plan(vol.data_ptr(), shape, shape, m, interp) == 'slice', name
+        for flag in (N.OOB_ZERO, N.OOB_SKIP):
+            a = torch.full(shape, -7.0, device='cuda')
+            b = torch.full(shape, -7.0, device='cuda')
+            N.affine(vol.data_ptr(), shape, a.data_ptr(), shape, m, interp, flag | N.KERNEL_SLICE)
+            N.affine(vol.data_ptr(), shape, b.data_ptr(), shape, m, interp, flag | N.KERNEL_GATHER)
+            a, b = a.cpu().numpy(), b.cpu().numpy()
+            assert np.array_equal(a == -7.0, b == -7.0), (name, 'skipped sets differ')
+            assert _err(a, b, 1.0) <= 1e-6, (name, _err(a, b, 1.0))
+        want = oracle.affine(vol_np, m, mode)
+        assert _err(a if flag == N.OOB_ZERO else np.where(a == -7.0, 0, a), want, 1.0) <= 1e-6, name
+    # a matrix with a fractional offset along axis 0 must NOT take the slice path
+    m = vt.utils.transform_matrix(rotation=(0, 30, 0), rotation_order='rzxz', center=_center(shape),
+                                  translation=(0.5, 0, 0))
+    assert N.affine_plan(vol.data_ptr(), shape, shape, m, interp) != 'slice'
+    # batched: several angles in one launch, z-slab restricted
+    mats = [vt.utils.transform_matrix(rotation=(0, a, 0), center=_center(shape)) for a in range(0, 180, 9)]
+    out = torch.zeros((len(mats),) + shape, device='cuda')
+    N.affine(vol.data_ptr(), shape, out.data_ptr(), shape, mats, interp, N.OOB_ZERO | N.KERNEL_SLICE, z_range=(2, 7))
+    ref = torch.zeros((len(mats),) + shape, device='cuda')
+    N.affine(vol.data_ptr(), shape, ref.data_ptr(), shape, mats, interp, N.OOB_ZERO | N.KERNEL_GATHER, z_range=(2, 7))
+    assert float((out - ref).abs().max()) <= 1e-6
+    assert float(out[:, :2].abs().max()) == 0 and float(out[:, 7:].abs().max()) == 0
 
 
 def test_output_semantics(vt):

@@ -26,7 +26,7 @@ def timeit(fn, iters=10, warm=3):
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [256, 512]
+    sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [256, 512]
     for n in sizes:
         shape = (n, n, n)
         nvox = n ** 3
@@ -42,23 +42,28 @@ def main():
         src = torch.from_numpy(vol).cuda()
         dst = torch.zeros(shape, device='cuda')
         st = torch.cuda.current_stream().cuda_stream
+        tmp = torch.empty_like(src)
         for variant in (1, 0):
-            tmp = src.clone()
-            ms = timeit(lambda: _native.prefilter(tmp.data_ptr(), shape, 0, st, variant=variant), iters=5, warm=1)
+            _native.profile_enable(True)
+            ms = timeit(lambda: _native.prefilter(src.data_ptr(), shape, 0, st, variant=variant, dst_ptr=tmp.data_ptr()),
+                        iters=5, warm=2)
+            prof = _native.profile_read()
+            _native.profile_enable(False)
             print(f'{n}^3 prefilter variant {variant}: {ms:.3f} ms  {nvox / ms / 1e6:.1f} Gvox/s  '
-                  f'({8 * nvox / ms / 1e6 / 6549.1 * 100:.1f}% of 8B/vox roofline)')
+                  f'({8 * nvox / ms / 1e6 / 6549.1 * 100:.1f}% of 8B/vox roofline)  '
+                  + ' '.join(f'{k}={v[0] / v[1]:.3f}ms' for k, v in prof.items()))
         for mname, m in mats.items():
             for interp, iname in ((0, 'linear'), (1, 'cubic_tex'), (2, 'cubic_simple')):
-                for fam, fname in ((_native.KERNEL_GATHER, 'gather'), (_native.KERNEL_BRICK, 'brick')):
+                for fam, fname in ((_native.KERNEL_GATHER, 'gather'), (_native.KERNEL_BRICK, 'brick'),
+                                   (_native.KERNEL_SLICE, 'slice')):
                     try:
                         ms = timeit(lambda: _native.affine(src.data_ptr(), shape, dst.data_ptr(), shape, m, interp,
                                                            _native.OOB_ZERO | fam, stream=st))
                     except RuntimeError as e:
-                        print(f'{n}^3 {mname} {iname} {fname}: {e}')
                         continue
                     print(f'{n}^3 {mname} {iname} {fname}: {ms:.3f} ms  {nvox / ms / 1e6:.1f} Gvox/s  '
                           f'({8 * nvox / ms / 1e6 / 6549.1 * 100:.1f}% roofline)')
-        if oracle.ref_gpu_available() and n <= 512:
+        if oracle.ref_gpu_available() and n <= 512 and '--ref' in sys.argv:
             for mname, m in mats.items():
                 for mode in ('linear', 'bspline', 'bspline_simple', 'filt_bspline'):
                     _, msk, msp = oracle.transform_ref_gpu(vol, m, mode, iters=5)

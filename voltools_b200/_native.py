@@ -13,7 +13,7 @@ _SO = Path(__file__).resolve().parent / 'libvoltools_b200.so'
 LINEAR, CUBIC_TEX, CUBIC_SIMPLE = 0, 1, 2
 OOB_SKIP, OOB_ZERO = 0x0, 0x1
 WEIGHTS_TEX_HW, WEIGHTS_EXACT = 0x0, 0x4
-KERNEL_AUTO, KERNEL_GATHER, KERNEL_BRICK = 0x00, 0x10, 0x20
+KERNEL_AUTO, KERNEL_GATHER, KERNEL_BRICK, KERNEL_SLICE = 0x00, 0x10, 0x20, 0x30
 MAX_BATCH = 32
 
 # interpolation name -> (device function, needs prefilter)      voltools/transforms.py:11-17
@@ -42,7 +42,7 @@ def lib():
         L.vt_error_string.restype = ctypes.c_char_p
         L.vt_error_string.argtypes = [_i]
         L.vt_device_count.argtypes = [ctypes.POINTER(_i)]
-        L.vt_prefilter_f32.argtypes = [_vp, _i, _i, _i, _i, _i, _vp]
+        L.vt_prefilter_f32.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp]
         L.vt_affine_f32.argtypes = [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i,
                                     ctypes.c_uint, _i, _i, _i, _vp]
         L.vt_affine_plan.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _f32p, _i, _i, ctypes.c_uint, ctypes.POINTER(_i)]
@@ -54,7 +54,7 @@ def lib():
         L.vt_profile_kernel_name.restype = ctypes.c_char_p
         L.vt_profile_kernel_name.argtypes = [_i]
         L.vt_profile_read.argtypes = [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
-        if L.vt_abi_version() != 1:
+        if L.vt_abi_version() != 2:
             raise RuntimeError('libvoltools_b200.so ABI version mismatch')
         _lib = L
     return _lib
@@ -95,8 +95,10 @@ def _mats(matrices):
     return m, m.ctypes.data_as(_f32p)
 
 
-def prefilter(ptr, shape, device=-1, stream=0, variant=0):
-    check(lib().vt_prefilter_f32(ptr, shape[0], shape[1], shape[2], variant, device, stream))
+def prefilter(src_ptr, shape, device=-1, stream=0, variant=0, dst_ptr=None):
+    """Samples at src_ptr -> coefficients at dst_ptr (default: in place)."""
+    check(lib().vt_prefilter_f32(src_ptr, src_ptr if dst_ptr is None else dst_ptr, shape[0], shape[1], shape[2],
+                                 variant, device, stream))
 
 
 def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None,
@@ -114,7 +116,7 @@ def affine_plan(src_ptr, src_shape, dst_shape, matrices, interp, flags=0):
     fam = _i(0)
     check(lib().vt_affine_plan(*map(int, src_shape), *map(int, dst_shape), src_ptr, mp, len(m), interp, flags,
                                ctypes.byref(fam)))
-    return {1: 'gather', 2: 'brick'}[fam.value]
+    return {1: 'gather', 2: 'brick', 3: 'slice'}[fam.value]
 
 
 class HostContext:

@@ -11,8 +11,10 @@
 int vt_launch_gather(const VtResampleParams &P, int interp, cudaStream_t st);   // vt_resample_gather.cu
 int vt_launch_brick(const VtResampleParams &P, int interp, cudaStream_t st);    // vt_resample_brick.cu
 int vt_brick_supported(const VtResampleParams &P, int interp);                  // vt_resample_brick.cu
+int vt_launch_slice(const VtResampleParams &P, int interp, cudaStream_t st);    // vt_resample_slice.cu
+int vt_slice_supported(const VtResampleParams &P, int interp);                  // vt_resample_slice.cu
 int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter.cu
-int vt_prefilter_win(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter_win.cu
+int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, cudaStream_t st);  // vt_prefilter_win.cu
 
 static std::atomic<long long> g_launches{0};
 void vt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -130,9 +132,10 @@ int choose_family(const VtResampleParams &P, int interp, unsigned flags)
 {
     const unsigned forced = flags & 0xf0u;
     if (forced == VT_KERNEL_GATHER) return 1;
-    const int ok = vt_brick_supported(P, interp);
-    if (forced == VT_KERNEL_BRICK) return ok ? 2 : -1;
-    return ok ? 2 : 1;
+    if (forced == VT_KERNEL_SLICE) return vt_slice_supported(P, interp) ? 3 : -1;
+    if (forced == VT_KERNEL_BRICK) return vt_brick_supported(P, interp) ? 2 : -1;
+    if (vt_slice_supported(P, interp)) return 3;
+    return vt_brick_supported(P, interp) ? 2 : 1;
 }
 
 }  // namespace
@@ -207,18 +210,20 @@ int vt_profile_read(int kernel, double *ms_total, long long *launches)
     return VT_OK;
 }
 
-int vt_prefilter_f32(float *d_vol, int d0, int d1, int d2, int variant, int device, void *stream)
+int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, int variant, int device, void *stream)
 {
-    if (!d_vol || d0 < 1 || d1 < 1 || d2 < 1) return VT_ERR_INVALID_ARG;
+    if (!d_src || !d_dst || d0 < 1 || d1 < 1 || d2 < 1) return VT_ERR_INVALID_ARG;
+    if (variant != 0 && variant != 1) return VT_ERR_INVALID_ARG;
     DeviceGuard g(device);
     if (g.status) return g.status;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (variant) {
-        case 0: return vt_prefilter_win(d_vol, d0, d1, d2, st);
-        case 1: return vt_prefilter_seq(d_vol, d0, d1, d2, st);
-        case 2: return vt_prefilter_win(d_vol, d0, d1, d2, st);
+    if (variant == 0 && d_src != d_dst) {
+        const int rc = vt_prefilter_win(d_src, d_dst, d0, d1, d2, st);
+        if (rc != VT_ERR_UNSUPPORTED) return rc;  // rows too long for shared memory: sequential kernels
     }
-    return VT_ERR_INVALID_ARG;
+    if (d_src != d_dst)
+        VT_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)d0 * d1 * d2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return vt_prefilter_seq(d_dst, d0, d1, d2, st);
 }
 
 int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d_src, const float *h_mats, int n_mats,
@@ -255,7 +260,8 @@ int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int 
         P.dst = d_dst + (size_t)first * dst_batch_stride;
         const int family = choose_family(P, interp, flags);
         if (family < 0) return VT_ERR_UNSUPPORTED;
-        rc = (family == 2) ? vt_launch_brick(P, interp, st) : vt_launch_gather(P, interp, st);
+        rc = family == 3 ? vt_launch_slice(P, interp, st)
+             : family == 2 ? vt_launch_brick(P, interp, st) : vt_launch_gather(P, interp, st);
         if (rc) return rc;
     }
     return VT_OK;
@@ -267,8 +273,8 @@ int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int 
 struct vt_host_ctx {
     int device;
     cudaStream_t st_in, st_k, st_out;
-    float *d_src, *d_dst;
-    size_t cap_src, cap_dst;
+    float *d_src, *d_dst, *d_coef;
+    size_t cap_src, cap_dst, cap_coef;
     cudaEvent_t ev_in, ev_k;
 };
 
@@ -300,6 +306,7 @@ int vt_host_ctx_destroy(vt_host_ctx *c)
     cudaStreamSynchronize(c->st_out);
     cudaFree(c->d_src);
     cudaFree(c->d_dst);
+    cudaFree(c->d_coef);
     cudaEventDestroy(c->ev_in);
     cudaEventDestroy(c->ev_k);
     cudaStreamDestroy(c->st_in);
@@ -334,9 +341,13 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
     if (rc) return rc;
     // upload (the source is needed whole before any output plane can be gathered under a general affine map)
     VT_CUDA(cudaMemcpyAsync(c->d_src, h_src, nsrc * 4, cudaMemcpyHostToDevice, c->st_k));
+    const float *sampled = c->d_src;
     if (prefilter) {
-        rc = vt_prefilter_f32(c->d_src, s0, s1, s2, 0, -1, c->st_k);
+        rc = ensure(&c->d_coef, &c->cap_coef, nsrc * 4);
         if (rc) return rc;
+        rc = vt_prefilter_f32(c->d_src, c->d_coef, s0, s1, s2, 0, -1, c->st_k);
+        if (rc) return rc;
+        sampled = c->d_coef;
     }
     // output=None semantics (transforms.py:207-210): skipped voxels are zero -> fused as VT_OOB_ZERO.
     // z-slabs: the kernel of slab i+1 overlaps the download of slab i.
@@ -345,7 +356,7 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
     for (int sl = 0; sl < nslab; sl++) {
         const int z0 = (int)((long long)o0 * sl / nslab), z1 = (int)((long long)o0 * (sl + 1) / nslab);
         if (z1 <= z0) continue;
-        rc = vt_affine_f32(c->d_src, s0, s1, s2, c->d_dst, o0, o1, o2, 0, h_m16, 1, interp, fl, z0, z1, -1, c->st_k);
+        rc = vt_affine_f32(sampled, s0, s1, s2, c->d_dst, o0, o1, o2, 0, h_m16, 1, interp, fl, z0, z1, -1, c->st_k);
         if (rc) return rc;
         VT_CUDA(cudaEventRecord(c->ev_k, c->st_k));
         VT_CUDA(cudaStreamWaitEvent(c->st_out, c->ev_k, 0));

@@ -210,18 +210,14 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
             if host_in:
                 src_t = torch.from_numpy(np.ascontiguousarray(volume, dtype=np.float32)).to(f'cuda:{dev}')
                 src_ptr = src_t.data_ptr()
-            elif needs_prefilter:
-                # never clobber the caller's array: filter a private copy
-                src_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
-                src_view = vin.owner if isinstance(vin.owner, torch.Tensor) \
-                    else torch.as_tensor(vin.owner, device=f'cuda:{dev}')
-                src_t.copy_(src_view)
-                src_ptr = src_t.data_ptr()
             else:
                 src_t = vin.owner
                 src_ptr = vin.ptr
             if needs_prefilter:
-                _native.prefilter(src_ptr, shape, dev, stream)
+                # never clobber the caller's array: the coefficients go to a private buffer (out of place)
+                coef_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
+                _native.prefilter(src_ptr, shape, dev, stream, dst_ptr=coef_t.data_ptr())
+                src_t, src_ptr = coef_t, coef_t.data_ptr()
             if vout is None:
                 out_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
                 _native.affine(src_ptr, shape, out_t.data_ptr(), shape, m, interp, _native.OOB_ZERO, device=dev,

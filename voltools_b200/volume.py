@@ -49,7 +49,11 @@ class StaticVolume:
                     else torch.as_tensor(vin.owner, device=f'cuda:{self._dev}')
                 self._coeffs = src.to(f'cuda:{self._dev}', copy=True)
             if needs_prefilter:
-                _native.prefilter(self._coeffs.data_ptr(), self.shape, self._dev, _stream(self._dev))
+                raw = self._coeffs
+                self._coeffs = torch.empty_like(raw)
+                _native.prefilter(raw.data_ptr(), self.shape, self._dev, _stream(self._dev),
+                                  dst_ptr=self._coeffs.data_ptr())
+                del raw
 
     # -- resident buffer access (used by the multi-GPU layer) -------------------------------------------
     @property
