@@ -53,6 +53,9 @@ extern "C" {
 #define VT_KERNEL_BRICK 0x20u  /* force: shared-memory brick cache, general matrices (VT_ERR_UNSUPPORTED if impossible) */
 #define VT_KERNEL_SLICE 0x30u  /* force: plane-marching kernels for matrices that leave axis 0 alone (ditto)         */
 
+#define VT_STAGE_CP_ASYNC 0x100u /* slice/brick families: stage with per-element cp.async even where TMA box loads are
+                                    possible (16-byte aligned source rows); diagnostic / A-B measurements            */
+
 #define VT_MAX_BATCH 32 /* matrices per launch held in kernel parameters; larger batches are chunked */
 
 int vt_abi_version(void);
@@ -78,6 +81,16 @@ int vt_device_count(int *count);
 int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, int variant, int device, void *stream);
 
 /*
+ * Same, writing the coefficients with padded strides (in elements): row y of plane z starts at
+ * d_dst + z*dst_plane_stride + y*dst_row_stride; the pad columns d2..dst_row_stride-1 are written as zeros.
+ * A row stride that is a multiple of 4 floats (16 bytes) lets vt_affine_strided_f32 stage the volume with TMA
+ * whatever d2 is (e.g. 250 -> 252).  Only variant 0 with d_dst != d_src supports padded strides.
+ * The reference has no counterpart: its resident copy is an opaque CUDA array (voltools/transforms.py:185-199).
+ */
+int vt_prefilter_strided_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride,
+                             long long dst_plane_stride, int variant, int device, void *stream);
+
+/*
  * The `transform` kernel launch (voltools/transforms.py:253-282 launched at :212 and volume.py:78), for a
  * batch of matrices over one resident source volume.
  *   d_src              sampled volume (s0,s1,s2): raw samples, or coefficients from vt_prefilter_f32
@@ -92,6 +105,11 @@ int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, i
 int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
                   long long dst_batch_stride, const float *h_mats, int n_mats, int interp, unsigned flags,
                   int z_begin, int z_end, int device, void *stream);
+
+/* vt_affine_f32 on a source volume with padded strides (elements), as written by vt_prefilter_strided_f32 */
+int vt_affine_strided_f32(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,
+                          float *d_dst, int o0, int o1, int o2, long long dst_batch_stride, const float *h_mats, int n_mats,
+                          int interp, unsigned flags, int z_begin, int z_end, int device, void *stream);
 
 /* which kernel family vt_affine_f32 would run for these arguments: 1 = gather, 2 = brick, 3 = slice */
 int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d_src, const float *h_mats,

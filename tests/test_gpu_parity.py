@@ -111,6 +111,13 @@ def test_prefilter(vt, shape):
     got = dst.cpu().numpy()
     assert np.array_equal(src.cpu().numpy(), vol), 'source modified'
     assert _err(got, want, r) <= 1e-6, ('windowed', shape, _err(got, want, r))
+    # variant 0 into a buffer with rows padded to 16 bytes (what the filt_* paths use): pad columns are zero
+    row = vt._native.padded_row(shape[2]) + 4
+    pad = torch.full((shape[0], shape[1], row), np.nan, device='cuda')
+    vt._native.prefilter(src.data_ptr(), shape, 0, st, variant=0, dst_ptr=pad.data_ptr(),
+                         dst_strides=(row, shape[1] * row))
+    pad = pad.cpu().numpy()
+    assert np.array_equal(pad[:, :, :shape[2]], got) and np.all(pad[:, :, shape[2]:] == 0)
     # variant 0 in place falls back to the sequential kernels
     t = torch.from_numpy(vol).cuda()
     vt._native.prefilter(t.data_ptr(), shape, 0, st, variant=0)
@@ -175,6 +182,23 @@ def test_slice_family(vt, shape, interp):
             assert _err(a, b, 1.0) <= 1e-6, (name, _err(a, b, 1.0))
         want = oracle.affine(vol_np, m, mode)
         assert _err(a if flag == N.OOB_ZERO else np.where(a == -7.0, 0, a), want, 1.0) <= 1e-6, name
+    # staging variants (TMA box loads vs per-element cp.async) are the same arithmetic: bit-identical; the TMA
+    # variant needs 16-byte aligned rows, so run it on a padded copy of the volume
+    row = N.padded_row(shape[2])
+    padded = torch.zeros((shape[0], shape[1], row), device='cuda')
+    padded[:, :, :shape[2]] = vol
+    for name in ('rot45', 'rot30_shift', 'inplane_scale'):
+        m = _slice_matrices(vt, shape)[name]
+        a = torch.zeros(shape, device='cuda')
+        b = torch.zeros(shape, device='cuda')
+        N.affine(padded.data_ptr(), shape, a.data_ptr(), shape, m, interp, N.OOB_ZERO | N.KERNEL_SLICE,
+                 src_strides=(row, shape[1] * row))
+        N.affine(padded.data_ptr(), shape, b.data_ptr(), shape, m, interp,
+                 N.OOB_ZERO | N.KERNEL_SLICE | N.STAGE_CP_ASYNC, src_strides=(row, shape[1] * row))
+        assert torch.equal(a, b), name
+        c = torch.zeros(shape, device='cuda')
+        N.affine(vol.data_ptr(), shape, c.data_ptr(), shape, m, interp, N.OOB_ZERO | N.KERNEL_GATHER)
+        assert float((a - c).abs().max()) <= 1e-6, name
     # a matrix with a fractional offset along axis 0 must NOT take the slice path
     m = vt.utils.transform_matrix(rotation=(0, 30, 0), rotation_order='rzxz', center=_center(shape),
                                   translation=(0.5, 0, 0))

@@ -14,6 +14,7 @@ LINEAR, CUBIC_TEX, CUBIC_SIMPLE = 0, 1, 2
 OOB_SKIP, OOB_ZERO = 0x0, 0x1
 WEIGHTS_TEX_HW, WEIGHTS_EXACT = 0x0, 0x4
 KERNEL_AUTO, KERNEL_GATHER, KERNEL_BRICK, KERNEL_SLICE = 0x00, 0x10, 0x20, 0x30
+STAGE_CP_ASYNC = 0x100
 MAX_BATCH = 32
 
 # interpolation name -> (device function, needs prefilter)      voltools/transforms.py:11-17
@@ -45,6 +46,9 @@ def lib():
         L.vt_prefilter_f32.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp]
         L.vt_affine_f32.argtypes = [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i,
                                     ctypes.c_uint, _i, _i, _i, _vp]
+        L.vt_prefilter_strided_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _vp]
+        L.vt_affine_strided_f32.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i, _i,
+                                            ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _i, _vp]
         L.vt_affine_plan.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _f32p, _i, _i, ctypes.c_uint, ctypes.POINTER(_i)]
         L.vt_host_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
         L.vt_host_ctx_destroy.argtypes = [_vp]
@@ -95,20 +99,33 @@ def _mats(matrices):
     return m, m.ctypes.data_as(_f32p)
 
 
-def prefilter(src_ptr, shape, device=-1, stream=0, variant=0, dst_ptr=None):
-    """Samples at src_ptr -> coefficients at dst_ptr (default: in place)."""
-    check(lib().vt_prefilter_f32(src_ptr, src_ptr if dst_ptr is None else dst_ptr, shape[0], shape[1], shape[2],
-                                 variant, device, stream))
+def padded_row(width):
+    """Row stride (elements) of a coefficient buffer: rows padded to 16 bytes so the kernels can stage with TMA."""
+    return (int(width) + 3) // 4 * 4
+
+
+def prefilter(src_ptr, shape, device=-1, stream=0, variant=0, dst_ptr=None, dst_strides=None):
+    """Samples at src_ptr -> coefficients at dst_ptr (default: in place).  dst_strides = (row, plane) in elements."""
+    dst = src_ptr if dst_ptr is None else dst_ptr
+    if dst_strides is None:
+        check(lib().vt_prefilter_f32(src_ptr, dst, shape[0], shape[1], shape[2], variant, device, stream))
+    else:
+        check(lib().vt_prefilter_strided_f32(src_ptr, dst, shape[0], shape[1], shape[2], int(dst_strides[0]),
+                                             int(dst_strides[1]), variant, device, stream))
 
 
 def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None,
-           device=-1, stream=0):
+           device=-1, stream=0, src_strides=None):
+    """src_strides = (row, plane) element strides of the source (default: dense)."""
     m, mp = _mats(matrices)
     if batch_stride is None:
         batch_stride = int(dst_shape[0]) * int(dst_shape[1]) * int(dst_shape[2])
     z0, z1 = (0, dst_shape[0]) if z_range is None else z_range
-    check(lib().vt_affine_f32(src_ptr, *map(int, src_shape), dst_ptr, *map(int, dst_shape), batch_stride, mp, len(m),
-                              interp, flags, z0, z1, device, stream))
+    if src_strides is None:
+        src_strides = (int(src_shape[2]), int(src_shape[1]) * int(src_shape[2]))
+    check(lib().vt_affine_strided_f32(src_ptr, *map(int, src_shape), int(src_strides[0]), int(src_strides[1]), dst_ptr,
+                                      *map(int, dst_shape), batch_stride, mp, len(m), interp, flags, z0, z1, device,
+                                      stream))
 
 
 def affine_plan(src_ptr, src_shape, dst_shape, matrices, interp, flags=0):

@@ -35,7 +35,7 @@ def build(verbose=False, force=False):
             if log:
                 print(log)
     if force or not SO.exists() or any(o.stat().st_mtime > SO.stat().st_mtime for o in objs):
-        r = subprocess.run(['nvcc', '-shared', '-o', str(SO), *[str(o) for o in objs], '-lcuda'],
+        r = subprocess.run(['nvcc', '-shared', '-o', str(SO), *[str(o) for o in objs]],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')

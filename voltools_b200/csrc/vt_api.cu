@@ -1,4 +1,6 @@
 // vt_api.cu -- the extern "C" surface of libvoltools_b200.so (see include/voltools_b200.h).
+#include <cuda.h>
+
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -11,10 +13,11 @@
 int vt_launch_gather(const VtResampleParams &P, int interp, cudaStream_t st);   // vt_resample_gather.cu
 int vt_launch_brick(const VtResampleParams &P, int interp, cudaStream_t st);    // vt_resample_brick.cu
 int vt_brick_supported(const VtResampleParams &P, int interp);                  // vt_resample_brick.cu
-int vt_launch_slice(const VtResampleParams &P, int interp, cudaStream_t st);    // vt_resample_slice.cu
+int vt_launch_slice(VtResampleParams &P, int interp, cudaStream_t st);          // vt_resample_slice.cu
 int vt_slice_supported(const VtResampleParams &P, int interp);                  // vt_resample_slice.cu
 int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter.cu
-int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, cudaStream_t st);  // vt_prefilter_win.cu
+int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
+                     cudaStream_t st);  // vt_prefilter_win.cu
 
 static std::atomic<long long> g_launches{0};
 void vt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -76,6 +79,30 @@ VtProf::~VtProf()
     g_prof_recs.push_back(r);
 }
 
+int vt_encode_tmap_3d(void *tmap, const void *base, const unsigned long long dims[3], const unsigned long long strides[2],
+                      const unsigned box[3])
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        VT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) return VT_ERR_UNSUPPORTED;
+        fn = (encode_fn)p;
+    }
+    const cuuint64_t gdim[3] = {dims[0], dims[1], dims[2]};
+    const cuuint64_t gstr[2] = {strides[0], strides[1]};
+    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = fn((CUtensorMap *)tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstr, bx, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return cr == CUDA_SUCCESS ? VT_OK : 2000 + (int)cr;
+}
+
 namespace {
 
 // scoped device switch: unlike the reference's switch_to_device (voltools/utils/general.py:84-88) the
@@ -101,14 +128,17 @@ struct DeviceGuard {
     }
 };
 
-int fill_params(VtResampleParams &P, const float *d_src, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
-                long long dst_batch_stride, unsigned flags, int z_begin, int z_end)
+int fill_params(VtResampleParams &P, const float *d_src, int s0, int s1, int s2, long long src_row, long long src_plane,
+                float *d_dst, int o0, int o1, int o2, long long dst_batch_stride, unsigned flags, int z_begin, int z_end)
 {
+    if (src_row < s2 || src_plane < src_row * s1) return VT_ERR_INVALID_ARG;
+    P.src_row = src_row;
+    P.src_plane = src_plane;
     if (!d_src || !d_dst) return VT_ERR_INVALID_ARG;
     if (s0 < 1 || s1 < 1 || s2 < 1 || o0 < 1 || o1 < 1 || o2 < 1) return VT_ERR_INVALID_ARG;
     if (z_begin < 0 || z_end > o0 || z_begin > z_end) return VT_ERR_INVALID_ARG;
     // the reference indexes voxels with 32-bit integers (transforms.py:258-264); so do the kernels' planes
-    if ((long long)s1 * s2 > 0x7fffffffLL || (long long)o1 * o2 > 0x7fffffffLL) return VT_ERR_UNSUPPORTED;
+    if (src_plane > 0x7fffffffLL || (long long)o1 * o2 > 0x7fffffffLL) return VT_ERR_UNSUPPORTED;
     P.src = d_src;
     P.dst = d_dst;
     P.s0 = s0; P.s1 = s1; P.s2 = s2;
@@ -210,20 +240,29 @@ int vt_profile_read(int kernel, double *ms_total, long long *launches)
     return VT_OK;
 }
 
-int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, int variant, int device, void *stream)
+int vt_prefilter_strided_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride,
+                             long long dst_plane_stride, int variant, int device, void *stream)
 {
     if (!d_src || !d_dst || d0 < 1 || d1 < 1 || d2 < 1) return VT_ERR_INVALID_ARG;
     if (variant != 0 && variant != 1) return VT_ERR_INVALID_ARG;
+    if (dst_row_stride < d2 || dst_plane_stride < dst_row_stride * d1) return VT_ERR_INVALID_ARG;
+    const bool dense = dst_row_stride == d2 && dst_plane_stride == (long long)d1 * d2;
+    if (!dense && (variant != 0 || d_src == (const float *)d_dst)) return VT_ERR_UNSUPPORTED;
     DeviceGuard g(device);
     if (g.status) return g.status;
     cudaStream_t st = (cudaStream_t)stream;
     if (variant == 0 && d_src != d_dst) {
-        const int rc = vt_prefilter_win(d_src, d_dst, d0, d1, d2, st);
-        if (rc != VT_ERR_UNSUPPORTED) return rc;  // rows too long for shared memory: sequential kernels
+        const int rc = vt_prefilter_win(d_src, d_dst, d0, d1, d2, dst_row_stride, dst_plane_stride, st);
+        if (rc != VT_ERR_UNSUPPORTED || !dense) return rc;  // rows too long for shared memory: sequential kernels
     }
     if (d_src != d_dst)
         VT_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)d0 * d1 * d2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return vt_prefilter_seq(d_dst, d0, d1, d2, st);
+}
+
+int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, int variant, int device, void *stream)
+{
+    return vt_prefilter_strided_f32(d_src, d_dst, d0, d1, d2, d2, (long long)d1 * d2, variant, device, stream);
 }
 
 int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d_src, const float *h_mats, int n_mats,
@@ -232,7 +271,7 @@ int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d
     if (!family || !h_mats || n_mats < 1) return VT_ERR_INVALID_ARG;
     VtResampleParams P;
     float dummy;
-    int rc = fill_params(P, (const float *)d_src, s0, s1, s2, &dummy, o0, o1, o2, 0, flags, 0, o0);
+    int rc = fill_params(P, (const float *)d_src, s0, s1, s2, s2, (long long)s1 * s2, &dummy, o0, o1, o2, 0, flags, 0, o0);
     if (rc) return rc;
     copy_mats(P, h_mats, 0, n_mats < VT_MAX_BATCH ? n_mats : VT_MAX_BATCH);
     const int f = choose_family(P, interp, flags);
@@ -241,15 +280,16 @@ int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d
     return VT_OK;
 }
 
-int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
-                  long long dst_batch_stride, const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin,
-                  int z_end, int device, void *stream)
+int vt_affine_strided_f32(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,
+                          float *d_dst, int o0, int o1, int o2, long long dst_batch_stride, const float *h_mats, int n_mats,
+                          int interp, unsigned flags, int z_begin, int z_end, int device, void *stream)
 {
     if (!h_mats || n_mats < 0) return VT_ERR_INVALID_ARG;
     if (interp != VT_LINEAR && interp != VT_CUBIC_TEX && interp != VT_CUBIC_SIMPLE) return VT_ERR_INVALID_ARG;
     if (n_mats == 0) return VT_OK;
     VtResampleParams P;
-    int rc = fill_params(P, d_src, s0, s1, s2, d_dst, o0, o1, o2, dst_batch_stride, flags, z_begin, z_end);
+    int rc = fill_params(P, d_src, s0, s1, s2, src_row_stride, src_plane_stride, d_dst, o0, o1, o2, dst_batch_stride, flags,
+                         z_begin, z_end);
     if (rc) return rc;
     DeviceGuard g(device);
     if (g.status) return g.status;
@@ -265,6 +305,14 @@ int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int 
         if (rc) return rc;
     }
     return VT_OK;
+}
+
+int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
+                  long long dst_batch_stride, const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin,
+                  int z_end, int device, void *stream)
+{
+    return vt_affine_strided_f32(d_src, s0, s1, s2, s2, (long long)s1 * s2, d_dst, o0, o1, o2, dst_batch_stride, h_mats,
+                                 n_mats, interp, flags, z_begin, z_end, device, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -342,10 +390,13 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
     // upload (the source is needed whole before any output plane can be gathered under a general affine map)
     VT_CUDA(cudaMemcpyAsync(c->d_src, h_src, nsrc * 4, cudaMemcpyHostToDevice, c->st_k));
     const float *sampled = c->d_src;
+    long long row = s2, plane = (long long)s1 * s2;
     if (prefilter) {
-        rc = ensure(&c->d_coef, &c->cap_coef, nsrc * 4);
+        row = ((long long)s2 + 3) / 4 * 4;  // rows padded to 16 bytes: TMA staging for any width
+        plane = row * s1;
+        rc = ensure(&c->d_coef, &c->cap_coef, (size_t)plane * s0 * 4);
         if (rc) return rc;
-        rc = vt_prefilter_f32(c->d_src, c->d_coef, s0, s1, s2, 0, -1, c->st_k);
+        rc = vt_prefilter_strided_f32(c->d_src, c->d_coef, s0, s1, s2, row, plane, 0, -1, c->st_k);
         if (rc) return rc;
         sampled = c->d_coef;
     }
@@ -356,7 +407,8 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
     for (int sl = 0; sl < nslab; sl++) {
         const int z0 = (int)((long long)o0 * sl / nslab), z1 = (int)((long long)o0 * (sl + 1) / nslab);
         if (z1 <= z0) continue;
-        rc = vt_affine_f32(sampled, s0, s1, s2, c->d_dst, o0, o1, o2, 0, h_m16, 1, interp, fl, z0, z1, -1, c->st_k);
+        rc = vt_affine_strided_f32(sampled, s0, s1, s2, row, plane, c->d_dst, o0, o1, o2, 0, h_m16, 1, interp, fl, z0, z1, -1,
+                                   c->st_k);
         if (rc) return rc;
         VT_CUDA(cudaEventRecord(c->ev_k, c->st_k));
         VT_CUDA(cudaStreamWaitEvent(c->st_out, c->ev_k, 0));

@@ -22,15 +22,23 @@ struct VtResampleParams {
     const float *src;
     float *dst;
     int s0, s1, s2;
+    long long src_row, src_plane;  // element strides of the source: row (axis 1) and plane (axis 0); dense = s2, s1*s2
     int o0, o1, o2;
     long long dst_batch_stride;
     int z_begin, z_end;
     int n_mats;
     unsigned flags;
+    unsigned char aux[VT_MAX_BATCH];  // per-matrix launch parameter chosen by the family's host code
     VtMat mats[VT_MAX_BATCH];
 };
 
 void vt_count_launch(int n = 1);
+
+// 3-D float32 tensor map (dims/strides fastest axis first, strides in bytes for axes 1 and 2), no swizzle, zeros out
+// of bounds.  `tmap` points to a CUtensorMap.  The driver entry point is resolved at run time so that the library
+// has no link-time dependency on libcuda (it must load on machines without a driver).
+int vt_encode_tmap_3d(void *tmap, const void *base, const unsigned long long dims[3], const unsigned long long strides[2],
+                      const unsigned box[3]);
 
 // ---------------------------------------------------------------------------------------------------
 // per-kernel device timing (vt_profile_* in the C ABI): every launch site wraps its <<<>>> in a VtProf,
@@ -114,6 +122,53 @@ __device__ __forceinline__ void vt_tex_fix(float x, int &i, float &alpha)
     const float fl = floorf(xb);
     i = (int)fl;
     alpha = __fsub_rn(xb, fl);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) + mbarrier wrappers.  Waits are bounded: a lost completion traps instead of hanging.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned vt_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void vt_mbar_init(unsigned bar, unsigned arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void vt_mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void vt_mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool vt_mbar_try_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void vt_mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned spins = 0;
+    while (!vt_mbar_try_wait(bar, parity))
+        if (++spins > (1u << 26)) __trap();  // a TMA that never completes must not hang the GPU
+}
+// 3-D tiled box load: coordinates (c0 fastest) may lie outside the tensor, those elements arrive as zeros
+__device__ __forceinline__ void vt_tma_load_3d(unsigned smem_dst, const void *tmap, unsigned bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
+            "r"(smem_dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void vt_tma_prefetch_desc(const void *tmap)
+{
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -10,11 +10,14 @@
 // ("warm-up") with an approximate start value therefore reproduces the full-line recursion to float32 rounding,
 // which is what lets a line be cut into independently processed windows:
 //
-//   kernel 1 (xy): a CTA stages (rows y0-K .. y1+K) x (all of x) of one z-plane in shared memory (coalesced
-//       loads), runs the X recursion with one thread per row over the COMPLETE row (same operation order as the
-//       reference -> bit-identical X pass), then the Y recursion with one thread per column over the staged rows
-//       (warm-up rows above and below unless the strip touches the volume face, where the reference's exact
-//       start formulas apply), and writes rows y0..y1 to the destination (coalesced).  src -> dst, out of place.
+//   kernel 1 (xy): a CTA walks down one z-plane 16 rows at a time.  The 16 rows are staged in shared memory
+//       (coalesced, register-prefetched one step ahead); the X recursion runs on them in 16-sample segments, one
+//       (row, segment) task per thread: a local recursion with zero carry-in, then the carry of the previous
+//       segment is added to the first 12 samples (|z|^k decay: the rest is below float32 resolution), for both
+//       directions; the exact start formulas of the reference are used at the true line ends.  Then one thread
+//       per column continues the Y recursion down the plane exactly like kernel 2 does along z (causal value in
+//       a register, anticausal restart from 12 rows ahead over a register window) and stores finished rows
+//       (coalesced).  Every sample is read once and written once.  src -> dst, out of place.
 //   kernel 2 (z): one thread per (y, x) column sweeps along z ONCE: the causal value is carried in a register;
 //       the anticausal recursion is restarted every B = 16 planes from K planes ahead with the reference's own
 //       start formula c = z/(z-1)*c+ (exact at the last plane, a |z|^12-accurate stand-in elsewhere) over a
@@ -54,81 +57,152 @@ __device__ __forceinline__ float causal_init(const float *e, int n, int step)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// kernel 1: X and Y passes of one strip of one plane, through shared memory
+// kernel 1: X and Y passes, marching down a plane
 // ---------------------------------------------------------------------------------------------------
-constexpr int XY_THREADS = 256;
+constexpr int RB = 16;   // rows per step
+constexpr int SEG = 16;  // X segment length
+// powers of the pole: kPow[j] = z^j
+__device__ constexpr float kPow[17] = {1.0000000000e+00f,  -2.6794922352e-01f, 7.1796786384e-02f,  -1.9237893163e-02f,
+                                       5.1547785351e-03f,  -1.3812189059e-03f, 3.7009653334e-04f,  -9.9167078735e-05f,
+                                       2.6571741746e-05f,  -7.1198775683e-06f, 1.9077656660e-06f,  -5.1118432885e-07f,
+                                       1.3697144399e-07f,  -3.6701392062e-08f, 9.8341095049e-09f,  -2.6350420058e-09f,
+                                       7.0605745940e-10f};
 
-__global__ void __launch_bounds__(XY_THREADS) prefilter_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
-                                                                  int H, int W, int rows_per_strip, int pitch)
+template <int NT>
+__global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restrict__ src, float *__restrict__ dst, int H,
+                                                          int W, long long dst_row, long long dst_plane, int y_chunk,
+                                                          int x_strip, int pitch, int nseg_max)
 {
-    extern __shared__ float tile[];  // [rows][pitch], pitch odd
-    const int z = blockIdx.y;
-    const int y0 = blockIdx.x * rows_per_strip;
-    const int y1 = min(y0 + rows_per_strip, H);        // rows [y0, y1) are written
-    const int ya = max(y0 - K, 0), yb = min(y1 + K, H);  // rows [ya, yb) are staged
-    const int rows = yb - ya;
-    const size_t plane = (size_t)z * H * W;
+    extern __shared__ float smem[];
+    float *tile = smem;                 // [RB][pitch], pitch odd
+    float *ends = smem + RB * pitch;    // [RB][nseg_max]: causal value at the end of each X segment
+    const int z = blockIdx.z;
+    const int x0 = blockIdx.x * x_strip, x1 = min(x0 + x_strip, W);  // columns written by this CTA
+    const int xa = max(x0 - K, 0), xb = min(x1 + K, W);              // columns staged (X warm-up on both sides)
+    const int sw = xb - xa;
+    const int yc0 = blockIdx.y * y_chunk, yc1 = min(yc0 + y_chunk, H);  // rows written
+    const int ra = max(yc0 - K, 0), rb = min(yc1 + K, H);               // rows processed (Y warm-up / look-ahead)
+    const float *splane = src + (size_t)z * H * W;
+    float *dplane = dst + (size_t)z * dst_plane;
     const int tid = threadIdx.x;
+    const int nseg = (sw + SEG - 1) / SEG;
+    const bool stager = tid < sw;
+    const bool has_col = x0 + tid < x1;   // this thread sweeps column x0 + tid along y
+    const int cx = x0 + tid - xa;         // its column inside the tile
+    const int npad = (x1 == W) ? (int)(dst_row - W) : 0;  // pad columns (written as zeros) belong to the last strip
 
-    // stage: the strip is contiguous in memory (complete rows): fully coalesced, any W
-    const float *g = src + plane + (size_t)ya * W;
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int r = warp; r < rows; r += XY_THREADS / 32) {
-        const float *gr = g + (size_t)r * W;
-        float *tr = tile + r * pitch;
-        for (int c = lane; c < W; c += 32) tr[c] = __ldg(gr + c);
+    float pf[RB];
+#pragma unroll
+    for (int i = 0; i < RB; i++) {
+        const int y = ra + i;
+        pf[i] = (stager && y < rb) ? __ldg(splane + (size_t)y * W + xa + tid) : 0.0f;
     }
-    __syncthreads();
+    float cp[K + RB];  // causal Y values of rows [r0 - K, r0 + RB)
+#pragma unroll
+    for (int k = 0; k < K + RB; k++) cp[k] = 0.0f;
+    float prev = 0.0f;
 
-    // X: one thread per staged row, the whole row, reference operation order
-    for (int r = tid; r < rows; r += XY_THREADS) {
-        float *c = tile + r * pitch;
-        float prev = causal_init(c, W, 1);
-        c[0] = prev;
-#pragma unroll 8
-        for (int k = 1; k < W; k++) {
-            prev = causal_step(c[k], prev);
-            c[k] = prev;
+    for (int r0 = ra;; r0 += RB) {
+        const int nrows = min(RB, rb - r0);  // <= 0 once the rows are exhausted (flush steps)
+        __syncthreads();                     // the previous step's column sweep is done with the tile
+        if (nrows > 0) {
+            if (stager) {
+#pragma unroll
+                for (int i = 0; i < RB; i++) tile[i * pitch + tid] = pf[i];
+            }
+#pragma unroll
+            for (int i = 0; i < RB; i++) {
+                const int y = r0 + RB + i;
+                pf[i] = (stager && y < rb) ? __ldg(splane + (size_t)y * W + xa + tid) : 0.0f;
+            }
+            __syncthreads();
+            // ---- X, causal: local recursion per (row, segment) ----
+            for (int task = tid; task < RB * nseg; task += NT) {
+                const int row = task & (RB - 1), seg = task >> 4;
+                if (row >= nrows) continue;
+                float *t = tile + row * pitch + seg * SEG;
+                const int len = min(SEG, sw - seg * SEG);
+                float v;
+                if (seg == 0) v = xa == 0 ? causal_init(t, sw, 1) : __fmul_rn(kWarm, t[0]);
+                else v = __fmul_rn(t[0], kLambda);
+                t[0] = v;
+                for (int k = 1; k < len; k++) {
+                    v = causal_step(t[k], v);
+                    t[k] = v;
+                }
+                ends[row * nseg_max + seg] = v;
+            }
+            __syncthreads();
+            // ---- X, anticausal: local recursion on the carry-corrected causal values ----
+            for (int task = tid; task < RB * nseg; task += NT) {
+                const int row = task & (RB - 1), seg = task >> 4;
+                if (row >= nrows) continue;
+                float *t = tile + row * pitch + seg * SEG;
+                const int len = min(SEG, sw - seg * SEG);
+                const float carry = seg > 0 ? ends[row * nseg_max + seg - 1] : 0.0f;
+                float u;
+                {
+                    const int k = len - 1;
+                    const float c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
+                    // true end of the line: the reference's start formula; otherwise zero carry-in from the right
+                    u = (seg == nseg - 1 && xb == W) ? __fmul_rn(kAnti, c) : __fmul_rn(kPole, -c);
+                    t[k] = u;
+                }
+                for (int k = len - 2; k >= 0; k--) {
+                    const float c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
+                    u = anticausal_step(u, c);
+                    t[k] = u;
+                }
+            }
+            __syncthreads();
+            // ---- X, anticausal carry: the first sample of the next segment feeds the last 12 of this one ----
+            for (int task = tid; task < RB * (nseg - 1); task += NT) {
+                const int row = task & (RB - 1), seg = task >> 4;
+                if (row >= nrows) continue;
+                float *t = tile + row * pitch + seg * SEG;
+                const float carry = t[SEG];
+#pragma unroll
+                for (int k = SEG - K; k < SEG; k++) t[k] = fmaf(kPow[SEG - k], carry, t[k]);
+            }
+            __syncthreads();
         }
-        prev = __fmul_rn(kAnti, prev);
-        c[W - 1] = prev;
-#pragma unroll 8
-        for (int k = W - 2; k >= 0; k--) {
-            prev = anticausal_step(prev, c[k]);
-            c[k] = prev;
+        // ---- Y: one thread per column, rows r0 .. r0+nrows-1 enter the window ----
+        if (has_col) {
+            const float *c = tile + cx;
+            int kstart = 0;
+            if (r0 == ra) {  // first row of the line (true start: exact formula) or of the warm-up
+                prev = ra == 0 ? causal_init(c, min(rb, RB), pitch) : __fmul_rn(kWarm, c[0]);
+                cp[K] = prev;
+                kstart = 1;
+            }
+#pragma unroll
+            for (int k = 0; k < RB; k++) {
+                if (k >= kstart) {
+                    if (r0 + k < rb) prev = causal_step(c[k * pitch], prev);
+                    cp[K + k] = prev;
+                }
+            }
+            const int w0 = r0 - K;                      // row of cp[0]
+            const int last = min(r0 + RB, rb) - 1;      // row where the anticausal recursion (re)starts
+            float a = 0.0f;
+            float *o = dplane + x0 + tid;
+#pragma unroll
+            for (int k = K + RB - 1; k >= 0; k--) {
+                const int y = w0 + k;
+                if (y == last) a = __fmul_rn(kAnti, cp[k]);
+                else if (y < last && y >= ra) a = anticausal_step(a, cp[k]);
+                if (k < RB && y >= yc0 && y < yc1) o[(size_t)y * dst_row] = a;
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) cp[k] = cp[RB + k];
         }
-    }
-    __syncthreads();
-
-    // Y: one thread per column over the staged rows
-    for (int x = tid; x < W; x += XY_THREADS) {
-        float *c = tile + x;
-        float prev;
-        if (ya == 0) prev = causal_init(c, rows, pitch);                 // true start of the line
-        else prev = __fmul_rn(kWarm, c[0]);                             // warm-up start, K rows early
-        c[0] = prev;
-#pragma unroll 8
-        for (int k = 1; k < rows; k++) {
-            prev = causal_step(c[k * pitch], prev);
-            c[k * pitch] = prev;
+        if (tid < npad) {
+            for (int k = 0; k < RB; k++) {
+                const int y = r0 - K + k;
+                if (y >= yc0 && y < yc1) dplane[(size_t)y * dst_row + W + tid] = 0.0f;
+            }
         }
-        // true end of the line: the reference's start formula is exact; otherwise it is the look-ahead start
-        prev = __fmul_rn(kAnti, prev);
-        c[(rows - 1) * pitch] = prev;
-#pragma unroll 8
-        for (int k = rows - 2; k >= 0; k--) {
-            prev = anticausal_step(prev, c[k * pitch]);
-            c[k * pitch] = prev;
-        }
-    }
-    __syncthreads();
-
-    float *o = dst + plane + (size_t)y0 * W;
-    const int roff = y0 - ya;
-    for (int r = warp; r < y1 - y0; r += XY_THREADS / 32) {
-        float *orow = o + (size_t)r * W;
-        const float *tr = tile + (r + roff) * pitch;
-        for (int c = lane; c < W; c += 32) orow[c] = tr[c];
+        if (r0 - K + RB >= yc1) break;
     }
 }
 
@@ -218,49 +292,51 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
 
 int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);  // vt_prefilter.cu
 
-// src -> dst (src != dst).  Returns VT_ERR_UNSUPPORTED when the plane strip does not fit shared memory.
-int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, cudaStream_t st)
+template <int NT>
+int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long dst_row, long long dst_plane, cudaStream_t st)
+{
+    const int x_strip = W <= NT ? W : NT - 2 * K;
+    const int strips = (W + x_strip - 1) / x_strip;
+    const int sw_max = W <= NT ? W : NT;
+    const int pitch = sw_max | 1;
+    const int nseg_max = (sw_max + SEG - 1) / SEG;
+    const size_t smem = ((size_t)RB * pitch + (size_t)RB * nseg_max) * sizeof(float);
+    // y-chunks: ~1000+ CTAs in flight, chunks of at least 64 rows (each pays 2*K rows of warm-up / look-ahead)
+    int chunks = (1200 + D * strips - 1) / (D * strips);
+    const int max_chunks = H / 64 > 0 ? H / 64 : 1;
+    if (chunks > max_chunks) chunks = max_chunks;
+    int y_chunk = (H + chunks - 1) / chunks;
+    chunks = (H + y_chunk - 1) / y_chunk;
+    if (D > 65535 || chunks > 65535) return VT_ERR_UNSUPPORTED;
+    VtProf prof(VT_K_PREFILTER_FUSED, st);
+    prefilter_xy_kernel<NT><<<dim3(strips, chunks, D), NT, smem, st>>>(d_src, d_dst, H, W, dst_row, dst_plane, y_chunk,
+                                                                      x_strip, pitch, nseg_max);
+    return VT_OK;
+}
+
+// src -> dst (src != dst), dst possibly with padded strides.
+int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
+                     cudaStream_t st)
 {
     const int D = d0, H = d1, W = d2;
-    const int pitch = W | 1;
-    // rows per strip: as many as fit ~100 KB of shared memory (2 CTAs per SM), at least 8
-    const size_t budget = 100 * 1024;
-    long rows_fit = (long)(budget / ((size_t)pitch * 4)) - 2 * K;
-    if (rows_fit >= H) rows_fit = H;
-    if (rows_fit < 8) {
-        rows_fit = (long)((220 * 1024) / ((size_t)pitch * 4)) - 2 * K;  // one CTA per SM
-        if (rows_fit < 4) return VT_ERR_UNSUPPORTED;
-        if (rows_fit > H) rows_fit = H;
-    }
-    int rps = (int)rows_fit;
-    const int strips = (H + rps - 1) / rps;
-    rps = (H + strips - 1) / strips;  // balance
-    const int staged = (rps + 2 * K) < H ? (rps + 2 * K) : H;
-    const size_t smem = (size_t)staged * pitch * 4;
-    if (D > 65535) return VT_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(prefilter_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    {
-        VtProf prof(VT_K_PREFILTER_FUSED, st);
-        prefilter_xy_kernel<<<dim3(strips, D), XY_THREADS, smem, st>>>(d_src, d_dst, H, W, rps, pitch);
-    }
+    if (dst_row - W > 32) return VT_ERR_UNSUPPORTED;
+    int rc;
+    if (W <= 128) rc = launch_xy<128>(d_src, d_dst, D, H, W, dst_row, dst_plane, st);
+    else if (W <= 256) rc = launch_xy<256>(d_src, d_dst, D, H, W, dst_row, dst_plane, st);
+    else rc = launch_xy<512>(d_src, d_dst, D, H, W, dst_row, dst_plane, st);
+    if (rc) return rc;
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
     {
-        const size_t cols = (size_t)H * W;
+        // columns of the (padded) plane: pad columns hold zeros and simply stay zero
+        const size_t cols = (size_t)dst_plane;
         const size_t bx = (cols + Z_THREADS - 1) / Z_THREADS;
         if (bx > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
         // the sweep runs in place (reads stay ahead of writes within a column), which rules out z-chunks: a
         // neighbouring chunk's warm-up would read planes this one has already overwritten.  One chunk.
-        int chunks = 1;
-        int z_chunk = (D + chunks - 1) / chunks;
-        z_chunk = (z_chunk + ZB - 1) / ZB * ZB;  // whole steps
-        chunks = (D + z_chunk - 1) / z_chunk;
+        const int z_chunk = (D + ZB - 1) / ZB * ZB;
         VtProf prof(VT_K_PREFILTER_Z, st);
-        prefilter_z_kernel<<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>(d_dst, d_dst, D, cols, z_chunk);
+        prefilter_z_kernel<<<dim3((unsigned)bx, 1), Z_THREADS, 0, st>>>(d_dst, d_dst, D, cols, z_chunk);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());

@@ -20,15 +20,12 @@ constexpr int TX = 32, TY = 8, TZ = 8;
 struct SrcView {
     const float *__restrict__ p;
     int s0, s1, s2;
+    size_t row, plane;  // element strides
     __device__ __forceinline__ float at(int i0, int i1, int i2) const
     {
         // cudaAddressModeBorder (transforms.py:187-189): texels outside the array read as 0
         if ((unsigned)i0 >= (unsigned)s0 || (unsigned)i1 >= (unsigned)s1 || (unsigned)i2 >= (unsigned)s2) return 0.0f;
-        return __ldg(p + ((size_t)i0 * s1 + i1) * s2 + i2);
-    }
-    __device__ __forceinline__ float at_unchecked(int i0, int i1, int i2) const
-    {
-        return __ldg(p + ((size_t)i0 * s1 + i1) * s2 + i2);
+        return __ldg(p + (size_t)i0 * plane + (size_t)i1 * row + i2);
     }
 };
 
@@ -51,8 +48,8 @@ __device__ __forceinline__ float tex3d_emul(const SrcView &s, float x, float y, 
     }
     const bool interior = i0 >= 0 && i1 >= 0 && i2 >= 0 && i0 + 1 < s.s0 && i1 + 1 < s.s1 && i2 + 1 < s.s2;
     if (interior) {
-        const float *q = s.p + ((size_t)i0 * s.s1 + i1) * s.s2 + i2;
-        const size_t sy = s.s2, sz = (size_t)s.s1 * s.s2;
+        const float *q = s.p + (size_t)i0 * s.plane + (size_t)i1 * s.row + i2;
+        const size_t sy = s.row, sz = s.plane;
         c000 = __ldg(q);           c001 = __ldg(q + 1);
         c010 = __ldg(q + sy);      c011 = __ldg(q + sy + 1);
         c100 = __ldg(q + sz);      c101 = __ldg(q + sz + 1);
@@ -123,8 +120,8 @@ __device__ __forceinline__ float cubic_simple(const SrcView &s, float x, float y
     const bool interior = iz >= 1 && iy >= 1 && ix >= 1 && iz + 2 < s.s0 && iy + 2 < s.s1 && ix + 2 < s.s2;
     float result = 0.0f;
     if (interior) {
-        const float *q = s.p + ((size_t)(iz - 1) * s.s1 + (iy - 1)) * s.s2 + (ix - 1);
-        const size_t sy = s.s2, sz = (size_t)s.s1 * s.s2;
+        const float *q = s.p + (size_t)(iz - 1) * s.plane + (size_t)(iy - 1) * s.row + (ix - 1);
+        const size_t sy = s.row, sz = s.plane;
 #pragma unroll
         for (int kz = 0; kz < 4; kz++) {
 #pragma unroll
@@ -161,7 +158,7 @@ __global__ void __launch_bounds__(TX *TY) vt_gather_kernel(const __grid_constant
     const int a1 = blockIdx.y * TY + threadIdx.y;
     if (a2 >= P.o2 || a1 >= P.o1) return;
     const VtMat &M = P.mats[mat];
-    const SrcView s{P.src, P.s0, P.s1, P.s2};
+    const SrcView s{P.src, P.s0, P.s1, P.s2, (size_t)P.src_row, (size_t)P.src_plane};
     const float f0 = (float)P.s0, f1 = (float)P.s1, f2 = (float)P.s2;
     float *__restrict__ dst = P.dst + (size_t)mat * P.dst_batch_stride;
     const float fa1 = (float)a1, fa2 = (float)a2;

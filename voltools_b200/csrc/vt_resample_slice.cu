@@ -18,6 +18,10 @@
 //
 // Replaces the reference's `transform` kernel (voltools/transforms.py:253-282) + linearTex3D / cubicTex3D /
 // cubicTex3DSimple (voltools/kernels/helper_interpolation.h:3-68) for this class of matrices.
+#include <cuda.h>
+
+#include <type_traits>
+
 #include "vt_common.cuh"
 
 namespace {
@@ -25,16 +29,22 @@ namespace {
 constexpr int TS = 16;            // tile edge in (a1, a2)
 constexpr int NT = TS * TS;       // threads per CTA, one column each
 constexpr int BMAX = 32;          // max footprint edge (texels)
-constexpr int PITCH = BMAX + 1;   // shared-memory row pitch (odd: spreads rows over banks)
-constexpr int STAGE = BMAX * PITCH;
-constexpr int NSTAGE = 3;
+constexpr int PITCH_MIN = 32, PITCH_MAX = 40;  // shared-memory row pitch, chosen per matrix by the host
+constexpr int STAGE = BMAX * PITCH_MAX;        // floats per ring stage (5 KB)
+// Ring depth.  A plane step is only ~60 instructions per thread, far shorter than the HBM latency, so many planes
+// must be in flight per CTA: 8 stages x 4-5 resident CTAs keep ~100 KB of loads outstanding per SM.
+constexpr int NSTAGE = 8;
 constexpr int EPT = (BMAX * BMAX + NT - 1) / NT;  // footprint elements per thread (4)
 
-__device__ __forceinline__ void cp_async4_zfill(float *smem_dst, const float *gmem_src, bool valid)
+// 4-byte async copy global -> shared; `take == 0` or `plane_ok == 0` writes a zero instead (ignore-src form: no
+// global access is made), which is how the texture's border mode is reproduced while staging
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const void *gmem_src, unsigned take, unsigned plane_ok)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int n = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
+    asm volatile(
+        "{\n .reg .pred p;\n setp.eq.u32 p, %2, 0;\n setp.eq.or.u32 p, %3, 0, p;\n"
+        " cp.async.ca.shared.global [%0], [%1], 4, p;\n}\n" ::"r"(smem_dst),
+        "l"(gmem_src), "r"(take), "r"(plane_ok)
+        : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -45,12 +55,19 @@ __device__ __forceinline__ void cp_async_wait()
 
 // in-plane coordinate of a column, reference recipe (transforms.py:264-274) with the a0 term dropped: it is an
 // exact no-op because M[r][0] == 0 (fma(a0, 0, t) == t).
-__device__ __forceinline__ float inplane_coord(const float *row, float a1, float a2)
+__host__ __device__ __forceinline__ float inplane_coord(const float *row, float a1, float a2)
 {
+#ifdef __CUDA_ARCH__
     float t = __fmul_rn(a1, row[1]);
     t = __fmaf_rn(a2, row[2], t);
     t = __fadd_rn(row[3], t);
     return __fadd_rn(t, 0.5f);
+#else
+    float t = a1 * row[1];
+    t = fmaf(a2, row[2], t);
+    t = row[3] + t;
+    return t + 0.5f;
+#endif
 }
 
 template <int INTERP>
@@ -62,9 +79,9 @@ struct Taps<VT_LINEAR> {
     static constexpr int LO = 0, HI = 2;  // footprint margins relative to floor(p - 0.5)
     static constexpr int PLANES_BEFORE = 0, PLANES_AFTER = 0;
     float w[4];
-    int off;
+    int r0, r1;  // element offsets of the two tap rows within a stage
     template <int RULE>
-    __device__ void init(float p1, float p2, int ylo, int xlo)
+    __device__ __forceinline__ void init(float p1, float p2, int ylo, int xlo, int pitch)
     {
         int by, bx;
         if (RULE == 0) {
@@ -84,14 +101,15 @@ struct Taps<VT_LINEAR> {
             w[2] = (1.0f - ax) * ay;
             w[3] = ax * ay;
         }
-        off = (by - ylo) * PITCH + (bx - xlo);
+        r0 = (by - ylo) * pitch + (bx - xlo);
+        r1 = r0 + pitch;
     }
     __device__ __forceinline__ float plane(const float *s) const
     {
-        float r = w[0] * s[off];
-        r = fmaf(w[1], s[off + 1], r);
-        r = fmaf(w[2], s[off + PITCH], r);
-        r = fmaf(w[3], s[off + PITCH + 1], r);
+        float r = w[0] * s[r0];
+        r = fmaf(w[1], s[r0 + 1], r);
+        r = fmaf(w[2], s[r1], r);
+        r = fmaf(w[3], s[r1 + 1], r);
         return r;
     }
 };
@@ -102,10 +120,10 @@ struct Taps<VT_CUBIC_SIMPLE> {
     static constexpr int LO = -1, HI = 2;
     static constexpr int PLANES_BEFORE = 1, PLANES_AFTER = 1;
     float w[16];
-    int off;
+    int row[4];
     float wz0, wz1, wz2;
     template <int RULE>
-    __device__ void init(float p1, float p2, int ylo, int xlo)
+    __device__ __forceinline__ void init(float p1, float p2, int ylo, int xlo, int pitch)
     {
         const float cgx = __fadd_rn(p2, -0.5f), cgy = __fadd_rn(p1, -0.5f);
         const float fx0 = floorf(cgx), fy0 = floorf(cgy);
@@ -120,7 +138,9 @@ struct Taps<VT_CUBIC_SIMPLE> {
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++) w[j * 4 + i] = __fmul_rn(wx[i], wy[j]);
-        off = ((int)fy0 - 1 - ylo) * PITCH + ((int)fx0 - 1 - xlo);
+        row[0] = ((int)fy0 - 1 - ylo) * pitch + ((int)fx0 - 1 - xlo);
+#pragma unroll
+        for (int j = 1; j < 4; j++) row[j] = row[j - 1] + pitch;
         wz0 = vt_bspline(-1.0f);  // fraction along axis 0 is exactly 0
         wz1 = vt_bspline(0.0f);
         wz2 = vt_bspline(1.0f);
@@ -131,7 +151,7 @@ struct Taps<VT_CUBIC_SIMPLE> {
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int i = 0; i < 4; i++) r = fmaf(w[j * 4 + i], s[off + j * PITCH + i], r);
+            for (int i = 0; i < 4; i++) r = fmaf(w[j * 4 + i], s[row[j] + i], r);
         return r;
     }
 };
@@ -145,9 +165,9 @@ struct Taps<VT_CUBIC_TEX> {
     static constexpr int LO = -1, HI = 2;
     static constexpr int PLANES_BEFORE = 1, PLANES_AFTER = 1;
     float wa[16], wb[16], wc[16];
-    int offy[4], offx[4];  // footprint row offsets (already * PITCH) and column offsets of the 4x4 taps
+    int adr[8];  // element offsets of taps (row j, x pair k): adr[j*2+k], the pair is (adr, adr+1)
     template <int RULE>
-    __device__ void init(float p1, float p2, int ylo, int xlo)
+    __device__ __forceinline__ void init(float p1, float p2, int ylo, int xlo, int pitch)
     {
         float g0x, g1x, h0x, h1x, g0y, g1y, h0y, h1y, g0z, g1z, h0z, h1z;
         vt_ruijters(p2, g0x, g1x, h0x, h1x);
@@ -155,21 +175,18 @@ struct Taps<VT_CUBIC_TEX> {
         vt_ruijters(8.5f, g0z, g1z, h0z, h1z);  // any texel centre: the fraction along axis 0 is exactly 0
         const float gx[2] = {g0x, g1x}, gy[2] = {g0y, g1y};
         const float hx[2] = {h0x, h1x}, hy[2] = {h0y, h1y};
+        const float gz[3] = {g0z, g0z, g1z};
+        int bx[2], by[2];
         if (RULE == 0) {
             int bz0, c0, bz1, c1;
             vt_tex_fix_hw(h0z, bz0, c0);  // (7, 205)
             vt_tex_fix_hw(h1z, bz1, c1);  // (9, 0)
             const int S[3] = {256 - c0, c0, 256 - c1};
-            const float gz[3] = {g0z, g0z, g1z};
-            int ax[2], bx[2], ay[2], by[2];
+            int ax[2], ay[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 vt_tex_fix_hw(hx[k], bx[k], ax[k]);
                 vt_tex_fix_hw(hy[k], by[k], ay[k]);
-                offx[2 * k] = bx[k] - xlo;
-                offx[2 * k + 1] = bx[k] + 1 - xlo;
-                offy[2 * k] = (by[k] - ylo) * PITCH;
-                offy[2 * k + 1] = (by[k] + 1 - ylo) * PITCH;
             }
 #pragma unroll
             for (int p = 0; p < 3; p++) {
@@ -194,17 +211,11 @@ struct Taps<VT_CUBIC_TEX> {
             vt_tex_fix<2>(h0z, bz0, c0);
             vt_tex_fix<2>(h1z, bz1, c1);
             const float S[3] = {1.0f - c0, c0, 1.0f - c1};
-            const float gz[3] = {g0z, g0z, g1z};
-            int bx[2], by[2];
             float ax[2], ay[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 vt_tex_fix<2>(hx[k], bx[k], ax[k]);
                 vt_tex_fix<2>(hy[k], by[k], ay[k]);
-                offx[2 * k] = bx[k] - xlo;
-                offx[2 * k + 1] = bx[k] + 1 - xlo;
-                offy[2 * k] = (by[k] - ylo) * PITCH;
-                offy[2 * k + 1] = (by[k] + 1 - ylo) * PITCH;
             }
 #pragma unroll
             for (int p = 0; p < 3; p++) {
@@ -221,6 +232,13 @@ struct Taps<VT_CUBIC_TEX> {
                     }
             }
         }
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                adr[(2 * j) * 2 + k] = (by[j] - ylo) * pitch + (bx[k] - xlo);
+                adr[(2 * j + 1) * 2 + k] = adr[(2 * j) * 2 + k] + pitch;
+            }
     }
     __device__ __forceinline__ void plane3(const float *s, float &qa, float &qb, float &qc) const
     {
@@ -229,7 +247,7 @@ struct Taps<VT_CUBIC_TEX> {
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float t = s[offy[j] + offx[i]];
+                const float t = s[adr[j * 2 + (i >> 1)] + (i & 1)];
                 qa = fmaf(wa[j * 4 + i], t, qa);
                 qb = fmaf(wb[j * 4 + i], t, qb);
                 qc = fmaf(wc[j * 4 + i], t, qc);
@@ -237,16 +255,32 @@ struct Taps<VT_CUBIC_TEX> {
     }
 };
 
-template <int INTERP, int RULE, bool OOB_ZERO>
-__global__ void __launch_bounds__(NT) vt_slice_kernel(const __grid_constant__ VtResampleParams P, int z_chunk)
+// Launch-wide staging parameters.  TMA variant: one tensor map over the source volume (x fastest), every plane
+// of a tile's footprint is ONE cp.async.bulk.tensor box load of box_w x box_h texels (coordinates may be negative
+// or past the end: those texels arrive as zeros = the texture's border mode, for whole planes too).
+// Measured on B200: the box must START on a 16-byte boundary of the row (x coordinate a multiple of 4 floats),
+// otherwise the load faults ("illegal instruction"); so the box start is rounded down and the box is 3 wider.
+struct VtSliceStaging {
+    CUtensorMap tmap;
+    int box_w, box_h;      // TMA box (box_w is also the shared-memory row pitch of the TMA variant)
+    unsigned stage_bytes;  // ring stage size in bytes (multiple of 128)
+};
+
+template <int INTERP, int RULE, bool OOB_ZERO, bool TMA>
+__global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : (INTERP == VT_CUBIC_SIMPLE ? 3 : 4))
+    vt_slice_kernel(const __grid_constant__ VtResampleParams P, const __grid_constant__ VtSliceStaging G, int z_chunk)
 {
-    __shared__ float ring[NSTAGE][STAGE];
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // [128 B of mbarriers][NSTAGE stages]
+    unsigned long long *bars = (unsigned long long *)smem_raw;
+    unsigned char *ring = smem_raw + 128;
     using T = Taps<INTERP>;
     const int tid = threadIdx.x;
     const int ntx = (P.o2 + TS - 1) / TS;
     const int tile_y = blockIdx.x / ntx, tile_x = blockIdx.x - tile_y * ntx;
     const int mat = blockIdx.z;
     const VtMat &M = P.mats[mat];
+    const int pitch = TMA ? G.box_w : (int)P.aux[mat];
+    const unsigned stage_bytes = G.stage_bytes;
     const int t0 = (int)M.r[0][3];
     const int zc0 = P.z_begin + blockIdx.y * z_chunk;
     const int zc1 = min(zc0 + z_chunk, P.z_end);
@@ -266,38 +300,47 @@ __global__ void __launch_bounds__(NT) vt_slice_kernel(const __grid_constant__ Vt
         x_min = fminf(fminf(x00, x01), fminf(x10, x11));
         x_max = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
     }
-    // clamp the footprint to one texel around the source: everything further out is border (zero) anyway and
-    // columns that far out are out of bounds; keeps the integer conversions safe for wild matrices
+    // clamp the footprint to a couple of texels around the source: everything further out is border (zero)
+    // anyway and columns that far out are out of bounds; keeps the integer conversions safe for wild matrices
     y_min = fmaxf(y_min, -2.0f); x_min = fmaxf(x_min, -2.0f);
     y_max = fminf(y_max, (float)P.s1 + 2.0f); x_max = fminf(x_max, (float)P.s2 + 2.0f);
     const int ylo = (int)floorf(y_min - 0.5f) + T::LO, yhi = (int)floorf(y_max - 0.5f) + T::HI;
-    const int xlo = (int)floorf(x_min - 0.5f) + T::LO, xhi = (int)floorf(x_max - 0.5f) + T::HI;
-    int bh = min(yhi - ylo + 1, BMAX), bw = min(xhi - xlo + 1, BMAX);  // host guarantees <= BMAX
+    int xlo = (int)floorf(x_min - 0.5f) + T::LO;
+    const int xhi = (int)floorf(x_max - 0.5f) + T::HI;
+    // TMA: the box must start on a 16-byte boundary of the row (the host widened the box by 3 texels for this)
+    if (TMA) xlo &= ~3;
+    int bh = min(yhi - ylo + 1, BMAX), bw = min(xhi - xlo + 1, BMAX);  // host guarantees <= BMAX (<= the TMA box)
     if (bh <= 0 || bw <= 0) bh = bw = 0;  // tile entirely outside the source: nothing to stage
 
-    // per-thread share of the footprint: constant along the march
-    int goff[EPT], soff[EPT];
-    bool gval[EPT];
+    // cp.async variant: per-thread share of the footprint, constant along the march
+    const unsigned ring_s = vt_smem_u32(ring);
+    const unsigned bars_s = vt_smem_u32(bars);
+    unsigned sdst[EPT], goff[EPT], gsz[EPT];  // smem byte address in stage 0, byte offset in a plane, 4 or 0
     const int nel = bh * bw;
+    const int kmax = (nel + NT - 1) / NT;     // uniform
+    if constexpr (!TMA) {
 #pragma unroll
-    for (int k = 0; k < EPT; k++) {
-        const int e = tid + k * NT;
-        const int r = bw > 0 ? e / bw : 0, c = e - r * bw;
-        const int y = ylo + r, x = xlo + c;
-        soff[k] = e < nel ? r * PITCH + c : -1;
-        gval[k] = e < nel && (unsigned)y < (unsigned)P.s1 && (unsigned)x < (unsigned)P.s2;
-        goff[k] = gval[k] ? y * P.s2 + x : 0;
+        for (int k = 0; k < EPT; k++) {
+            const int e = tid + k * NT;
+            const int r = bw > 0 ? e / bw : 0, c = e - r * bw;
+            const int y = ylo + r, x = xlo + c;
+            const bool in = e < nel;
+            const bool val = in && (unsigned)y < (unsigned)P.s1 && (unsigned)x < (unsigned)P.s2;
+            // elements past the footprint are parked on the last float of the stage (never read)
+            sdst[k] = ring_s + (in ? 4u * (unsigned)(r * pitch + c) : stage_bytes - 4u);
+            gsz[k] = val ? 4u : 0u;
+            goff[k] = val ? 4u * (unsigned)(y * (int)P.src_row + x) : 0u;
+        }
+    } else {
+        if (tid == 0) {
+            vt_tma_prefetch_desc(&G.tmap);
+#pragma unroll
+            for (int i = 0; i < NSTAGE; i++) vt_mbar_init(bars_s + 8u * i, 1);
+            vt_mbar_fence_init();
+        }
+        __syncthreads();
     }
-    const size_t plane_elems = (size_t)P.s1 * P.s2;
-    auto issue = [&](int q) {  // stage input plane q (may lie outside the source: all zero)
-        float *dst = ring[((q % NSTAGE) + NSTAGE) % NSTAGE];
-        const bool zin = (unsigned)q < (unsigned)P.s0;
-        const float *src = P.src + (zin ? (size_t)q * plane_elems : 0);
-#pragma unroll
-        for (int k = 0; k < EPT; k++)
-            if (soff[k] >= 0) cp_async4_zfill(dst + soff[k], src + goff[k], zin && gval[k]);
-        cp_async_commit();
-    };
+    const size_t plane_bytes = (size_t)P.src_plane * sizeof(float);
 
     // this thread's column
     const int ty = tid / TS, tx = tid - ty * TS;
@@ -308,21 +351,49 @@ __global__ void __launch_bounds__(NT) vt_slice_kernel(const __grid_constant__ Vt
     // transforms.py:276-278 for the two in-plane axes
     const bool inplane = live && !(p2 < 0 || p1 < 0 || p2 >= (float)P.s2 || p1 >= (float)P.s1);
     T taps;
-    if (inplane) taps.template init<RULE>(p1, p2, ylo, xlo);
-    float *__restrict__ dst = P.dst + (size_t)mat * P.dst_batch_stride + ((size_t)a1 * P.o2 + a2);
+    if (inplane) taps.template init<RULE>(p1, p2, ylo, xlo, pitch);
     const size_t oplane = (size_t)P.o1 * P.o2;
 
     // input planes needed: q = z + t0 + d, d in [-PLANES_BEFORE, PLANES_AFTER]
     const int q_first = zc0 + t0 - T::PLANES_BEFORE, q_last = zc1 - 1 + t0 + T::PLANES_AFTER;
-    issue(q_first);
-    if (q_first + 1 <= q_last) issue(q_first + 1); else cp_async_commit();
+    // running pointers: input plane q (may point outside the source for out-of-range q: never dereferenced then)
+    const char *srcq = (const char *)P.src + (long long)q_first * (long long)plane_bytes;
+    float *dstz = P.dst + (size_t)mat * P.dst_batch_stride + ((size_t)a1 * P.o2 + a2) +
+                  (long long)(q_first - t0 - T::PLANES_AFTER) * (long long)oplane;
+
+    // stage input plane q (gq = its address) into ring stage `st`
+    auto issue = [&](int q, const char *gq, unsigned st) {
+        if constexpr (TMA) {
+            if (tid == 0 && q <= q_last) {
+                const unsigned bar = bars_s + 8u * st;
+                vt_mbar_expect_tx(bar, (unsigned)(G.box_w * G.box_h) * 4u);
+                vt_tma_load_3d(ring_s + st * stage_bytes, &G.tmap, bar, xlo, ylo, q);
+            }
+        } else {
+            if (q <= q_last) {
+                const unsigned zin = (unsigned)q < (unsigned)P.s0 ? 1u : 0u;  // uniform
+                const char *g = zin ? gq : (const char *)P.src;              // keep the (unused) address in bounds
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                    if (k < kmax) cp_async4(sdst[k] + st * stage_bytes, g + goff[k], gsz[k], zin);
+            }
+            cp_async_commit();
+        }
+    };
+
+    // prologue: NSTAGE-1 planes in flight
+#pragma unroll
+    for (int i = 0; i < NSTAGE - 1; i++) issue(q_first + i, srcq + (size_t)i * plane_bytes, (unsigned)i);
     float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // sliding window of per-plane sums
+    unsigned cur = 0, fill = NSTAGE - 1;     // ring stage being consumed / refilled
+    unsigned phase = 0;                      // mbarrier parity of stage `cur`
+    const char *srcf = srcq + (size_t)(NSTAGE - 1) * plane_bytes;  // address of plane q + NSTAGE - 1
     for (int q = q_first; q <= q_last; q++) {
-        cp_async_wait<1>();
+        if constexpr (TMA) vt_mbar_wait(bars_s + 8u * cur, phase);
+        else cp_async_wait<NSTAGE - 2>();
         __syncthreads();  // plane q has landed for every thread; everyone is done with plane q-1
-        if (q + 2 <= q_last) issue(q + 2); else cp_async_commit();
-        const float *s = ring[((q % NSTAGE) + NSTAGE) % NSTAGE];
-        const int z = q - t0 - T::PLANES_AFTER;  // output plane completed by input plane q
+        issue(q + NSTAGE - 1, srcf, fill);  // refills the stage plane q-1 lived in
+        const float *s = (const float *)(ring + cur * stage_bytes);
         float r = 0.0f;
         if (inplane) {
             if constexpr (INTERP == VT_LINEAR) {
@@ -342,18 +413,30 @@ __global__ void __launch_bounds__(NT) vt_slice_kernel(const __grid_constant__ Vt
                 s1 = qb;
             }
         }
-        if (z >= zc0 && live) {
-            const bool zok = (unsigned)(z + t0) < (unsigned)P.s0;  // 0 <= p0 < s0 with p0 = z + t0 + 0.5
-            if (inplane && zok) dst[(size_t)z * oplane] = r;
-            else if (OOB_ZERO) dst[(size_t)z * oplane] = 0.0f;
+        const int zi = q - T::PLANES_AFTER;                 // input plane at the centre of the output voxel
+        if (zi - t0 >= zc0) {                               // uniform: past the warm-up planes
+            const bool ok = inplane && (unsigned)zi < (unsigned)P.s0;  // 0 <= p0 < s0 with p0 = zi + 0.5
+            if (OOB_ZERO) {
+                if (live) *dstz = ok ? r : 0.0f;
+            } else if (ok) {
+                *dstz = r;
+            }
         }
+        srcf += plane_bytes;
+        dstz += oplane;
+        if (++cur == NSTAGE) { cur = 0; phase ^= 1u; }
+        if (++fill == NSTAGE) fill = 0;
     }
 }
 
-// host side: can this batch run on the slice family?
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+// can this batch run on the slice family?
 bool slice_ok(const VtResampleParams &P, int interp)
 {
     if (P.s0 >= 16384) return false;  // h0z = idx + 0.3 must keep its 1/256 quantum (see Taps<VT_CUBIC_TEX>)
+    if (P.src_plane >= (1ll << 29)) return false;  // 32-bit byte offsets inside a plane
     for (int k = 0; k < P.n_mats; k++) {
         const VtMat &M = P.mats[k];
         if (M.r[0][0] != 1.0f || M.r[0][1] != 0.0f || M.r[0][2] != 0.0f) return false;
@@ -369,8 +452,41 @@ bool slice_ok(const VtResampleParams &P, int interp)
     return true;
 }
 
+// Shared-memory row pitch: the warp's 32 columns (2 tile rows x 16) read the same tap of their own footprint
+// position; lanes land on bank (y*pitch + x) mod 32.  The host picks the pitch (cp.async variant: per matrix; TMA
+// variant: the box width) with the fewest bank conflicts over a few sample warps.
+// bank conflicts of one warp's first tap for a given shared-memory pitch (see choose_pitch)
+int pitch_cost(const VtMat &M, int pitch)
+{
+    int cost = 0;
+    for (int sample = 0; sample < 4; sample++) {
+        const int a1_0 = 16 * (1 + 3 * sample) + 2 * sample, a2_0 = 16 * (2 + 5 * sample);
+        unsigned char count[32] = {0};
+        int first_addr[32];
+        int worst = 0;
+        for (int lane = 0; lane < 32; lane++) {
+            const int a1 = a1_0 + lane / 16, a2 = a2_0 + lane % 16;
+            const int y = (int)floorf(inplane_coord(M.r[1], (float)a1, (float)a2) - 0.5f);
+            const int x = (int)floorf(inplane_coord(M.r[2], (float)a1, (float)a2) - 0.5f);
+            const int addr = y * pitch + x + (1 << 20);
+            const int bank = addr & 31;
+            if (count[bank] && first_addr[bank] == addr) continue;  // same word: broadcast
+            if (!count[bank]) first_addr[bank] = addr;
+            if (++count[bank] > worst) worst = count[bank];
+        }
+        cost += worst;
+    }
+    return cost;
+}
+
+// TMA staging is possible when the source rows/planes are 16-byte aligned
+bool tma_ok(const VtResampleParams &P)
+{
+    return (P.src_row % 4) == 0 && (P.src_plane % 4) == 0 && ((uintptr_t)P.src % 16) == 0;
+}
+
 template <int INTERP, int RULE>
-int launch2(const VtResampleParams &P, cudaStream_t st)
+int launch2(VtResampleParams &P, cudaStream_t st)
 {
     const int nz = P.z_end - P.z_begin;
     const int tiles = ((P.o1 + TS - 1) / TS) * ((P.o2 + TS - 1) / TS);
@@ -382,10 +498,68 @@ int launch2(const VtResampleParams &P, cudaStream_t st)
     chunks = (nz + z_chunk - 1) / z_chunk;
     dim3 grid(tiles, chunks, P.n_mats);
     if (chunks > 65535 || P.n_mats > 65535) return VT_ERR_UNSUPPORTED;
+    const bool tma = tma_ok(P) && !(P.flags & VT_STAGE_CP_ASYNC);
+    VtSliceStaging G;
+    memset(&G, 0, sizeof G);
+    if (tma) {
+        // box: the largest footprint of the batch (+5 texels of filter support / rounding), rows padded to 16 B
+        float ext_y = 0.0f, ext_x = 0.0f;
+        for (int k = 0; k < P.n_mats; k++) {
+            ext_y = fmaxf(ext_y, (fabsf(P.mats[k].r[1][1]) + fabsf(P.mats[k].r[1][2])) * (float)(TS - 1));
+            ext_x = fmaxf(ext_x, (fabsf(P.mats[k].r[2][1]) + fabsf(P.mats[k].r[2][2])) * (float)(TS - 1));
+        }
+        const int need_h = min(BMAX, (int)floorf(ext_y + 0.1f) + 6), need_w = min(BMAX, (int)floorf(ext_x + 0.1f) + 6);
+        // + 3: the box start is rounded down to a multiple of 4 texels (16-byte aligned start address)
+        int best_w = (need_w + 3 + 3) / 4 * 4, best_cost = 1 << 30;
+        for (int w = (need_w + 3 + 3) / 4 * 4; w <= need_w + 3 + 12 && w <= PITCH_MAX; w += 4) {
+            const int c = pitch_cost(P.mats[0], w) + pitch_cost(P.mats[P.n_mats / 2], w);
+            if (c < best_cost) {
+                best_cost = c;
+                best_w = w;
+            }
+        }
+        G.box_w = best_w;
+        G.box_h = need_h;
+        G.stage_bytes = ((unsigned)(G.box_w * G.box_h * 4) + 127u) & ~127u;
+        const unsigned long long gdim[3] = {(unsigned long long)P.s2, (unsigned long long)P.s1, (unsigned long long)P.s0};
+        const unsigned long long gstr[2] = {(unsigned long long)P.src_row * 4, (unsigned long long)P.src_plane * 4};
+        const unsigned box[3] = {(unsigned)G.box_w, (unsigned)G.box_h, 1};
+        const int rc = vt_encode_tmap_3d(&G.tmap, P.src, gdim, gstr, box);
+        if (rc) return rc;
+    } else {
+        for (int k = 0; k < P.n_mats; k++) {
+            int best = 33, best_cost = 1 << 30;
+            for (int pitch = PITCH_MIN; pitch <= PITCH_MAX; pitch++) {
+                const int c = pitch_cost(P.mats[k], pitch);
+                if (c < best_cost) {
+                    best_cost = c;
+                    best = pitch;
+                }
+            }
+            P.aux[k] = (unsigned char)best;
+        }
+        G.stage_bytes = STAGE * 4;
+    }
+    const size_t smem = 128 + (size_t)NSTAGE * G.stage_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const int mx = 128 + NSTAGE * STAGE * 4;
+        VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr_set = true;
+    }
     {
         VtProf prof(VT_K_SLICE_LINEAR + INTERP, st);
-        if (P.flags & VT_OOB_ZERO) vt_slice_kernel<INTERP, RULE, true><<<grid, NT, 0, st>>>(P, z_chunk);
-        else vt_slice_kernel<INTERP, RULE, false><<<grid, NT, 0, st>>>(P, z_chunk);
+        const bool zero = (P.flags & VT_OOB_ZERO) != 0;
+        if (tma) {
+            if (zero) vt_slice_kernel<INTERP, RULE, true, true><<<grid, NT, smem, st>>>(P, G, z_chunk);
+            else vt_slice_kernel<INTERP, RULE, false, true><<<grid, NT, smem, st>>>(P, G, z_chunk);
+        } else {
+            if (zero) vt_slice_kernel<INTERP, RULE, true, false><<<grid, NT, smem, st>>>(P, G, z_chunk);
+            else vt_slice_kernel<INTERP, RULE, false, false><<<grid, NT, smem, st>>>(P, G, z_chunk);
+        }
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
@@ -393,7 +567,7 @@ int launch2(const VtResampleParams &P, cudaStream_t st)
 }
 
 template <int INTERP>
-int launch1(const VtResampleParams &P, cudaStream_t st)
+int launch1(VtResampleParams &P, cudaStream_t st)
 {
     if (INTERP != VT_CUBIC_SIMPLE && (P.flags & VT_WEIGHTS_EXACT)) return launch2<INTERP, 2>(P, st);
     return launch2<INTERP, 0>(P, st);
@@ -403,7 +577,7 @@ int launch1(const VtResampleParams &P, cudaStream_t st)
 
 int vt_slice_supported(const VtResampleParams &P, int interp) { return slice_ok(P, interp) ? 1 : 0; }
 
-int vt_launch_slice(const VtResampleParams &P, int interp, cudaStream_t st)
+int vt_launch_slice(VtResampleParams &P, int interp, cudaStream_t st)
 {
     if (P.z_end <= P.z_begin || P.o1 <= 0 || P.o2 <= 0 || P.n_mats <= 0) return VT_OK;
     switch (interp) {

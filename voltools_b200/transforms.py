@@ -213,18 +213,23 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
             else:
                 src_t = vin.owner
                 src_ptr = vin.ptr
+            src_strides = None
             if needs_prefilter:
-                # never clobber the caller's array: the coefficients go to a private buffer (out of place)
-                coef_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
-                _native.prefilter(src_ptr, shape, dev, stream, dst_ptr=coef_t.data_ptr())
+                # never clobber the caller's array: the coefficients go to a private buffer (out of place) whose
+                # rows are padded to 16 bytes (TMA staging works for any width)
+                row = _native.padded_row(shape[2])
+                src_strides = (row, shape[1] * row)
+                coef_t = torch.empty((shape[0], shape[1], row), dtype=torch.float32, device=f'cuda:{dev}')
+                _native.prefilter(src_ptr, shape, dev, stream, dst_ptr=coef_t.data_ptr(), dst_strides=src_strides)
                 src_t, src_ptr = coef_t, coef_t.data_ptr()
             if vout is None:
                 out_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
                 _native.affine(src_ptr, shape, out_t.data_ptr(), shape, m, interp, _native.OOB_ZERO, device=dev,
-                               stream=stream)
+                               stream=stream, src_strides=src_strides)
                 result = out_t.cpu().numpy()
             else:
-                _native.affine(src_ptr, shape, vout.ptr, shape, m, interp, _native.OOB_SKIP, device=dev, stream=stream)
+                _native.affine(src_ptr, shape, vout.ptr, shape, m, interp, _native.OOB_SKIP, device=dev, stream=stream,
+                               src_strides=src_strides)
                 result = None
             del src_t
 

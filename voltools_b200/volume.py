@@ -48,28 +48,42 @@ class StaticVolume:
                 src = vin.owner if isinstance(vin.owner, torch.Tensor) \
                     else torch.as_tensor(vin.owner, device=f'cuda:{self._dev}')
                 self._coeffs = src.to(f'cuda:{self._dev}', copy=True)
+            self._strides = (self.shape[2], self.shape[1] * self.shape[2])
             if needs_prefilter:
+                # coefficients live in a buffer whose rows are padded to 16 bytes (TMA staging for any width)
                 raw = self._coeffs
-                self._coeffs = torch.empty_like(raw)
+                row = _native.padded_row(self.shape[2])
+                self._strides = (row, self.shape[1] * row)
+                self._coeffs = torch.empty((self.shape[0], self.shape[1], row), dtype=torch.float32,
+                                           device=f'cuda:{self._dev}')
                 _native.prefilter(raw.data_ptr(), self.shape, self._dev, _stream(self._dev),
-                                  dst_ptr=self._coeffs.data_ptr())
+                                  dst_ptr=self._coeffs.data_ptr(), dst_strides=self._strides)
                 del raw
 
     # -- resident buffer access (used by the multi-GPU layer) -------------------------------------------
     @property
     def coefficients(self):
-        """The resident (prefiltered, for filt_* modes) volume as a torch CUDA tensor."""
+        """The resident (prefiltered, for filt_* modes) volume as a torch CUDA tensor view of shape `shape`
+        (rows may be padded: the view is then non-contiguous)."""
+        return self._coeffs[:, :, :self.shape[2]]
+
+    @property
+    def coefficient_buffer(self):
+        """The resident buffer itself, shape (d0, d1, padded row); what the multi-GPU layer broadcasts."""
         return self._coeffs
 
     @classmethod
-    def from_coefficients(cls, coeffs, interpolation: str = 'linear'):
-        """Wrap an already prepared coefficient tensor (e.g. one received by NCCL broadcast) without copying."""
+    def from_coefficients(cls, coeffs, interpolation: str = 'linear', width: int = None):
+        """Wrap an already prepared coefficient buffer (e.g. one received by NCCL broadcast) without copying.
+        `coeffs` is contiguous with shape (d0, d1, row); `width` <= row is the true extent of axis 2."""
         self = cls.__new__(cls)
         self.device = f'gpu:{coeffs.device.index}'
         self.interpolation = interpolation
         self._interp, _ = _INTERPOLATIONS[interpolation]
         self._dev = coeffs.device.index
-        self.shape = tuple(int(s) for s in coeffs.shape)
+        row = int(coeffs.shape[2])
+        self.shape = (int(coeffs.shape[0]), int(coeffs.shape[1]), row if width is None else int(width))
+        self._strides = (row, int(coeffs.shape[1]) * row)
         self.d_type = np.float32
         self._coeffs = coeffs
         return self
@@ -90,10 +104,10 @@ class StaticVolume:
             if vout is None:
                 out_t = torch.empty(self.shape, dtype=torch.float32, device=f'cuda:{self._dev}')
                 _native.affine(self._coeffs.data_ptr(), self.shape, out_t.data_ptr(), self.shape, m, self._interp,
-                               _native.OOB_ZERO, device=self._dev, stream=stream)
+                               _native.OOB_ZERO, device=self._dev, stream=stream, src_strides=self._strides)
             else:
                 _native.affine(self._coeffs.data_ptr(), self.shape, vout.ptr, self.shape, m, self._interp,
-                               _native.OOB_SKIP, device=self._dev, stream=stream)
+                               _native.OOB_SKIP, device=self._dev, stream=stream, src_strides=self._strides)
             if profile:
                 t1.record()
                 t1.synchronize()
@@ -122,7 +136,7 @@ class StaticVolume:
                 out_t, ptr = None, vout.ptr
                 flags = _native.OOB_ZERO if zero_fill else _native.OOB_SKIP
             _native.affine(self._coeffs.data_ptr(), self.shape, ptr, self.shape, m, self._interp, flags,
-                           device=self._dev, stream=stream)
+                           device=self._dev, stream=stream, src_strides=self._strides)
         return out_t
 
     def transform(self, scale: Union[float, Tuple[float, float, float], np.ndarray] = None,
