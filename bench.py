@@ -243,6 +243,12 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
     torch.cuda.synchronize()
     uuid = str(getattr(torch.cuda.get_device_properties(dev), 'uuid', dev))
     clocks = ClockSampler(uuid if uuid.startswith('GPU-') or uuid.isdigit() else 'GPU-' + uuid)
+    # keep the GPU under the same load for >= 0.5 s before the timed region so that nvidia-smi (100 ms period)
+    # gets samples of the clocks this workload runs at; the sampler stays on through the timed region
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:
+        step()
+        torch.cuda.synchronize()
     l0 = _native.launch_count()
     sec = timed(torch, step, args.steps, 0, barrier)
     launches = _native.launch_count() - l0

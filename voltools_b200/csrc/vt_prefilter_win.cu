@@ -68,6 +68,57 @@ __device__ constexpr float kPow[17] = {1.0000000000e+00f,  -2.6794922352e-01f, 7
                                        1.3697144399e-07f,  -3.6701392062e-08f, 9.8341095049e-09f,  -2.6350420058e-09f,
                                        7.0605745940e-10f};
 
+// X pass pieces for one (row, segment) task; LEN is the compile-time segment length for full segments (SEG) so
+// that the recursions unroll completely and the pole powers become immediates, or 0 for the ragged last segment.
+template <int LEN>
+__device__ __forceinline__ float xseg_causal(float *t, int len, int seg, bool line_start, int sw)
+{
+    float v;
+    if (seg == 0) v = line_start ? causal_init(t, sw, 1) : __fmul_rn(kWarm, t[0]);
+    else v = __fmul_rn(t[0], kLambda);
+    t[0] = v;
+    if (LEN) {
+#pragma unroll
+        for (int k = 1; k < LEN; k++) {
+            v = causal_step(t[k], v);
+            t[k] = v;
+        }
+    } else {
+        for (int k = 1; k < len; k++) {
+            v = causal_step(t[k], v);
+            t[k] = v;
+        }
+    }
+    return v;
+}
+
+template <int LEN>
+__device__ __forceinline__ void xseg_anticausal(float *t, int len, float carry, bool line_end)
+{
+    if (LEN) {
+        // full segment: never the end of the line's last segment unless line_end (then len == SEG too)
+        float c = t[LEN - 1];  // k = 15 >= K: no carry correction
+        float u = line_end ? __fmul_rn(kAnti, c) : __fmul_rn(kPole, -c);
+        t[LEN - 1] = u;
+#pragma unroll
+        for (int k = LEN - 2; k >= 0; k--) {
+            c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
+            u = anticausal_step(u, c);
+            t[k] = u;
+        }
+    } else {
+        int k = len - 1;
+        float c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
+        float u = line_end ? __fmul_rn(kAnti, c) : __fmul_rn(kPole, -c);
+        t[k] = u;
+        for (k = len - 2; k >= 0; k--) {
+            c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
+            u = anticausal_step(u, c);
+            t[k] = u;
+        }
+    }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restrict__ src, float *__restrict__ dst, int H,
                                                           int W, long long dst_row, long long dst_plane, int y_chunk,
@@ -82,21 +133,21 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
     const int sw = xb - xa;
     const int yc0 = blockIdx.y * y_chunk, yc1 = min(yc0 + y_chunk, H);  // rows written
     const int ra = max(yc0 - K, 0), rb = min(yc1 + K, H);               // rows processed (Y warm-up / look-ahead)
-    const float *splane = src + (size_t)z * H * W;
-    float *dplane = dst + (size_t)z * dst_plane;
     const int tid = threadIdx.x;
     const int nseg = (sw + SEG - 1) / SEG;
+    const int last_len = sw - (nseg - 1) * SEG;
     const bool stager = tid < sw;
     const bool has_col = x0 + tid < x1;   // this thread sweeps column x0 + tid along y
     const int cx = x0 + tid - xa;         // its column inside the tile
     const int npad = (x1 == W) ? (int)(dst_row - W) : 0;  // pad columns (written as zeros) belong to the last strip
+    // running pointers
+    const float *sp = src + (size_t)z * H * W + (size_t)ra * W + xa + tid;  // row being prefetched, this thread's column
+    float *op = dst + (size_t)z * dst_plane + (long long)(ra - K) * dst_row + x0 + tid;  // row r0 - K of the output
 
     float pf[RB];
 #pragma unroll
-    for (int i = 0; i < RB; i++) {
-        const int y = ra + i;
-        pf[i] = (stager && y < rb) ? __ldg(splane + (size_t)y * W + xa + tid) : 0.0f;
-    }
+    for (int i = 0; i < RB; i++) pf[i] = (stager && ra + i < rb) ? __ldg(sp + (size_t)i * W) : 0.0f;
+    sp += (size_t)RB * W;
     float cp[K + RB];  // causal Y values of rows [r0 - K, r0 + RB)
 #pragma unroll
     for (int k = 0; k < K + RB; k++) cp[k] = 0.0f;
@@ -110,26 +161,25 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
 #pragma unroll
                 for (int i = 0; i < RB; i++) tile[i * pitch + tid] = pf[i];
             }
+            if (r0 + 2 * RB <= rb) {  // uniform: the next step is a full one
+                if (stager) {
 #pragma unroll
-            for (int i = 0; i < RB; i++) {
-                const int y = r0 + RB + i;
-                pf[i] = (stager && y < rb) ? __ldg(splane + (size_t)y * W + xa + tid) : 0.0f;
+                    for (int i = 0; i < RB; i++) pf[i] = __ldg(sp + (size_t)i * W);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < RB; i++) pf[i] = (stager && r0 + RB + i < rb) ? __ldg(sp + (size_t)i * W) : 0.0f;
             }
+            sp += (size_t)RB * W;
             __syncthreads();
             // ---- X, causal: local recursion per (row, segment) ----
             for (int task = tid; task < RB * nseg; task += NT) {
                 const int row = task & (RB - 1), seg = task >> 4;
                 if (row >= nrows) continue;
                 float *t = tile + row * pitch + seg * SEG;
-                const int len = min(SEG, sw - seg * SEG);
                 float v;
-                if (seg == 0) v = xa == 0 ? causal_init(t, sw, 1) : __fmul_rn(kWarm, t[0]);
-                else v = __fmul_rn(t[0], kLambda);
-                t[0] = v;
-                for (int k = 1; k < len; k++) {
-                    v = causal_step(t[k], v);
-                    t[k] = v;
-                }
+                if (seg < nseg - 1 || last_len == SEG) v = xseg_causal<SEG>(t, SEG, seg, xa == 0, sw);
+                else v = xseg_causal<0>(t, last_len, seg, xa == 0, sw);
                 ends[row * nseg_max + seg] = v;
             }
             __syncthreads();
@@ -138,21 +188,10 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
                 const int row = task & (RB - 1), seg = task >> 4;
                 if (row >= nrows) continue;
                 float *t = tile + row * pitch + seg * SEG;
-                const int len = min(SEG, sw - seg * SEG);
                 const float carry = seg > 0 ? ends[row * nseg_max + seg - 1] : 0.0f;
-                float u;
-                {
-                    const int k = len - 1;
-                    const float c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
-                    // true end of the line: the reference's start formula; otherwise zero carry-in from the right
-                    u = (seg == nseg - 1 && xb == W) ? __fmul_rn(kAnti, c) : __fmul_rn(kPole, -c);
-                    t[k] = u;
-                }
-                for (int k = len - 2; k >= 0; k--) {
-                    const float c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
-                    u = anticausal_step(u, c);
-                    t[k] = u;
-                }
+                const bool line_end = seg == nseg - 1 && xb == W;
+                if (seg < nseg - 1 || last_len == SEG) xseg_anticausal<SEG>(t, SEG, carry, line_end);
+                else xseg_anticausal<0>(t, last_len, carry, line_end);
             }
             __syncthreads();
             // ---- X, anticausal carry: the first sample of the next segment feeds the last 12 of this one ----
@@ -167,42 +206,66 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
             __syncthreads();
         }
         // ---- Y: one thread per column, rows r0 .. r0+nrows-1 enter the window ----
+        const int w0 = r0 - K;  // row of cp[0]
         if (has_col) {
             const float *c = tile + cx;
-            int kstart = 0;
-            if (r0 == ra) {  // first row of the line (true start: exact formula) or of the warm-up
-                prev = ra == 0 ? causal_init(c, min(rb, RB), pitch) : __fmul_rn(kWarm, c[0]);
-                cp[K] = prev;
-                kstart = 1;
-            }
+            if (r0 > ra && nrows == RB && w0 >= ra) {
+                // steady state (uniform): a full step strictly inside the processed rows
 #pragma unroll
-            for (int k = 0; k < RB; k++) {
-                if (k >= kstart) {
-                    if (r0 + k < rb) prev = causal_step(c[k * pitch], prev);
+                for (int k = 0; k < RB; k++) {
+                    prev = causal_step(c[k * pitch], prev);
                     cp[K + k] = prev;
                 }
-            }
-            const int w0 = r0 - K;                      // row of cp[0]
-            const int last = min(r0 + RB, rb) - 1;      // row where the anticausal recursion (re)starts
-            float a = 0.0f;
-            float *o = dplane + x0 + tid;
+                float a = __fmul_rn(kAnti, cp[K + RB - 1]);
+                if (w0 >= yc0 && w0 + RB <= yc1) {
 #pragma unroll
-            for (int k = K + RB - 1; k >= 0; k--) {
-                const int y = w0 + k;
-                if (y == last) a = __fmul_rn(kAnti, cp[k]);
-                else if (y < last && y >= ra) a = anticausal_step(a, cp[k]);
-                if (k < RB && y >= yc0 && y < yc1) o[(size_t)y * dst_row] = a;
+                    for (int k = K + RB - 2; k >= 0; k--) {
+                        a = anticausal_step(a, cp[k]);
+                        if (k < RB) op[(size_t)k * dst_row] = a;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = K + RB - 2; k >= 0; k--) {
+                        a = anticausal_step(a, cp[k]);
+                        if (k < RB && w0 + k >= yc0 && w0 + k < yc1) op[(size_t)k * dst_row] = a;
+                    }
+                }
+            } else {
+                int kstart = 0;
+                if (r0 == ra) {  // first row of the line (true start: exact formula) or of the warm-up
+                    prev = ra == 0 ? causal_init(c, min(rb, RB), pitch) : __fmul_rn(kWarm, c[0]);
+                    cp[K] = prev;
+                    kstart = 1;
+                }
+#pragma unroll
+                for (int k = 0; k < RB; k++) {
+                    if (k >= kstart) {
+                        if (r0 + k < rb) prev = causal_step(c[k * pitch], prev);
+                        cp[K + k] = prev;
+                    }
+                }
+                const int last = min(r0 + RB, rb) - 1;  // row where the anticausal recursion (re)starts
+                float a = 0.0f;
+#pragma unroll
+                for (int k = K + RB - 1; k >= 0; k--) {
+                    const int y = w0 + k;
+                    if (y == last) a = __fmul_rn(kAnti, cp[k]);
+                    else if (y < last && y >= ra) a = anticausal_step(a, cp[k]);
+                    if (k < RB && y >= yc0 && y < yc1) op[(size_t)k * dst_row] = a;
+                }
             }
 #pragma unroll
             for (int k = 0; k < K; k++) cp[k] = cp[RB + k];
         }
         if (tid < npad) {
+            float *pp = op + (W - x0);  // column W + tid
             for (int k = 0; k < RB; k++) {
-                const int y = r0 - K + k;
-                if (y >= yc0 && y < yc1) dplane[(size_t)y * dst_row + W + tid] = 0.0f;
+                const int y = w0 + k;
+                if (y >= yc0 && y < yc1) pp[(size_t)k * dst_row] = 0.0f;
             }
         }
-        if (r0 - K + RB >= yc1) break;
+        op += (size_t)RB * dst_row;
+        if (w0 + RB >= yc1) break;
     }
 }
 
