@@ -29,7 +29,23 @@ constexpr int MAX_BRICK_BYTES = 72 * 1024;    // 3 CTAs per SM
 struct VtBrickStaging {
     CUtensorMap tmap;
     int bw, bh, bd;  // box = brick dimensions (bw multiple of 4; also the row pitch)
+    int layout;      // how a warp's 32 lanes tile (a1, a2): 0 = 2 x 16, 1 = 4 x 8 (chosen against bank conflicts)
 };
+
+// thread -> position inside the 8 x 8 x 16 tile (tz selects a group of VPT consecutive planes)
+__host__ __device__ __forceinline__ void thread_pos(int tid, int layout, int &tx, int &ty, int &tz)
+{
+    if (layout == 0) {
+        tx = tid & 15;
+        ty = (tid >> 4) & 7;
+        tz = tid >> 7;
+    } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        tx = (warp & 1) * 8 + (lane & 7);
+        ty = ((warp >> 1) & 1) * 4 + (lane >> 3);
+        tz = warp >> 2;
+    }
+}
 
 struct Brick {
     const float *s;
@@ -174,7 +190,8 @@ __global__ void __launch_bounds__(NT, 3)
     }
     const Brick b{brick, G.bw, G.bw * G.bh, lo[0], lo[1], lo[2]};
     // this thread's voxels: (a0 = a0_0 + tz*VPT + v, a1, a2)
-    const int tx = tid & (TX - 1), ty = (tid >> 4) & (TY - 1), tz = tid >> 7;
+    int tx, ty, tz;
+    thread_pos(tid, G.layout, tx, ty, tz);
     const int a1 = a1_0 + ty, a2 = a2_0 + tx;
     const bool live = a1 < P.o1 && a2 < P.o2;
     const float f0 = (float)P.s0, f1 = (float)P.s1, f2 = (float)P.s2;
@@ -229,12 +246,78 @@ bool brick_dims(const VtResampleParams &P, int interp, int &bw, int &bh, int &bd
     return (size_t)bw * bh * bd * 4 <= (size_t)MAX_BRICK_BYTES;
 }
 
+// host copy of the coordinate recipe (same operations; used only to predict bank conflicts)
+float host_coord(const float *row, float a0, float a1, float a2)
+{
+    float t = a1 * row[1];
+    t = fmaf(a0, row[0], t);
+    t = fmaf(a2, row[2], t);
+    return (row[3] + t) + 0.5f;
+}
+
+// Shared-memory bank conflicts are what bounds the cubic brick kernels (64 four-byte loads per voxel): a warp's
+// lanes hit bank (z*bw*bh + y*bw + x) mod 32.  The brick may be padded (bw by multiples of 4 texels, bh by a few
+// rows) and the warp may tile the output 2 x 16 or 4 x 8; pick the combination with the fewest predicted conflicts
+// for the first matrix of the batch over a couple of sample tiles.
+void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
+{
+    const VtMat &M = P.mats[0];
+    constexpr int NS = 2;
+    static thread_local int iz[2][NS][NT], iy[2][NS][NT], ix[2][NS][NT];
+    for (int layout = 0; layout < 2; layout++)
+        for (int smp = 0; smp < NS; smp++) {
+            const int a0_0 = P.z_begin + ((P.z_end - P.z_begin) / 3 * (smp + 1)) / TZ * TZ;
+            const int a1_0 = (P.o1 / 3 * (smp + 1)) / TY * TY, a2_0 = (P.o2 / 3 * (2 - smp)) / TX * TX;
+            for (int tid = 0; tid < NT; tid++) {
+                int tx, ty, tz;
+                thread_pos(tid, layout, tx, ty, tz);
+                const float a0 = (float)(a0_0 + tz * VPT), a1 = (float)(a1_0 + ty), a2 = (float)(a2_0 + tx);
+                iz[layout][smp][tid] = (int)floorf(host_coord(M.r[0], a0, a1, a2) - 0.5f);
+                iy[layout][smp][tid] = (int)floorf(host_coord(M.r[1], a0, a1, a2) - 0.5f);
+                ix[layout][smp][tid] = (int)floorf(host_coord(M.r[2], a0, a1, a2) - 0.5f);
+            }
+        }
+    const int bw0 = G.bw, bh0 = G.bh;
+    long best = -1;
+    for (int bw = bw0; bw <= bw0 + 8; bw += 4)
+        for (int bh = bh0; bh <= bh0 + 7; bh++) {
+            if ((size_t)bw * bh * G.bd * 4 > (size_t)MAX_BRICK_BYTES) continue;
+            for (int layout = 0; layout < 2; layout++) {
+                long cost = 0;
+                for (int smp = 0; smp < NS; smp++)
+                    for (int w = 0; w < NT / 32; w++) {
+                        unsigned char cnt[32] = {0};
+                        int first[32];
+                        int worst = 0;
+                        for (int l = 0; l < 32; l++) {
+                            const int t = w * 32 + l;
+                            const int addr = (iz[layout][smp][t] * bh + iy[layout][smp][t]) * bw + ix[layout][smp][t];
+                            const int bank = addr & 31;
+                            if (cnt[bank] && first[bank] == addr) continue;
+                            if (!cnt[bank]) first[bank] = addr;
+                            if (++cnt[bank] > worst) worst = cnt[bank];
+                        }
+                        cost += worst;
+                    }
+                // prefer smaller bricks on ties (less shared memory, less L2 traffic)
+                cost = cost * 4096 + (long)bw * bh / 8;
+                if (best < 0 || cost < best) {
+                    best = cost;
+                    G.bw = bw;
+                    G.bh = bh;
+                    G.layout = layout;
+                }
+            }
+        }
+}
+
 template <int INTERP, int RULE>
 int launch2(const VtResampleParams &P, cudaStream_t st)
 {
     VtBrickStaging G;
     memset(&G, 0, sizeof G);
     if (!brick_dims(P, INTERP, G.bw, G.bh, G.bd)) return VT_ERR_UNSUPPORTED;
+    if (INTERP != VT_LINEAR) tune_brick(P, G);
     const unsigned long long gdim[3] = {(unsigned long long)P.s2, (unsigned long long)P.s1, (unsigned long long)P.s0};
     const unsigned long long gstr[2] = {(unsigned long long)P.src_row * 4, (unsigned long long)P.src_plane * 4};
     const unsigned box[3] = {(unsigned)G.bw, (unsigned)G.bh, (unsigned)G.bd};
