@@ -364,13 +364,84 @@ def run_modes(args, torch, vt, dev):
     return res
 
 
+def run_sweep(args, torch, vt, dev, barrier, reduce_max):
+    """configs[2]: StaticVolume 256^3 filt_bspline, 180-angle sweep rotation=(0,i,0); root prefilters, one broadcast of
+    the coefficient buffer (NCCL), angles split across ranks.  Strong scaling: the 180 angles are the fixed job."""
+    from voltools_b200 import _native, multigpu
+    import torch.distributed as dist
+    rank, _, world = dist_env()
+    n = args.size if args.size != 512 else 256
+    shape = (n, n, n)
+    c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+    mats = [vt.utils.transform_matrix(rotation=(0, i, 0), rotation_order='rzxz', center=c) for i in range(180)]
+    vol = torch.rand(shape, device=f'cuda:{dev}', generator=torch.Generator(f'cuda:{dev}').manual_seed(7)) \
+        if rank == 0 else None
+    mine = multigpu.split_batch(len(mats), world, rank)
+    out = torch.empty((len(mine),) + shape, device=f'cuda:{dev}')
+    eng = multigpu.CudaEngine(dev)
+
+    def step():
+        if world > 1:
+            outs, _ = multigpu.sweep(vol, mats, 'filt_bspline', src=0, engine=eng)
+        else:
+            buf, width = eng.prepare(vol, 'filt_bspline')
+            sv = vt.StaticVolume.from_coefficients(buf, 'filt_bspline', width)
+            sv.affine_many(mats, output=out, zero_fill=True)
+
+    l0 = _native.launch_count()
+    sec = reduce_max(timed(torch, step, args.steps, max(3, args.warmup), barrier))
+    launches = _native.launch_count() - l0
+    value = len(mats) * n ** 3 * args.steps / sec / 1e9
+    peak, _ = peaks()
+    return {'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'configs[2]: StaticVolume {n}^3 filt_bspline, 180-angle sweep rotation=(0,i,0), '
+                                   'prefilter on rank 0 + 1 NCCL broadcast + angles split across ranks',
+                       'parallelism': f'dp{world}', 'l2': 'outputs (180 volumes) exceed L2; the coefficient volume is '
+                                                         'L2-resident by design'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'note': '8 B/voxel/matrix', 'frac': 8.0 * value / peak / world, 'peak': peak}}
+
+
+def run_zslab(args, torch, vt, dev, barrier, reduce_max):
+    """configs[4]: one large filt_bspline full-affine transform, output z-slabs split across ranks."""
+    from voltools_b200 import _native, multigpu
+    rank, _, world = dist_env()
+    n = args.size
+    shape = (n, n, n)
+    c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+    m = vt.utils.transform_matrix(center=c, **FULL_AFFINE)
+    vol = torch.rand(shape, device=f'cuda:{dev}', generator=torch.Generator(f'cuda:{dev}').manual_seed(7)) \
+        if rank == 0 else None
+    eng = multigpu.CudaEngine(dev)
+
+    def step():
+        if world > 1:
+            multigpu.zslab_affine(vol, m, 'filt_bspline', src=0, engine=eng)
+        else:
+            buf, width = eng.prepare(vol, 'filt_bspline')
+            eng.resample_slab(buf, width, 'filt_bspline', m, 0, n)
+
+    l0 = _native.launch_count()
+    sec = reduce_max(timed(torch, step, args.steps, max(3, args.warmup), barrier))
+    launches = _native.launch_count() - l0
+    value = n ** 3 * args.steps / sec / 1e9
+    return {'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'configs[4]: {n}^3 filt_bspline full affine, prefilter on rank 0 + NCCL broadcast of '
+                                   'the coefficients + output z-slabs across ranks', 'parallelism': f'dp{world}'},
+            'gpu_launches': int(launches)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes'])
+    ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes', 'sweep', 'zslab'])
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--batch', type=int, default=None, help='volumes per step (default 8; smaller only for profiling)')
@@ -411,6 +482,18 @@ def main():
         res = run_modes(args, torch, vt, dev)
         if rank == 0:
             print(json.dumps({'metric': METRIC, 'workload': f'modes {args.size}^3', 'modes': res}))
+        return
+    if args.workload in ('sweep', 'zslab'):
+        if world == 1:  # single-process: the helpers still want a process group for get_rank()
+            import torch.distributed as dist
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            os.environ.setdefault('MASTER_PORT', '29533')
+            dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device(f'cuda:{dev}'))
+        line = (run_sweep if args.workload == 'sweep' else run_zslab)(args, torch, vt, dev, barrier, reduce_max)
+        if rank == 0:
+            print(json.dumps(line))
+        import torch.distributed as dist
+        dist.destroy_process_group()
         return
     line = run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max)
     if rank == 0:

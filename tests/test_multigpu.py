@@ -1,0 +1,105 @@
+"""CPU suite for the multi-GPU layer: world_size-2 gloo processes, the oracle standing in for the CUDA engine.
+
+What is tested is the host-side orchestration of voltools_b200/multigpu.py (partitioning of matrices and z-slabs,
+metadata + buffer broadcast from the root, result placement); the kernels themselves are covered by the -m gpu suite.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle
+from voltools_b200 import multigpu
+from voltools_b200.utils import transform_matrix
+
+
+def test_partitions_cover_everything_once():
+    for n in (0, 1, 2, 7, 180, 181, 1024):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                blk = multigpu.split_batch(n, world, r)
+                seen += list(blk)
+                assert len(blk) in (n // world, n // world + 1)
+            assert seen == list(range(n))
+            z = [multigpu.split_slabs(n, world, r) for r in range(world)]
+            assert z[0][0] == 0 and z[-1][1] == n and all(z[i][1] == z[i + 1][0] for i in range(world - 1))
+
+
+class OracleEngine:
+    """CPU stand-in for CudaEngine (test infrastructure): same interface, oracle arithmetic, torch CPU tensors."""
+
+    def prepare(self, volume, interpolation):
+        import torch
+        v = oracle.prefilter(volume) if interpolation.startswith('filt') else np.asarray(volume, np.float32)
+        return torch.from_numpy(np.ascontiguousarray(v)), v.shape[2]
+
+    def empty(self, shape):
+        import torch
+        return torch.empty(shape, dtype=torch.float32)
+
+    @staticmethod
+    def _mode(interpolation):  # the buffer already holds coefficients
+        return interpolation.replace('filt_', '')
+
+    def resample_many(self, buffer, width, interpolation, matrices):
+        import torch
+        v = buffer.numpy()[:, :, :width]
+        return torch.from_numpy(np.stack([oracle.affine(v, m, self._mode(interpolation)) for m in matrices]))
+
+    def resample_slab(self, buffer, width, interpolation, matrix, z0, z1):
+        import torch
+        v = buffer.numpy()[:, :, :width]
+        full = oracle.affine(v, matrix, self._mode(interpolation), z_range=(z0, z1))
+        return torch.from_numpy(full[z0:z1].copy())
+
+
+def _worker(rank, world, init_file, outdir):
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group('gloo', init_method=f'file://{init_file}', rank=rank, world_size=world)
+    try:
+        shape = (13, 16, 18)
+        rng = np.random.default_rng(42)
+        vol = rng.random(shape, dtype=np.float32)
+        c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+        mats = [transform_matrix(rotation=(0, a, 0), center=c) for a in range(0, 180, 36)]
+        eng = OracleEngine()
+        # only the root has the samples
+        out, idx = multigpu.sweep(vol if rank == 0 else None, mats, 'filt_bspline', src=0, engine=eng)
+        np.savez(os.path.join(outdir, f'sweep_{rank}.npz'), out=out.numpy(), idx=np.array(idx))
+        m = transform_matrix(rotation=(20, 30, 40), translation=(1, -2, 0.5), center=c)
+        slab, (z0, z1) = multigpu.zslab_affine(vol if rank == 0 else None, m, 'bspline_simple', src=0, engine=eng)
+        full = multigpu.gather_slabs(slab, dst=0)
+        np.savez(os.path.join(outdir, f'slab_{rank}.npz'), slab=slab.numpy(), z=np.array([z0, z1]),
+                 full=full.numpy() if full is not None else np.zeros(0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sweep_and_zslab_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        init_file = os.path.join(d, 'rendezvous')
+        mp.spawn(_worker, args=(world, init_file, d), nprocs=world, join=True)
+        shape = (13, 16, 18)
+        vol = np.random.default_rng(42).random(shape, dtype=np.float32)
+        c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+        mats = [transform_matrix(rotation=(0, a, 0), center=c) for a in range(0, 180, 36)]
+        seen = []
+        for r in range(world):
+            z = np.load(os.path.join(d, f'sweep_{r}.npz'))
+            for o, i in zip(z['out'], z['idx']):
+                assert np.array_equal(o, oracle.affine(vol, mats[int(i)], 'filt_bspline'))
+                seen.append(int(i))
+        assert sorted(seen) == list(range(len(mats)))
+        m = transform_matrix(rotation=(20, 30, 40), translation=(1, -2, 0.5), center=c)
+        want = oracle.affine(vol, m, 'bspline_simple')
+        z0 = np.load(os.path.join(d, 'slab_0.npz'))
+        z1 = np.load(os.path.join(d, 'slab_1.npz'))
+        assert tuple(z0['z']) == (0, 7) and tuple(z1['z']) == (7, 13)
+        assert np.array_equal(z0['slab'], want[0:7]) and np.array_equal(z1['slab'], want[7:13])
+        assert np.array_equal(z0['full'], want)

@@ -383,22 +383,28 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
     DeviceGuard g(c->device);
     if (g.status) return g.status;
     const size_t nsrc = (size_t)s0 * s1 * s2, plane_out = (size_t)o1 * o2;
-    int rc = ensure(&c->d_src, &c->cap_src, nsrc * 4);
+    // device copies keep their rows padded to 16 bytes so that the resampling kernels can stage with TMA whatever
+    // the width is; the upload itself does the padding (2-D copy), the prefilter writes padded rows directly
+    const long long row = ((long long)s2 + 3) / 4 * 4, plane = row * s1;
+    int rc = ensure(&c->d_dst, &c->cap_dst, (size_t)o0 * plane_out * 4);
     if (rc) return rc;
-    rc = ensure(&c->d_dst, &c->cap_dst, (size_t)o0 * plane_out * 4);
-    if (rc) return rc;
-    // upload (the source is needed whole before any output plane can be gathered under a general affine map)
-    VT_CUDA(cudaMemcpyAsync(c->d_src, h_src, nsrc * 4, cudaMemcpyHostToDevice, c->st_k));
-    const float *sampled = c->d_src;
-    long long row = s2, plane = (long long)s1 * s2;
+    const float *sampled;
     if (prefilter) {
-        row = ((long long)s2 + 3) / 4 * 4;  // rows padded to 16 bytes: TMA staging for any width
-        plane = row * s1;
+        rc = ensure(&c->d_src, &c->cap_src, nsrc * 4);
+        if (rc) return rc;
         rc = ensure(&c->d_coef, &c->cap_coef, (size_t)plane * s0 * 4);
         if (rc) return rc;
+        // upload (the source is needed whole before any output plane can be gathered under a general affine map)
+        VT_CUDA(cudaMemcpyAsync(c->d_src, h_src, nsrc * 4, cudaMemcpyHostToDevice, c->st_k));
         rc = vt_prefilter_strided_f32(c->d_src, c->d_coef, s0, s1, s2, row, plane, 0, -1, c->st_k);
         if (rc) return rc;
         sampled = c->d_coef;
+    } else {
+        rc = ensure(&c->d_src, &c->cap_src, (size_t)plane * s0 * 4);
+        if (rc) return rc;
+        VT_CUDA(cudaMemcpy2DAsync(c->d_src, (size_t)row * 4, h_src, (size_t)s2 * 4, (size_t)s2 * 4, (size_t)s0 * s1,
+                                  cudaMemcpyHostToDevice, c->st_k));
+        sampled = c->d_src;
     }
     // output=None semantics (transforms.py:207-210): skipped voxels are zero -> fused as VT_OOB_ZERO.
     // z-slabs: the kernel of slab i+1 overlaps the download of slab i.

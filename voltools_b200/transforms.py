@@ -209,19 +209,23 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
             stream = _stream(dev)
             if host_in:
                 src_t = torch.from_numpy(np.ascontiguousarray(volume, dtype=np.float32)).to(f'cuda:{dev}')
-                src_ptr = src_t.data_ptr()
             else:
-                src_t = vin.owner
-                src_ptr = vin.ptr
-            src_strides = None
+                src_t = vin.owner if isinstance(vin.owner, torch.Tensor) \
+                    else torch.as_tensor(vin.owner, device=f'cuda:{dev}')
+            src_ptr = src_t.data_ptr()
+            # the sampled volume lives in a private buffer whose rows are padded to 16 bytes: the kernels can then
+            # stage it with TMA whatever the width is.  The prefilter writes that layout directly (out of place: the
+            # caller's array is never modified); an unfiltered volume with an odd width is copied once.
+            row = _native.padded_row(shape[2])
+            src_strides = (row, shape[1] * row)
             if needs_prefilter:
-                # never clobber the caller's array: the coefficients go to a private buffer (out of place) whose
-                # rows are padded to 16 bytes (TMA staging works for any width)
-                row = _native.padded_row(shape[2])
-                src_strides = (row, shape[1] * row)
                 coef_t = torch.empty((shape[0], shape[1], row), dtype=torch.float32, device=f'cuda:{dev}')
                 _native.prefilter(src_ptr, shape, dev, stream, dst_ptr=coef_t.data_ptr(), dst_strides=src_strides)
                 src_t, src_ptr = coef_t, coef_t.data_ptr()
+            elif row != shape[2]:
+                pad_t = torch.empty((shape[0], shape[1], row), dtype=torch.float32, device=f'cuda:{dev}')
+                pad_t[:, :, :shape[2]].copy_(src_t)
+                src_t, src_ptr = pad_t, pad_t.data_ptr()
             if vout is None:
                 out_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
                 _native.affine(src_ptr, shape, out_t.data_ptr(), shape, m, interp, _native.OOB_ZERO, device=dev,

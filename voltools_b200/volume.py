@@ -48,17 +48,21 @@ class StaticVolume:
                 src = vin.owner if isinstance(vin.owner, torch.Tensor) \
                     else torch.as_tensor(vin.owner, device=f'cuda:{self._dev}')
                 self._coeffs = src.to(f'cuda:{self._dev}', copy=True)
-            self._strides = (self.shape[2], self.shape[1] * self.shape[2])
+            # the resident buffer has rows padded to 16 bytes (TMA staging for any width); the prefilter writes that
+            # layout directly, an unfiltered volume with an odd width is copied into it once
+            raw = self._coeffs
+            row = _native.padded_row(self.shape[2])
+            self._strides = (row, self.shape[1] * row)
             if needs_prefilter:
-                # coefficients live in a buffer whose rows are padded to 16 bytes (TMA staging for any width)
-                raw = self._coeffs
-                row = _native.padded_row(self.shape[2])
-                self._strides = (row, self.shape[1] * row)
                 self._coeffs = torch.empty((self.shape[0], self.shape[1], row), dtype=torch.float32,
                                            device=f'cuda:{self._dev}')
                 _native.prefilter(raw.data_ptr(), self.shape, self._dev, _stream(self._dev),
                                   dst_ptr=self._coeffs.data_ptr(), dst_strides=self._strides)
-                del raw
+            elif row != self.shape[2]:
+                self._coeffs = torch.zeros((self.shape[0], self.shape[1], row), dtype=torch.float32,
+                                           device=f'cuda:{self._dev}')
+                self._coeffs[:, :, :self.shape[2]].copy_(raw)
+            del raw
 
     # -- resident buffer access (used by the multi-GPU layer) -------------------------------------------
     @property
