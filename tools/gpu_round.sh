@@ -3,7 +3,7 @@
 # usage (under gpurun): bash tools/gpu_round.sh [top-kernel-regex]
 set -u
 mkdir -p gpurun_out
-REGEX=${1:-vt_gather_kernel}
+REGEX=${1:-vt_slice_kernel}
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
