@@ -353,3 +353,53 @@ def test_errors(vt):
         vt.utils.rotation_matrix((1, 2, 3), rotation_units='grad')
     with pytest.raises(ValueError):
         vt.utils.rotation_matrix((1, 2, 3), rotation_order='xyz')
+
+
+@pytest.mark.parametrize('n', [512])
+def test_full_size_properties(vt, n):
+    """BASELINE sizes, where the oracle would take minutes: size-independent properties instead.
+    identity (exact for linear, reconstruction for prefilter + cubic), linearity, z-slab composition, batching."""
+    import torch
+    N = vt._native
+    shape = (n, n, n)
+    g = torch.Generator('cuda').manual_seed(11)
+    u = torch.rand(shape, device='cuda', generator=g)
+    eye = np.identity(4, dtype=np.float32)
+    out = torch.empty_like(u)
+    vt.affine(u, eye, interpolation='linear', output=out, device='gpu')
+    assert torch.equal(out, u), 'linear identity must be exact (alpha = 0 at texel centres)'
+    vt.affine(u, eye, interpolation='filt_bspline_simple', output=out, device='gpu')
+    inner = (slice(16, -16),) * 3
+    assert float((out[inner] - u[inner]).abs().max()) <= 2e-5, 'prefilter followed by cubic sampling at the knots'
+    vt.affine(u, eye, interpolation='filt_bspline', output=out, device='gpu')
+    assert float((out[inner] - u[inner]).abs().max()) <= 2e-3 * 12, 'same through the 8-fetch path (8-bit weights)'
+    # linearity of the whole pipeline (prefilter + resample) under a general matrix
+    c = _center(shape)
+    m = vt.utils.transform_matrix(scale=(1.1, 0.9, 1.05), shear=(0.05, -0.03, 0.02), rotation=(30, 45, 60),
+                                  translation=(5.5, -3.25, 2.0), center=c)
+    v = torch.rand(shape, device='cuda', generator=g)
+    tu, tv, tw = torch.zeros_like(u), torch.zeros_like(u), torch.zeros_like(u)
+    for mode, tol in (('filt_bspline_simple', 2e-5), ('linear', 1e-5)):
+        vt.affine(u, m, interpolation=mode, output=tu, device='gpu')
+        vt.affine(v, m, interpolation=mode, output=tv, device='gpu')
+        vt.affine(2.0 * u - 0.5 * v, m, interpolation=mode, output=tw, device='gpu')
+        assert float((tw - (2.0 * tu - 0.5 * tv)).abs().max()) <= tol * 12, mode
+    # z-slabs written by separate calls reproduce the single call bit for bit (both kernel families)
+    rot = vt.utils.transform_matrix(rotation=(0, 33, 0), center=c)
+    for mat in (m, rot):
+        full = torch.zeros(shape, device='cuda')
+        N.affine(u.data_ptr(), shape, full.data_ptr(), shape, mat, 2, N.OOB_ZERO)
+        parts = torch.full(shape, -1.0, device='cuda')
+        for z0, z1 in ((0, 100), (100, 101), (101, 400), (400, n)):
+            N.affine(u.data_ptr(), shape, parts.data_ptr(), shape, mat, 2, N.OOB_ZERO, z_range=(z0, z1))
+        assert torch.equal(full, parts)
+    # rotating by +a then -a about the centre returns the interior of a smooth volume
+    zz, yy, xx = torch.meshgrid(*(torch.linspace(-1, 1, n, device='cuda'),) * 3, indexing='ij')
+    smooth = torch.exp(-4 * (zz ** 2 + yy ** 2 + xx ** 2)) * torch.cos(6 * xx) * torch.sin(5 * yy + 1)
+    fwd = vt.utils.transform_matrix(rotation=(0, 20, 0), center=c)
+    bwd = vt.utils.transform_matrix(rotation=(0, -20, 0), center=c)
+    a, b = torch.zeros_like(smooth), torch.zeros_like(smooth)
+    vt.affine(smooth, fwd, interpolation='filt_bspline_simple', output=a, device='gpu')
+    vt.affine(a, bwd, interpolation='filt_bspline_simple', output=b, device='gpu')
+    core = (slice(n // 4, -n // 4),) * 3
+    assert float((b[core] - smooth[core]).abs().max()) <= 1e-4
