@@ -172,6 +172,29 @@ __device__ __forceinline__ void vt_tma_prefetch_desc(const void *tmap)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// packed float32 pairs: sm_100 issues two IEEE fp32 FMAs per lane with one FFMA2 (fma.rn.f32x2); ptxas folds a
+// pair built from the same scalar, vt_pk(t, t), into the instruction's broadcast operand form.  Each half is an
+// ordinary fma.rn.f32, so results are bit-identical to the scalar code.
+// ---------------------------------------------------------------------------------------------------
+typedef unsigned long long vt_f2;
+__device__ __forceinline__ vt_f2 vt_pk(float lo, float hi)
+{
+    vt_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void vt_unpk(vt_f2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ vt_f2 vt_fma2(vt_f2 a, vt_f2 b, vt_f2 c)
+{
+    vt_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // cubic B-spline pieces
 // ---------------------------------------------------------------------------------------------------
 // bspline() of voltools/kernels/bspline.h:114-122, in its compiled operation order

@@ -322,19 +322,29 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
         }
     }
     // ---- steady state ----
+    // raw[] holds the next ZB planes of the look-ahead region; it is reloaded for the following step right after
+    // the causal recursion has consumed it, so those loads are in flight during the anticausal sweep and the stores
+    // (2 x ZB loads outstanding per thread: enough to cover the HBM latency at ~13 warps per SM)
+    float raw[ZB];
+#pragma unroll
+    for (int k = 0; k < ZB; k++) {
+        const int zz = zw + K + k;
+        raw[k] = zz < D ? s[(size_t)zz * cols] : 0.0f;
+    }
     for (; zw < zc1; zw += ZB) {
         // causal values of the next ZB planes (look-ahead region moves forward)
-        float raw[ZB];
-#pragma unroll
-        for (int k = 0; k < ZB; k++) {
-            const int zz = zw + K + k;
-            raw[k] = zz < D ? s[(size_t)zz * cols] : 0.0f;
-        }
 #pragma unroll
         for (int k = 0; k < ZB; k++) {
             const int zz = zw + K + k;
             if (zz < D) prev = causal_step(raw[k], prev);
             cp[K + k] = prev;
+        }
+        if (zw + ZB < zc1) {
+#pragma unroll
+            for (int k = 0; k < ZB; k++) {
+                const int zz = zw + ZB + K + k;
+                raw[k] = zz < D ? s[(size_t)zz * cols] : 0.0f;
+            }
         }
         // anticausal from the last available plane of the window back to zw
         const int last = min(zw + K + ZB, D) - 1;  // plane index where the recursion (re)starts

@@ -30,10 +30,12 @@ constexpr int TS = 16;            // tile edge in (a1, a2)
 constexpr int NT = TS * TS;       // threads per CTA, one column each
 constexpr int BMAX = 32;          // max footprint edge (texels)
 constexpr int PITCH_MIN = 32, PITCH_MAX = 40;  // shared-memory row pitch, chosen per matrix by the host
-constexpr int STAGE = BMAX * PITCH_MAX;        // floats per ring stage (5 KB)
-// Ring depth.  A plane step is only ~60 instructions per thread, far shorter than the HBM latency, so many planes
-// must be in flight per CTA: 8 stages x 4-5 resident CTAs keep ~100 KB of loads outstanding per SM.
-constexpr int NSTAGE = 8;
+constexpr int STAGE = BMAX * PITCH_MAX;        // floats per staged plane, cp.async variant (5 KB)
+// Ring: NSTAGE stages of PPS planes each (per interpolator, see Taps<>).  One stage = one mbarrier round trip, one
+// __syncthreads and one TMA box of depth PPS, so the per-stage overhead (~45 instructions per thread) is shared by
+// PPS planes; the planes of a stage are also paired in FFMA2 instructions.  A plane step is far shorter than the
+// HBM latency, so several planes must be in flight per CTA: (NSTAGE-1)*PPS planes x 2-4 resident CTAs.
+constexpr int MAX_NSTAGE = 8;
 constexpr int EPT = (BMAX * BMAX + NT - 1) / NT;  // footprint elements per thread (4)
 
 // 4-byte async copy global -> shared; `take == 0` or `plane_ok == 0` writes a zero instead (ignore-src form: no
@@ -78,6 +80,7 @@ template <>
 struct Taps<VT_LINEAR> {
     static constexpr int LO = 0, HI = 2;  // footprint margins relative to floor(p - 0.5)
     static constexpr int PLANES_BEFORE = 0, PLANES_AFTER = 0;
+    static constexpr int PPS = 4, NSTAGE = 3;
     float w[4];
     int r0, r1;  // element offsets of the two tap rows within a stage
     template <int RULE>
@@ -104,13 +107,20 @@ struct Taps<VT_LINEAR> {
         r0 = (by - ylo) * pitch + (bx - xlo);
         r1 = r0 + pitch;
     }
-    __device__ __forceinline__ float plane(const float *s) const
+    // per-plane sums of the stage's four planes (plane p starts at s + p*pe); planes are paired in FFMA2s
+    __device__ __forceinline__ void planes(const float *s, int pe, float (&out)[PPS]) const
     {
-        float r = w[0] * s[r0];
-        r = fmaf(w[1], s[r0 + 1], r);
-        r = fmaf(w[2], s[r1], r);
-        r = fmaf(w[3], s[r1 + 1], r);
-        return r;
+        const float *s1 = s + pe, *s2 = s1 + pe, *s3 = s2 + pe;
+        vt_f2 a01 = 0ull, a23 = 0ull;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o = (k < 2 ? r0 : r1) + (k & 1);
+            const vt_f2 ww = vt_pk(w[k], w[k]);
+            a01 = vt_fma2(vt_pk(s[o], s1[o]), ww, a01);
+            a23 = vt_fma2(vt_pk(s2[o], s3[o]), ww, a23);
+        }
+        vt_unpk(a01, out[0], out[1]);
+        vt_unpk(a23, out[2], out[3]);
     }
 };
 
@@ -119,6 +129,7 @@ template <>
 struct Taps<VT_CUBIC_SIMPLE> {
     static constexpr int LO = -1, HI = 2;
     static constexpr int PLANES_BEFORE = 1, PLANES_AFTER = 1;
+    static constexpr int PPS = 2, NSTAGE = 4;
     float w[16];
     int row[4];
     float wz0, wz1, wz2;
@@ -145,14 +156,17 @@ struct Taps<VT_CUBIC_SIMPLE> {
         wz1 = vt_bspline(0.0f);
         wz2 = vt_bspline(1.0f);
     }
-    __device__ __forceinline__ float plane(const float *s) const
+    // in-plane sums of the stage's two planes, one FFMA2 per tap: {plane q, plane q+1} x {w, w}
+    __device__ __forceinline__ void planes(const float *s, int pe, float (&out)[PPS]) const
     {
-        float r = 0.0f;
+        const float *s1 = s + pe;
+        vt_f2 acc = 0ull;
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int i = 0; i < 4; i++) r = fmaf(w[j * 4 + i], s[row[j] + i], r);
-        return r;
+            for (int i = 0; i < 4; i++)
+                acc = vt_fma2(vt_pk(s[row[j] + i], s1[row[j] + i]), vt_pk(w[j * 4 + i], w[j * 4 + i]), acc);
+        vt_unpk(acc, out[0], out[1]);
     }
 };
 
@@ -164,6 +178,7 @@ template <>
 struct Taps<VT_CUBIC_TEX> {
     static constexpr int LO = -1, HI = 2;
     static constexpr int PLANES_BEFORE = 1, PLANES_AFTER = 1;
+    static constexpr int PPS = 2, NSTAGE = 4;
     float wa[16], wb[16], wc[16];
     int adr[8];  // element offsets of taps (row j, x pair k): adr[j*2+k], the pair is (adr, adr+1)
     template <int RULE>
@@ -240,18 +255,26 @@ struct Taps<VT_CUBIC_TEX> {
                 adr[(2 * j + 1) * 2 + k] = adr[(2 * j) * 2 + k] + pitch;
             }
     }
-    __device__ __forceinline__ void plane3(const float *s, float &qa, float &qb, float &qc) const
+    // A-, B- and C-weighted sums of the stage's two planes: per tap {wa, wb} x {t, t} for each plane (the scalar
+    // texel is FFMA2's broadcast operand) and {t0, t1} x {wc, wc}: 3 FFMA2 instead of 6 FFMA
+    __device__ __forceinline__ void planes3(const float *s, int pe, float (&qa)[PPS], float (&qb)[PPS], float (&qc)[PPS]) const
     {
-        qa = qb = qc = 0.0f;
+        const float *s1 = s + pe;
+        vt_f2 ab0 = 0ull, ab1 = 0ull, c01 = 0ull;
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float t = s[adr[j * 2 + (i >> 1)] + (i & 1)];
-                qa = fmaf(wa[j * 4 + i], t, qa);
-                qb = fmaf(wb[j * 4 + i], t, qb);
-                qc = fmaf(wc[j * 4 + i], t, qc);
+                const int o = adr[j * 2 + (i >> 1)] + (i & 1);
+                const float t0 = s[o], t1 = s1[o];
+                const vt_f2 wab = vt_pk(wa[j * 4 + i], wb[j * 4 + i]);
+                ab0 = vt_fma2(wab, vt_pk(t0, t0), ab0);
+                ab1 = vt_fma2(wab, vt_pk(t1, t1), ab1);
+                c01 = vt_fma2(vt_pk(t0, t1), vt_pk(wc[j * 4 + i], wc[j * 4 + i]), c01);
             }
+        vt_unpk(ab0, qa[0], qb[0]);
+        vt_unpk(ab1, qa[1], qb[1]);
+        vt_unpk(c01, qc[0], qc[1]);
     }
 };
 
@@ -262,7 +285,8 @@ struct Taps<VT_CUBIC_TEX> {
 // otherwise the load faults ("illegal instruction"); so the box start is rounded down and the box is 3 wider.
 struct VtSliceStaging {
     CUtensorMap tmap;
-    int box_w, box_h;      // TMA box (box_w is also the shared-memory row pitch of the TMA variant)
+    int box_w, box_h;      // TMA box (box_w is also the shared-memory row pitch of the TMA variant); box depth = PPS
+    int plane_elems;       // floats between consecutive planes of a stage
     unsigned stage_bytes;  // ring stage size in bytes (multiple of 128)
 };
 
@@ -270,10 +294,12 @@ template <int INTERP, int RULE, bool OOB_ZERO, bool TMA>
 __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : (INTERP == VT_CUBIC_SIMPLE ? 3 : 4))
     vt_slice_kernel(const __grid_constant__ VtResampleParams P, const __grid_constant__ VtSliceStaging G, int z_chunk)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];  // [128 B of mbarriers][NSTAGE stages]
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // [128 B of mbarriers][NSTAGE stages of PPS planes]
     unsigned long long *bars = (unsigned long long *)smem_raw;
     unsigned char *ring = smem_raw + 128;
     using T = Taps<INTERP>;
+    constexpr int PPS = T::PPS, NSTAGE = T::NSTAGE;
+    static_assert(NSTAGE <= MAX_NSTAGE, "mbarrier block holds MAX_NSTAGE barriers");
     const int tid = threadIdx.x;
     const int ntx = (P.o2 + TS - 1) / TS;
     const int tile_y = blockIdx.x / ntx, tile_x = blockIdx.x - tile_y * ntx;
@@ -281,6 +307,7 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : (INTERP == VT
     const VtMat &M = P.mats[mat];
     const int pitch = TMA ? G.box_w : (int)P.aux[mat];
     const unsigned stage_bytes = G.stage_bytes;
+    const int pe = G.plane_elems;
     const int t0 = (int)M.r[0][3];
     const int zc0 = P.z_begin + blockIdx.y * z_chunk;
     const int zc1 = min(zc0 + z_chunk, P.z_end);
@@ -326,8 +353,8 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : (INTERP == VT
             const int y = ylo + r, x = xlo + c;
             const bool in = e < nel;
             const bool val = in && (unsigned)y < (unsigned)P.s1 && (unsigned)x < (unsigned)P.s2;
-            // elements past the footprint are parked on the last float of the stage (never read)
-            sdst[k] = ring_s + (in ? 4u * (unsigned)(r * pitch + c) : stage_bytes - 4u);
+            // elements past the footprint are parked on the last float of the plane (never read)
+            sdst[k] = ring_s + (in ? 4u * (unsigned)(r * pitch + c) : 4u * (unsigned)pe - 4u);
             gsz[k] = val ? 4u : 0u;
             goff[k] = val ? 4u * (unsigned)(y * (int)P.src_row + x) : 0u;
         }
@@ -361,69 +388,86 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : (INTERP == VT
     float *dstz = P.dst + (size_t)mat * P.dst_batch_stride + ((size_t)a1 * P.o2 + a2) +
                   (long long)(q_first - t0 - T::PLANES_AFTER) * (long long)oplane;
 
-    // stage input plane q (gq = its address) into ring stage `st`
+    // stage input planes q .. q+PPS-1 (gq = address of plane q) into ring stage `st`
     auto issue = [&](int q, const char *gq, unsigned st) {
         if constexpr (TMA) {
             if (tid == 0 && q <= q_last) {
                 const unsigned bar = bars_s + 8u * st;
-                vt_mbar_expect_tx(bar, (unsigned)(G.box_w * G.box_h) * 4u);
-                vt_tma_load_3d(ring_s + st * stage_bytes, &G.tmap, bar, xlo, ylo, q);
+                vt_mbar_expect_tx(bar, (unsigned)(G.box_w * G.box_h * PPS) * 4u);
+                vt_tma_load_3d(ring_s + st * stage_bytes, &G.tmap, bar, xlo, ylo, q);  // planes past the source: zeros
             }
         } else {
-            if (q <= q_last) {
-                const unsigned zin = (unsigned)q < (unsigned)P.s0 ? 1u : 0u;  // uniform
-                const char *g = zin ? gq : (const char *)P.src;              // keep the (unused) address in bounds
 #pragma unroll
-                for (int k = 0; k < EPT; k++)
-                    if (k < kmax) cp_async4(sdst[k] + st * stage_bytes, g + goff[k], gsz[k], zin);
+            for (int p = 0; p < PPS; p++) {
+                if (q + p <= q_last) {
+                    const unsigned zin = (unsigned)(q + p) < (unsigned)P.s0 ? 1u : 0u;            // uniform
+                    const char *g = zin ? gq + (size_t)p * plane_bytes : (const char *)P.src;      // keep the address in bounds
+                    const unsigned sb = st * stage_bytes + 4u * (unsigned)(p * pe);
+#pragma unroll
+                    for (int k = 0; k < EPT; k++)
+                        if (k < kmax) cp_async4(sdst[k] + sb, g + goff[k], gsz[k], zin);
+                }
             }
             cp_async_commit();
         }
     };
 
-    // prologue: NSTAGE-1 planes in flight
+    // prologue: NSTAGE-1 stages in flight
 #pragma unroll
-    for (int i = 0; i < NSTAGE - 1; i++) issue(q_first + i, srcq + (size_t)i * plane_bytes, (unsigned)i);
+    for (int i = 0; i < NSTAGE - 1; i++) issue(q_first + i * PPS, srcq + (size_t)(i * PPS) * plane_bytes, (unsigned)i);
     float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // sliding window of per-plane sums
     unsigned cur = 0, fill = NSTAGE - 1;     // ring stage being consumed / refilled
     unsigned phase = 0;                      // mbarrier parity of stage `cur`
-    const char *srcf = srcq + (size_t)(NSTAGE - 1) * plane_bytes;  // address of plane q + NSTAGE - 1
-    for (int q = q_first; q <= q_last; q++) {
+    const char *srcf = srcq + (size_t)((NSTAGE - 1) * PPS) * plane_bytes;  // address of plane q + (NSTAGE-1)*PPS
+    for (int q = q_first; q <= q_last; q += PPS) {
         if constexpr (TMA) vt_mbar_wait(bars_s + 8u * cur, phase);
         else cp_async_wait<NSTAGE - 2>();
-        __syncthreads();  // plane q has landed for every thread; everyone is done with plane q-1
-        issue(q + NSTAGE - 1, srcf, fill);  // refills the stage plane q-1 lived in
+        __syncthreads();  // stage `cur` has landed for every thread; everyone is done with the previous stage
+        issue(q + (NSTAGE - 1) * PPS, srcf, fill);  // refills the stage the previous planes lived in
         const float *s = (const float *)(ring + cur * stage_bytes);
-        float r = 0.0f;
+        float r[PPS];
+#pragma unroll
+        for (int p = 0; p < PPS; p++) r[p] = 0.0f;
         if (inplane) {
             if constexpr (INTERP == VT_LINEAR) {
-                r = taps.plane(s);
+                taps.planes(s, pe, r);
             } else if constexpr (INTERP == VT_CUBIC_SIMPLE) {
-                const float pq = taps.plane(s);
-                // the reference accumulates kz = -1, 0, 1 in that order (helper_interpolation.h:51)
-                r = fmaf(taps.wz2, pq, fmaf(taps.wz1, s1, __fmul_rn(taps.wz0, s2)));
-                s2 = s1;
-                s1 = pq;
+                float pq[PPS];
+                taps.planes(s, pe, pq);
+#pragma unroll
+                for (int p = 0; p < PPS; p++) {
+                    // the reference accumulates kz = -1, 0, 1 in that order (helper_interpolation.h:51)
+                    r[p] = fmaf(taps.wz2, pq[p], fmaf(taps.wz1, s1, __fmul_rn(taps.wz0, s2)));
+                    s2 = s1;
+                    s1 = pq[p];
+                }
             } else {
-                float qa, qb, qc;
-                taps.plane3(s, qa, qb, qc);
-                r = (s3 + s1) + qc;  // s3 = A-sum of plane q-2, s1 = B-sum of plane q-1
-                s3 = s2;             // s2 = A-sum of plane q-1
-                s2 = qa;
-                s1 = qb;
+                float qa[PPS], qb[PPS], qc[PPS];
+                taps.planes3(s, pe, qa, qb, qc);
+#pragma unroll
+                for (int p = 0; p < PPS; p++) {
+                    r[p] = (s3 + s1) + qc[p];  // s3 = A-sum of plane q-2, s1 = B-sum of plane q-1
+                    s3 = s2;                   // s2 = A-sum of plane q-1
+                    s2 = qa[p];
+                    s1 = qb[p];
+                }
             }
         }
-        const int zi = q - T::PLANES_AFTER;                 // input plane at the centre of the output voxel
-        if (zi - t0 >= zc0) {                               // uniform: past the warm-up planes
-            const bool ok = inplane && (unsigned)zi < (unsigned)P.s0;  // 0 <= p0 < s0 with p0 = zi + 0.5
-            if (OOB_ZERO) {
-                if (live) *dstz = ok ? r : 0.0f;
-            } else if (ok) {
-                *dstz = r;
+#pragma unroll
+        for (int p = 0; p < PPS; p++) {
+            const int zi = q + p - T::PLANES_AFTER;            // input plane at the centre of the output voxel
+            const int zo = zi - t0;                            // output plane
+            if (zo >= zc0 && zo < zc1) {                       // uniform: past the warm-up planes, inside the chunk
+                const bool ok = inplane && (unsigned)zi < (unsigned)P.s0;  // 0 <= p0 < s0 with p0 = zi + 0.5
+                if (OOB_ZERO) {
+                    if (live) *dstz = ok ? r[p] : 0.0f;
+                } else if (ok) {
+                    *dstz = r[p];
+                }
             }
+            dstz += oplane;
         }
-        srcf += plane_bytes;
-        dstz += oplane;
+        srcf += (size_t)PPS * plane_bytes;
         if (++cur == NSTAGE) { cur = 0; phase ^= 1u; }
         if (++fill == NSTAGE) fill = 0;
     }
@@ -488,13 +532,17 @@ bool tma_ok(const VtResampleParams &P)
 template <int INTERP, int RULE>
 int launch2(VtResampleParams &P, cudaStream_t st)
 {
+    constexpr int PPS = Taps<INTERP>::PPS, NSTAGE = Taps<INTERP>::NSTAGE;
     const int nz = P.z_end - P.z_begin;
     const int tiles = ((P.o1 + TS - 1) / TS) * ((P.o2 + TS - 1) / TS);
     // enough CTAs for ~3 waves of 148 SMs x resident CTAs, without making z-chunks so short that the
     // warm-up planes (2 per chunk for the cubic modes) cost more than a few percent
     int chunks = (148 * 8 * 3 + tiles * P.n_mats - 1) / (tiles * P.n_mats);
     chunks = max(1, min(chunks, nz / 32 > 0 ? nz / 32 : 1));
-    const int z_chunk = (nz + chunks - 1) / chunks;
+    int z_chunk = (nz + chunks - 1) / chunks;
+    // a chunk stages z_chunk + PLANES_BEFORE + PLANES_AFTER planes: make that a whole number of stages
+    constexpr int WARM = Taps<INTERP>::PLANES_BEFORE + Taps<INTERP>::PLANES_AFTER;
+    if (chunks > 1) z_chunk = (z_chunk + WARM + PPS - 1) / PPS * PPS - WARM;
     chunks = (nz + z_chunk - 1) / z_chunk;
     dim3 grid(tiles, chunks, P.n_mats);
     if (chunks > 65535 || P.n_mats > 65535) return VT_ERR_UNSUPPORTED;
@@ -520,10 +568,11 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         }
         G.box_w = best_w;
         G.box_h = need_h;
-        G.stage_bytes = ((unsigned)(G.box_w * G.box_h * 4) + 127u) & ~127u;
+        G.plane_elems = G.box_w * G.box_h;  // a box of depth PPS lands as PPS densely packed planes
+        G.stage_bytes = ((unsigned)(G.plane_elems * PPS * 4) + 127u) & ~127u;
         const unsigned long long gdim[3] = {(unsigned long long)P.s2, (unsigned long long)P.s1, (unsigned long long)P.s0};
         const unsigned long long gstr[2] = {(unsigned long long)P.src_row * 4, (unsigned long long)P.src_plane * 4};
-        const unsigned box[3] = {(unsigned)G.box_w, (unsigned)G.box_h, 1};
+        const unsigned box[3] = {(unsigned)G.box_w, (unsigned)G.box_h, (unsigned)PPS};
         const int rc = vt_encode_tmap_3d(&G.tmap, P.src, gdim, gstr, box);
         if (rc) return rc;
     } else {
@@ -538,12 +587,13 @@ int launch2(VtResampleParams &P, cudaStream_t st)
             }
             P.aux[k] = (unsigned char)best;
         }
-        G.stage_bytes = STAGE * 4;
+        G.plane_elems = STAGE;
+        G.stage_bytes = PPS * STAGE * 4;
     }
     const size_t smem = 128 + (size_t)NSTAGE * G.stage_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        const int mx = 128 + NSTAGE * STAGE * 4;
+        const int mx = 128 + NSTAGE * PPS * STAGE * 4;
         VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
