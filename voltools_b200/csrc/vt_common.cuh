@@ -172,6 +172,20 @@ __device__ __forceinline__ void vt_tma_prefetch_desc(const void *tmap)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// cp.async (LDGSTS), 4-byte form.  `take == 0` writes a zero instead (ignore-src form: no global access is made).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void vt_cp_async4(unsigned smem_dst, const void *gmem_src, unsigned take)
+{
+    asm volatile(
+        "{\n .reg .pred p;\n setp.eq.u32 p, %2, 0;\n"
+        " cp.async.ca.shared.global [%0], [%1], 4, p;\n}\n" ::"r"(smem_dst),
+        "l"(gmem_src), "r"(take)
+        : "memory");
+}
+__device__ __forceinline__ void vt_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void vt_cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
 // packed float32 pairs: sm_100 issues two IEEE fp32 FMAs per lane with one FFMA2 (fma.rn.f32x2); ptxas folds a
 // pair built from the same scalar, vt_pk(t, t), into the instruction's broadcast operand form.  Each half is an
 // ordinary fma.rn.f32, so results are bit-identical to the scalar code.

@@ -25,6 +25,8 @@
 //
 // Accuracy vs the sequential variant (vt_prefilter.cu, bit-identical to the reference): <= ~3e-7 of the
 // coefficient range (tests/test_gpu_parity.py::test_prefilter).
+#include <cstdlib>
+
 #include "vt_common.cuh"
 
 namespace {
@@ -60,7 +62,8 @@ __device__ __forceinline__ float causal_init(const float *e, int n, int step)
 // kernel 1: X and Y passes, marching down a plane
 // ---------------------------------------------------------------------------------------------------
 constexpr int RB = 16;   // rows per step
-constexpr int SEG = 16;  // X segment length
+constexpr int SEG = 16;  // X chunk: samples per thread in the X pass
+constexpr int HX = 16;   // X halo of interior strips (>= K; a multiple of SEG keeps the Y pass's warps chunk-aligned)
 // powers of the pole: kPow[j] = z^j
 __device__ constexpr float kPow[17] = {1.0000000000e+00f,  -2.6794922352e-01f, 7.1796786384e-02f,  -1.9237893163e-02f,
                                        5.1547785351e-03f,  -1.3812189059e-03f, 3.7009653334e-04f,  -9.9167078735e-05f,
@@ -68,152 +71,132 @@ __device__ constexpr float kPow[17] = {1.0000000000e+00f,  -2.6794922352e-01f, 7
                                        1.3697144399e-07f,  -3.6701392062e-08f, 9.8341095049e-09f,  -2.6350420058e-09f,
                                        7.0605745940e-10f};
 
-// X pass pieces for one (row, segment) task; LEN is the compile-time segment length for full segments (SEG) so
-// that the recursions unroll completely and the pole powers become immediates, or 0 for the ragged last segment.
-template <int LEN>
-__device__ __forceinline__ float xseg_causal(float *t, int len, int seg, bool line_start, int sw)
+// Position of strip-local column lx inside a tile row.  A row is a sequence of 16-sample chunks; the four 16-byte
+// units of chunk c are rotated by (c >> 1), which makes the X pass's LDS.128 / STS.128 (lane = chunk, i.e. a
+// 64-byte lane stride) bank-conflict free while a warp of the Y pass (32 consecutive columns = 2 chunks with the
+// same rotation) still reads a permutation of 32 consecutive words.
+__device__ __forceinline__ int tile_col(int lx)
 {
-    float v;
-    if (seg == 0) v = line_start ? causal_init(t, sw, 1) : __fmul_rn(kWarm, t[0]);
-    else v = __fmul_rn(t[0], kLambda);
+    const int c = lx >> 4, g = (lx >> 2) & 3;
+    return (c << 4) + (((g + (c >> 1)) & 3) << 2) + (lx & 3);
+}
+
+// The X pass of one (row, chunk) task, entirely in registers.  Both recursions run locally with a zero carry-in;
+// the carry of the neighbouring chunk (one warp shuffle) is then added to the 12 samples it can still reach
+// (|z|^k decay: beyond 12 samples it is below float32 resolution, and a chunk's own end value is its true end
+// value to |z|^16).  Line ends: the reference's exact causal start (bspline.h:2-19) for the chunk at x = 0, and the
+// anticausal start c[W-1] = z/(z-1) c+[W-1] through the per-sample factor cf[] (-z inside the line, z/(z-1) on its
+// last sample, 0 beyond it).
+template <int L>
+__device__ __forceinline__ void x_pass(float *tb, int xc, const float (&cf)[SEG], bool exact_start)
+{
+    const int rot = (xc >> 1) & 3;
+    float t[SEG];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const float4 q = *reinterpret_cast<const float4 *>(tb + (((g + rot) & 3) << 2));
+        t[4 * g] = q.x; t[4 * g + 1] = q.y; t[4 * g + 2] = q.z; t[4 * g + 3] = q.w;
+    }
+    // ---- causal ----
+    float sum = t[0];
+#pragma unroll
+    for (int n = 0; n < 12; n++) sum = __fmaf_rn(kPow[n + 1], t[n], sum);  // samples past the line end are staged as 0
+    float v = __fmul_rn(kLambda, xc == 0 ? (exact_start ? sum : __fmul_rn(kWarm / kLambda, t[0])) : t[0]);
     t[0] = v;
-    if (LEN) {
 #pragma unroll
-        for (int k = 1; k < LEN; k++) {
-            v = causal_step(t[k], v);
-            t[k] = v;
-        }
-    } else {
-        for (int k = 1; k < len; k++) {
-            v = causal_step(t[k], v);
-            t[k] = v;
-        }
+    for (int k = 1; k < SEG; k++) {
+        v = __fmaf_rn(kPole, v, __fmul_rn(kLambda, t[k]));
+        t[k] = v;
     }
-    return v;
-}
-
-template <int LEN>
-__device__ __forceinline__ void xseg_anticausal(float *t, int len, float carry, bool line_end)
-{
-    if (LEN) {
-        // full segment: never the end of the line's last segment unless line_end (then len == SEG too)
-        float c = t[LEN - 1];  // k = 15 >= K: no carry correction
-        float u = line_end ? __fmul_rn(kAnti, c) : __fmul_rn(kPole, -c);
-        t[LEN - 1] = u;
+    float carry = __shfl_up_sync(0xffffffffu, v, 1, L);
+    if (xc == 0) carry = 0.0f;
 #pragma unroll
-        for (int k = LEN - 2; k >= 0; k--) {
-            c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
-            u = anticausal_step(u, c);
-            t[k] = u;
-        }
-    } else {
-        int k = len - 1;
-        float c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
-        float u = line_end ? __fmul_rn(kAnti, c) : __fmul_rn(kPole, -c);
+    for (int k = 0; k < K; k++) t[k] = __fmaf_rn(kPow[k + 1], carry, t[k]);
+    // ---- anticausal ----
+    float u = 0.0f;
+#pragma unroll
+    for (int k = SEG - 1; k >= 0; k--) {
+        u = __fmaf_rn(kPole, u, __fmul_rn(cf[k], t[k]));
         t[k] = u;
-        for (k = len - 2; k >= 0; k--) {
-            c = k < K ? fmaf(kPow[k + 1], carry, t[k]) : t[k];
-            u = anticausal_step(u, c);
-            t[k] = u;
-        }
     }
+    float nxt = __shfl_down_sync(0xffffffffu, u, 1, L);  // first sample of the next chunk (true value to |z|^16)
+    if (xc == L - 1) nxt = 0.0f;
+#pragma unroll
+    for (int k = SEG - K; k < SEG; k++) t[k] = __fmaf_rn(kPow[SEG - k], nxt, t[k]);
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+        *reinterpret_cast<float4 *>(tb + (((g + rot) & 3) << 2)) = make_float4(t[4 * g], t[4 * g + 1], t[4 * g + 2], t[4 * g + 3]);
 }
 
+// One CTA walks down (a y-chunk of) one z-plane RB rows at a time.  Per step: the RB rows are staged into a
+// shared-memory tile with cp.async (double buffered: the next step's rows are in flight during this step's math),
+// the X recursion runs on them with one (row, 16-sample chunk) task per thread (x_pass), then one thread per
+// column continues the Y recursion down the plane (causal value in a register, anticausal restart from K rows
+// ahead over a register window) and stores finished rows (coalesced).  NT = RB * L threads.
 template <int NT>
 __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restrict__ src, float *__restrict__ dst, int H,
                                                           int W, long long dst_row, long long dst_plane, int y_chunk,
-                                                          int x_strip, int pitch, int nseg_max)
+                                                          int x_strip)
 {
-    extern __shared__ float smem[];
-    float *tile = smem;                 // [RB][pitch], pitch odd
-    float *ends = smem + RB * pitch;    // [RB][nseg_max]: causal value at the end of each X segment
+    constexpr int L = NT / RB;   // chunks (X-pass lanes) per row
+    constexpr int P = L * SEG;   // tile row pitch in floats (= NT)
+    extern __shared__ __align__(16) float smem[];  // two tiles [RB][P]
     const int z = blockIdx.z;
     const int x0 = blockIdx.x * x_strip, x1 = min(x0 + x_strip, W);  // columns written by this CTA
-    const int xa = max(x0 - K, 0), xb = min(x1 + K, W);              // columns staged (X warm-up on both sides)
+    const int xa = max(x0 - HX, 0), xb = min(x1 + HX, W);            // columns staged (X warm-up on both sides)
     const int sw = xb - xa;
     const int yc0 = blockIdx.y * y_chunk, yc1 = min(yc0 + y_chunk, H);  // rows written
     const int ra = max(yc0 - K, 0), rb = min(yc1 + K, H);               // rows processed (Y warm-up / look-ahead)
     const int tid = threadIdx.x;
-    const int nseg = (sw + SEG - 1) / SEG;
-    const int last_len = sw - (nseg - 1) * SEG;
-    const bool stager = tid < sw;
+    const bool stager = tid < sw;         // this thread stages column xa + tid of every row
     const bool has_col = x0 + tid < x1;   // this thread sweeps column x0 + tid along y
-    const int cx = x0 + tid - xa;         // its column inside the tile
     const int npad = (x1 == W) ? (int)(dst_row - W) : 0;  // pad columns (written as zeros) belong to the last strip
-    // running pointers
-    const float *sp = src + (size_t)z * H * W + (size_t)ra * W + xa + tid;  // row being prefetched, this thread's column
-    float *op = dst + (size_t)z * dst_plane + (long long)(ra - K) * dst_row + x0 + tid;  // row r0 - K of the output
-
-    float pf[RB];
+    // X-pass task of this thread
+    const int xrow = tid / L, xc = tid % L;
+    float cf[SEG];
 #pragma unroll
-    for (int i = 0; i < RB; i++) pf[i] = (stager && ra + i < rb) ? __ldg(sp + (size_t)i * W) : 0.0f;
-    sp += (size_t)RB * W;
+    for (int k = 0; k < SEG; k++) {
+        const int x = xa + xc * SEG + k;
+        cf[k] = x < W - 1 ? kNegPole : (x == W - 1 ? kAnti : 0.0f);
+    }
+    // running pointers
+    const float *sp = src + (size_t)z * H * W + (size_t)ra * W + xa + tid;  // this thread's column, first row to stage
+    float *op = dst + (size_t)z * dst_plane + (long long)(ra - K) * dst_row + x0 + tid;  // row r0 - K of the output
+    const unsigned tile_s = vt_smem_u32(smem);
+    const unsigned stage_dst = tile_s + 4u * (unsigned)tile_col(tid);
+    const float *ycol = smem + tile_col(x0 + tid - xa);
+
+    auto stage = [&](int r0, int buf) {  // rows r0 .. r0+RB-1 -> tile[buf]; rows past rb and columns past sw: zeros
+#pragma unroll
+        for (int i = 0; i < RB; i++)
+            vt_cp_async4(stage_dst + 4u * (unsigned)((buf * RB + i) * P), sp + (size_t)i * W, (stager && r0 + i < rb) ? 1u : 0u);
+        vt_cp_async_commit();
+        sp += (size_t)RB * W;
+    };
+
+    stage(ra, 0);
     float cp[K + RB];  // causal Y values of rows [r0 - K, r0 + RB)
 #pragma unroll
     for (int k = 0; k < K + RB; k++) cp[k] = 0.0f;
     float prev = 0.0f;
+    int buf = 0;
 
-    for (int r0 = ra;; r0 += RB) {
+    for (int r0 = ra;; r0 += RB, buf ^= 1) {
         const int nrows = min(RB, rb - r0);  // <= 0 once the rows are exhausted (flush steps)
-        __syncthreads();                     // the previous step's column sweep is done with the tile
-        if (nrows > 0) {
-            if (stager) {
-#pragma unroll
-                for (int i = 0; i < RB; i++) tile[i * pitch + tid] = pf[i];
-            }
-            if (r0 + 2 * RB <= rb) {  // uniform: the next step is a full one
-                if (stager) {
-#pragma unroll
-                    for (int i = 0; i < RB; i++) pf[i] = __ldg(sp + (size_t)i * W);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < RB; i++) pf[i] = (stager && r0 + RB + i < rb) ? __ldg(sp + (size_t)i * W) : 0.0f;
-            }
-            sp += (size_t)RB * W;
-            __syncthreads();
-            // ---- X, causal: local recursion per (row, segment) ----
-            for (int task = tid; task < RB * nseg; task += NT) {
-                const int row = task & (RB - 1), seg = task >> 4;
-                if (row >= nrows) continue;
-                float *t = tile + row * pitch + seg * SEG;
-                float v;
-                if (seg < nseg - 1 || last_len == SEG) v = xseg_causal<SEG>(t, SEG, seg, xa == 0, sw);
-                else v = xseg_causal<0>(t, last_len, seg, xa == 0, sw);
-                ends[row * nseg_max + seg] = v;
-            }
-            __syncthreads();
-            // ---- X, anticausal: local recursion on the carry-corrected causal values ----
-            for (int task = tid; task < RB * nseg; task += NT) {
-                const int row = task & (RB - 1), seg = task >> 4;
-                if (row >= nrows) continue;
-                float *t = tile + row * pitch + seg * SEG;
-                const float carry = seg > 0 ? ends[row * nseg_max + seg - 1] : 0.0f;
-                const bool line_end = seg == nseg - 1 && xb == W;
-                if (seg < nseg - 1 || last_len == SEG) xseg_anticausal<SEG>(t, SEG, carry, line_end);
-                else xseg_anticausal<0>(t, last_len, carry, line_end);
-            }
-            __syncthreads();
-            // ---- X, anticausal carry: the first sample of the next segment feeds the last 12 of this one ----
-            for (int task = tid; task < RB * (nseg - 1); task += NT) {
-                const int row = task & (RB - 1), seg = task >> 4;
-                if (row >= nrows) continue;
-                float *t = tile + row * pitch + seg * SEG;
-                const float carry = t[SEG];
-#pragma unroll
-                for (int k = SEG - K; k < SEG; k++) t[k] = fmaf(kPow[SEG - k], carry, t[k]);
-            }
-            __syncthreads();
-        }
+        vt_cp_async_wait_all();
+        __syncthreads();  // tile[buf] has landed; the previous step's column sweep is done with tile[buf ^ 1]
+        if (r0 + RB < rb) stage(r0 + RB, buf ^ 1);
+        if (nrows > 0) x_pass<L>(smem + (buf * RB + xrow) * P + xc * SEG, xc, cf, xa == 0);
+        __syncthreads();
         // ---- Y: one thread per column, rows r0 .. r0+nrows-1 enter the window ----
         const int w0 = r0 - K;  // row of cp[0]
         if (has_col) {
-            const float *c = tile + cx;
+            const float *c = ycol + buf * RB * P;
             if (r0 > ra && nrows == RB && w0 >= ra) {
                 // steady state (uniform): a full step strictly inside the processed rows
 #pragma unroll
                 for (int k = 0; k < RB; k++) {
-                    prev = causal_step(c[k * pitch], prev);
+                    prev = causal_step(c[k * P], prev);
                     cp[K + k] = prev;
                 }
                 float a = __fmul_rn(kAnti, cp[K + RB - 1]);
@@ -233,14 +216,14 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
             } else {
                 int kstart = 0;
                 if (r0 == ra) {  // first row of the line (true start: exact formula) or of the warm-up
-                    prev = ra == 0 ? causal_init(c, min(rb, RB), pitch) : __fmul_rn(kWarm, c[0]);
+                    prev = ra == 0 ? causal_init(c, min(rb, RB), P) : __fmul_rn(kWarm, c[0]);
                     cp[K] = prev;
                     kstart = 1;
                 }
 #pragma unroll
                 for (int k = 0; k < RB; k++) {
                     if (k >= kstart) {
-                        if (r0 + k < rb) prev = causal_step(c[k * pitch], prev);
+                        if (r0 + k < rb) prev = causal_step(c[k * P], prev);
                         cp[K + k] = prev;
                     }
                 }
@@ -368,22 +351,22 @@ int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);  //
 template <int NT>
 int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long dst_row, long long dst_plane, cudaStream_t st)
 {
-    const int x_strip = W <= NT ? W : NT - 2 * K;
+    const int x_strip = W <= NT ? W : NT - 2 * HX;
     const int strips = (W + x_strip - 1) / x_strip;
-    const int sw_max = W <= NT ? W : NT;
-    const int pitch = sw_max | 1;
-    const int nseg_max = (sw_max + SEG - 1) / SEG;
-    const size_t smem = ((size_t)RB * pitch + (size_t)RB * nseg_max) * sizeof(float);
-    // y-chunks: ~1000+ CTAs in flight, chunks of at least 64 rows (each pays 2*K rows of warm-up / look-ahead)
-    int chunks = (1200 + D * strips - 1) / (D * strips);
+    const size_t smem = (size_t)2 * RB * NT * sizeof(float);
+    // y-chunks: enough CTAs to fill the GPU, chunks of at least 64 rows (each pays 2*K rows of warm-up / look-ahead)
+    int chunks = (600 + D * strips - 1) / (D * strips);
     const int max_chunks = H / 64 > 0 ? H / 64 : 1;
     if (chunks > max_chunks) chunks = max_chunks;
+    if (const char *e = getenv("VT_XY_CHUNKS")) chunks = atoi(e) > 0 ? atoi(e) : chunks;  // tuning knob
     int y_chunk = (H + chunks - 1) / chunks;
     chunks = (H + y_chunk - 1) / y_chunk;
     if (D > 65535 || chunks > 65535) return VT_ERR_UNSUPPORTED;
+    // per device, so not cached in a static: a process may drive several GPUs
+    VT_CUDA(cudaFuncSetAttribute(prefilter_xy_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VtProf prof(VT_K_PREFILTER_FUSED, st);
     prefilter_xy_kernel<NT><<<dim3(strips, chunks, D), NT, smem, st>>>(d_src, d_dst, H, W, dst_row, dst_plane, y_chunk,
-                                                                      x_strip, pitch, nseg_max);
+                                                                      x_strip);
     return VT_OK;
 }
 
