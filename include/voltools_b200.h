@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 2
+#define VT_ABI_VERSION 3
 
 /* status codes: 0 ok; 1..99 library errors; 1000+e = cudaError_t e; 2000+e = CUresult e */
 #define VT_OK 0
@@ -89,6 +89,18 @@ int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, i
  */
 int vt_prefilter_strided_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride,
                              long long dst_plane_stride, int variant, int device, void *stream);
+
+/*
+ * Same with a caller-owned device workspace of vt_prefilter_workspace_bytes(...) bytes (distinct from d_src and
+ * d_dst; contents undefined afterwards).  With it variant 0 runs its Z sweep out of place and in z-chunks, which is
+ * what keeps small volumes (<= 256^3: too few columns to cover the HBM latency with one thread per column) at
+ * speed.  d_workspace == NULL or too small: identical to vt_prefilter_strided_f32.  Same coefficients either way
+ * to ~1e-7 of the range.  The library itself never allocates device memory on this path.
+ */
+size_t vt_prefilter_workspace_bytes(int d0, int d1, int d2, long long dst_row_stride, long long dst_plane_stride);
+int vt_prefilter_ws_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride,
+                        long long dst_plane_stride, void *d_workspace, size_t workspace_bytes, int variant, int device,
+                        void *stream);
 
 /*
  * The `transform` kernel launch (voltools/transforms.py:253-282 launched at :212 and volume.py:78), for a

@@ -47,6 +47,10 @@ def lib():
         L.vt_affine_f32.argtypes = [_vp, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i,
                                     ctypes.c_uint, _i, _i, _i, _vp]
         L.vt_prefilter_strided_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _vp]
+        L.vt_prefilter_workspace_bytes.restype = ctypes.c_size_t
+        L.vt_prefilter_workspace_bytes.argtypes = [_i, _i, _i, ctypes.c_longlong, ctypes.c_longlong]
+        L.vt_prefilter_ws_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, ctypes.c_size_t,
+                                          _i, _i, _vp]
         L.vt_affine_strided_f32.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i, _i,
                                             ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _i, _vp]
         L.vt_affine_plan.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _f32p, _i, _i, ctypes.c_uint, ctypes.POINTER(_i)]
@@ -58,7 +62,7 @@ def lib():
         L.vt_profile_kernel_name.restype = ctypes.c_char_p
         L.vt_profile_kernel_name.argtypes = [_i]
         L.vt_profile_read.argtypes = [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
-        if L.vt_abi_version() != 2:
+        if L.vt_abi_version() != 3:
             raise RuntimeError('libvoltools_b200.so ABI version mismatch')
         _lib = L
     return _lib
@@ -104,14 +108,27 @@ def padded_row(width):
     return (int(width) + 3) // 4 * 4
 
 
-def prefilter(src_ptr, shape, device=-1, stream=0, variant=0, dst_ptr=None, dst_strides=None):
-    """Samples at src_ptr -> coefficients at dst_ptr (default: in place).  dst_strides = (row, plane) in elements."""
+def prefilter(src_ptr, shape, device=-1, stream=0, variant=0, dst_ptr=None, dst_strides=None, workspace=True):
+    """Samples at src_ptr -> coefficients at dst_ptr (default: in place).  dst_strides = (row, plane) in elements.
+
+    workspace=True (out-of-place variant 0 only): a scratch volume from torch's caching allocator is handed to the
+    library so that its Z sweep can run out of place in z-chunks (vt_prefilter_ws_f32); the library itself
+    allocates nothing.  `stream` must then be torch's current stream on that device (it is, for every caller here).
+    """
     dst = src_ptr if dst_ptr is None else dst_ptr
     if dst_strides is None:
-        check(lib().vt_prefilter_f32(src_ptr, dst, shape[0], shape[1], shape[2], variant, device, stream))
-    else:
-        check(lib().vt_prefilter_strided_f32(src_ptr, dst, shape[0], shape[1], shape[2], int(dst_strides[0]),
-                                             int(dst_strides[1]), variant, device, stream))
+        dst_strides = (int(shape[2]), int(shape[1]) * int(shape[2]))
+    row, plane = int(dst_strides[0]), int(dst_strides[1])
+    ws, ws_ptr, ws_bytes = None, None, 0
+    if workspace and variant == 0 and dst != src_ptr and int(shape[0]) >= 128:
+        import torch
+        ws_bytes = lib().vt_prefilter_workspace_bytes(shape[0], shape[1], shape[2], row, plane)
+        dev = torch.cuda.current_device() if device < 0 else device
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f'cuda:{dev}')
+        ws_ptr = ws.data_ptr()
+    check(lib().vt_prefilter_ws_f32(src_ptr, dst, shape[0], shape[1], shape[2], row, plane, ws_ptr, ws_bytes, variant,
+                                    device, stream))
+    del ws
 
 
 def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None,

@@ -17,7 +17,7 @@ int vt_launch_slice(VtResampleParams &P, int interp, cudaStream_t st);          
 int vt_slice_supported(const VtResampleParams &P, int interp);                  // vt_resample_slice.cu
 int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter.cu
 int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
-                     cudaStream_t st);  // vt_prefilter_win.cu
+                     float *d_ws, size_t ws_bytes, cudaStream_t st);  // vt_prefilter_win.cu
 
 static std::atomic<long long> g_launches{0};
 void vt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -240,8 +240,22 @@ int vt_profile_read(int kernel, double *ms_total, long long *launches)
     return VT_OK;
 }
 
+size_t vt_prefilter_workspace_bytes(int d0, int d1, int d2, long long dst_row_stride, long long dst_plane_stride)
+{
+    if (d0 < 1 || d1 < 1 || d2 < 1 || dst_row_stride < d2 || dst_plane_stride < dst_row_stride * d1) return 0;
+    return (size_t)d0 * (size_t)dst_plane_stride * sizeof(float);
+}
+
 int vt_prefilter_strided_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride,
                              long long dst_plane_stride, int variant, int device, void *stream)
+{
+    return vt_prefilter_ws_f32(d_src, d_dst, d0, d1, d2, dst_row_stride, dst_plane_stride, nullptr, 0, variant, device,
+                               stream);
+}
+
+int vt_prefilter_ws_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride,
+                        long long dst_plane_stride, void *d_workspace, size_t workspace_bytes, int variant, int device,
+                        void *stream)
 {
     if (!d_src || !d_dst || d0 < 1 || d1 < 1 || d2 < 1) return VT_ERR_INVALID_ARG;
     if (variant != 0 && variant != 1) return VT_ERR_INVALID_ARG;
@@ -252,7 +266,8 @@ int vt_prefilter_strided_f32(const float *d_src, float *d_dst, int d0, int d1, i
     if (g.status) return g.status;
     cudaStream_t st = (cudaStream_t)stream;
     if (variant == 0 && d_src != d_dst) {
-        const int rc = vt_prefilter_win(d_src, d_dst, d0, d1, d2, dst_row_stride, dst_plane_stride, st);
+        const int rc = vt_prefilter_win(d_src, d_dst, d0, d1, d2, dst_row_stride, dst_plane_stride, (float *)d_workspace,
+                                        workspace_bytes, st);
         if (rc != VT_ERR_UNSUPPORTED || !dense) return rc;  // rows too long for shared memory: sequential kernels
     }
     if (d_src != d_dst)
@@ -321,8 +336,8 @@ int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int 
 struct vt_host_ctx {
     int device;
     cudaStream_t st_in, st_k, st_out;
-    float *d_src, *d_dst, *d_coef;
-    size_t cap_src, cap_dst, cap_coef;
+    float *d_src, *d_dst, *d_coef, *d_ws;
+    size_t cap_src, cap_dst, cap_coef, cap_ws;
     cudaEvent_t ev_in, ev_k;
 };
 
@@ -355,6 +370,7 @@ int vt_host_ctx_destroy(vt_host_ctx *c)
     cudaFree(c->d_src);
     cudaFree(c->d_dst);
     cudaFree(c->d_coef);
+    cudaFree(c->d_ws);
     cudaEventDestroy(c->ev_in);
     cudaEventDestroy(c->ev_k);
     cudaStreamDestroy(c->st_in);
@@ -396,7 +412,9 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
         if (rc) return rc;
         // upload (the source is needed whole before any output plane can be gathered under a general affine map)
         VT_CUDA(cudaMemcpyAsync(c->d_src, h_src, nsrc * 4, cudaMemcpyHostToDevice, c->st_k));
-        rc = vt_prefilter_strided_f32(c->d_src, c->d_coef, s0, s1, s2, row, plane, 0, -1, c->st_k);
+        rc = ensure(&c->d_ws, &c->cap_ws, (size_t)plane * s0 * 4);
+        if (rc) return rc;
+        rc = vt_prefilter_ws_f32(c->d_src, c->d_coef, s0, s1, s2, row, plane, c->d_ws, c->cap_ws, 0, -1, c->st_k);
         if (rc) return rc;
         sampled = c->d_coef;
     } else {

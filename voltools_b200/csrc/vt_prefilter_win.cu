@@ -275,10 +275,13 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
     // ---- start-up: fill cp[0..K) ----
     if (zc0 == 0) {
         // exact start of the line (InitialCausalCoefficient, bspline.h:2-19)
-        const int horizon = D < 12 ? D : 12;
-        float zn = kPole, sum = s[0];
-        for (int k = 0; k < horizon; k++) {
-            sum = __fmaf_rn(zn, s[(size_t)k * cols], sum);
+        float first[12];  // loaded together (independent), then summed in the reference's order
+#pragma unroll
+        for (int k = 0; k < 12; k++) first[k] = k < D ? s[(size_t)k * cols] : 0.0f;
+        float zn = kPole, sum = first[0];
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            if (k < D) sum = __fmaf_rn(zn, first[k], sum);
             zn = __fmul_rn(zn, kPole);
         }
         prev = __fmul_rn(kLambda, sum);
@@ -370,29 +373,41 @@ int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long d
     return VT_OK;
 }
 
-// src -> dst (src != dst), dst possibly with padded strides.
+// src -> dst (src != dst), dst possibly with padded strides.  With a workspace of d0 * dst_plane floats the XY kernel
+// writes there and the Z sweep runs out of place, which allows it to be cut into z-chunks (more threads in flight:
+// what a 250^3 volume, with only 63 000 columns, needs to cover the HBM latency); without one it runs in place.
 int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
-                     cudaStream_t st)
+                     float *d_ws, size_t ws_bytes, cudaStream_t st)
 {
     const int D = d0, H = d1, W = d2;
     if (dst_row - W > 32) return VT_ERR_UNSUPPORTED;
+    const size_t cols = (size_t)dst_plane;  // columns of the (padded) plane: pad columns hold zeros and stay zero
+    const size_t bx = (cols + Z_THREADS - 1) / Z_THREADS;
+    if (bx > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
+    // z-chunks: aim at >= ~300 000 threads, chunks of at least 64 planes (each pays 2*K planes of warm-up/look-ahead)
+    int chunks = 1;
+    if (d_ws && ws_bytes >= cols * (size_t)D * sizeof(float) && d_ws != d_dst && d_ws != d_src) {
+        chunks = (int)((300000 + cols - 1) / cols);
+        const int max_chunks = D / 64 > 0 ? D / 64 : 1;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (const char *e = getenv("VT_Z_CHUNKS")) chunks = atoi(e) > 0 ? atoi(e) : chunks;  // tuning knob
+    }
+    float *xy_out = chunks > 1 ? d_ws : d_dst;
     int rc;
-    if (W <= 128) rc = launch_xy<128>(d_src, d_dst, D, H, W, dst_row, dst_plane, st);
-    else if (W <= 256) rc = launch_xy<256>(d_src, d_dst, D, H, W, dst_row, dst_plane, st);
-    else rc = launch_xy<512>(d_src, d_dst, D, H, W, dst_row, dst_plane, st);
+    if (W <= 128) rc = launch_xy<128>(d_src, xy_out, D, H, W, dst_row, dst_plane, st);
+    else if (W <= 256) rc = launch_xy<256>(d_src, xy_out, D, H, W, dst_row, dst_plane, st);
+    else rc = launch_xy<512>(d_src, xy_out, D, H, W, dst_row, dst_plane, st);
     if (rc) return rc;
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
     {
-        // columns of the (padded) plane: pad columns hold zeros and simply stay zero
-        const size_t cols = (size_t)dst_plane;
-        const size_t bx = (cols + Z_THREADS - 1) / Z_THREADS;
-        if (bx > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
-        // the sweep runs in place (reads stay ahead of writes within a column), which rules out z-chunks: a
-        // neighbouring chunk's warm-up would read planes this one has already overwritten.  One chunk.
-        const int z_chunk = (D + ZB - 1) / ZB * ZB;
+        // in place the sweep must be one chunk: a neighbouring chunk's warm-up would read planes this one has
+        // already overwritten
+        int z_chunk = ((D + chunks - 1) / chunks + ZB - 1) / ZB * ZB;
+        chunks = (D + z_chunk - 1) / z_chunk;
+        if (chunks > 65535) return VT_ERR_UNSUPPORTED;
         VtProf prof(VT_K_PREFILTER_Z, st);
-        prefilter_z_kernel<<<dim3((unsigned)bx, 1), Z_THREADS, 0, st>>>(d_dst, d_dst, D, cols, z_chunk);
+        prefilter_z_kernel<<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>(xy_out, d_dst, D, cols, z_chunk);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
