@@ -40,6 +40,11 @@ def main():
                                                 translation=(5.5, -3.25, 2.0), center=c),
         }
         src = torch.from_numpy(vol).cuda()
+        # the resampling kernels see what the API hands them: rows padded to 16 bytes (TMA staging)
+        row = _native.padded_row(n)
+        srcp = torch.zeros((n, n, row), device='cuda')
+        srcp[:, :, :n].copy_(src)
+        strides = (row, n * row)
         dst = torch.zeros(shape, device='cuda')
         st = torch.cuda.current_stream().cuda_stream
         tmp = torch.empty_like(src)
@@ -57,8 +62,8 @@ def main():
                 for fam, fname in ((_native.KERNEL_GATHER, 'gather'), (_native.KERNEL_BRICK, 'brick'),
                                    (_native.KERNEL_SLICE, 'slice')):
                     try:
-                        ms = timeit(lambda: _native.affine(src.data_ptr(), shape, dst.data_ptr(), shape, m, interp,
-                                                           _native.OOB_ZERO | fam, stream=st))
+                        ms = timeit(lambda: _native.affine(srcp.data_ptr(), shape, dst.data_ptr(), shape, m, interp,
+                                                           _native.OOB_ZERO | fam, stream=st, src_strides=strides))
                     except RuntimeError as e:
                         continue
                     print(f'{n}^3 {mname} {iname} {fname}: {ms:.3f} ms  {nvox / ms / 1e6:.1f} Gvox/s  '

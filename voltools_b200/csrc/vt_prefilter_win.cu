@@ -310,38 +310,59 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
     // ---- steady state ----
     // raw[] holds the next ZB planes of the look-ahead region; it is reloaded for the following step right after
     // the causal recursion has consumed it, so those loads are in flight during the anticausal sweep and the stores
-    // (2 x ZB loads outstanding per thread: enough to cover the HBM latency at ~13 warps per SM)
+    // (2 x ZB loads outstanding per thread).  Steps whose whole window lies inside the volume and the chunk take a
+    // guard-free path with one IMAD.WIDE per address (32-bit plane stride).
+    const unsigned stride = (unsigned)cols;  // host: cols < 2^31
+    const float *sp = s + (size_t)(zw + K) * cols;  // plane zw + K of this column
+    float *dp = d + (size_t)zw * cols;              // plane zw
     float raw[ZB];
 #pragma unroll
-    for (int k = 0; k < ZB; k++) {
-        const int zz = zw + K + k;
-        raw[k] = zz < D ? s[(size_t)zz * cols] : 0.0f;
-    }
+    for (int k = 0; k < ZB; k++) raw[k] = zw + K + k < D ? sp[(size_t)k * stride] : 0.0f;
     for (; zw < zc1; zw += ZB) {
-        // causal values of the next ZB planes (look-ahead region moves forward)
-#pragma unroll
-        for (int k = 0; k < ZB; k++) {
-            const int zz = zw + K + k;
-            if (zz < D) prev = causal_step(raw[k], prev);
-            cp[K + k] = prev;
-        }
-        if (zw + ZB < zc1) {
+        sp += (size_t)ZB * stride;
+        if (zw + K + ZB <= D && zw + ZB <= zc1) {  // uniform
 #pragma unroll
             for (int k = 0; k < ZB; k++) {
-                const int zz = zw + ZB + K + k;
-                raw[k] = zz < D ? s[(size_t)zz * cols] : 0.0f;
+                prev = causal_step(raw[k], prev);
+                cp[K + k] = prev;
+            }
+            if (zw + K + 2 * ZB <= D) {
+#pragma unroll
+                for (int k = 0; k < ZB; k++) raw[k] = sp[(size_t)k * stride];
+            } else if (zw + ZB < zc1) {
+#pragma unroll
+                for (int k = 0; k < ZB; k++) raw[k] = zw + ZB + K + k < D ? sp[(size_t)k * stride] : 0.0f;
+            }
+            float c = __fmul_rn(kAnti, cp[K + ZB - 1]);
+#pragma unroll
+            for (int k = K + ZB - 2; k >= 0; k--) {
+                c = anticausal_step(c, cp[k]);
+                if (k < ZB) dp[(size_t)k * stride] = c;
+            }
+        } else {
+            // causal values of the next ZB planes (look-ahead region moves forward)
+#pragma unroll
+            for (int k = 0; k < ZB; k++) {
+                const int zz = zw + K + k;
+                if (zz < D) prev = causal_step(raw[k], prev);
+                cp[K + k] = prev;
+            }
+            if (zw + ZB < zc1) {
+#pragma unroll
+                for (int k = 0; k < ZB; k++) raw[k] = zw + ZB + K + k < D ? sp[(size_t)k * stride] : 0.0f;
+            }
+            // anticausal from the last available plane of the window back to zw
+            const int last = min(zw + K + ZB, D) - 1;  // plane index where the recursion (re)starts
+            float c = 0.0f;
+#pragma unroll
+            for (int k = K + ZB - 1; k >= 0; k--) {
+                const int zz = zw + k;
+                if (zz == last) c = __fmul_rn(kAnti, cp[k]);
+                else if (zz < last) c = anticausal_step(c, cp[k]);
+                if (k < ZB && zz < zc1) dp[(size_t)k * stride] = c;
             }
         }
-        // anticausal from the last available plane of the window back to zw
-        const int last = min(zw + K + ZB, D) - 1;  // plane index where the recursion (re)starts
-        float c = 0.0f;
-#pragma unroll
-        for (int k = K + ZB - 1; k >= 0; k--) {
-            const int zz = zw + k;
-            if (zz == last) c = __fmul_rn(kAnti, cp[k]);
-            else if (zz < last) c = anticausal_step(c, cp[k]);
-            if (k < ZB && zz < zc1) d[(size_t)zz * cols] = c;
-        }
+        dp += (size_t)ZB * stride;
 #pragma unroll
         for (int k = 0; k < K; k++) cp[k] = cp[ZB + k];
     }
@@ -358,7 +379,7 @@ int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long d
     const int strips = (W + x_strip - 1) / x_strip;
     const size_t smem = (size_t)2 * RB * NT * sizeof(float);
     // y-chunks: enough CTAs to fill the GPU, chunks of at least 64 rows (each pays 2*K rows of warm-up / look-ahead)
-    int chunks = (600 + D * strips - 1) / (D * strips);
+    int chunks = (200 + D * strips - 1) / (D * strips);
     const int max_chunks = H / 64 > 0 ? H / 64 : 1;
     if (chunks > max_chunks) chunks = max_chunks;
     if (const char *e = getenv("VT_XY_CHUNKS")) chunks = atoi(e) > 0 ? atoi(e) : chunks;  // tuning knob

@@ -20,6 +20,7 @@
 // cubicTex3DSimple (voltools/kernels/helper_interpolation.h:3-68) for this class of matrices.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "vt_common.cuh"
@@ -291,7 +292,7 @@ struct VtSliceStaging {
 };
 
 template <int INTERP, int RULE, bool OOB_ZERO, bool TMA>
-__global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : (INTERP == VT_CUBIC_SIMPLE ? 3 : 4))
+__global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
     vt_slice_kernel(const __grid_constant__ VtResampleParams P, const __grid_constant__ VtSliceStaging G, int z_chunk)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // [128 B of mbarriers][NSTAGE stages of PPS planes]
@@ -535,15 +536,37 @@ int launch2(VtResampleParams &P, cudaStream_t st)
     constexpr int PPS = Taps<INTERP>::PPS, NSTAGE = Taps<INTERP>::NSTAGE;
     const int nz = P.z_end - P.z_begin;
     const int tiles = ((P.o1 + TS - 1) / TS) * ((P.o2 + TS - 1) / TS);
-    // enough CTAs for ~3 waves of 148 SMs x resident CTAs, without making z-chunks so short that the
-    // warm-up planes (2 per chunk for the cubic modes) cost more than a few percent
-    int chunks = (148 * 8 * 3 + tiles * P.n_mats - 1) / (tiles * P.n_mats);
-    chunks = max(1, min(chunks, nz / 32 > 0 ? nz / 32 : 1));
-    int z_chunk = (nz + chunks - 1) / chunks;
-    // a chunk stages z_chunk + PLANES_BEFORE + PLANES_AFTER planes: make that a whole number of stages
+    // z-chunks: a CTA marches z_chunk + WARM planes and pays a fixed start-up (weights, descriptor fetch, first
+    // loads in flight) worth a few more; CTAs run in waves of (SMs x resident CTAs).  Pick the chunk count with
+    // the smallest waves x march length -- for a single 250^3 volume (256 tiles) that is the difference between
+    // 5 ragged waves and 3 full ones.
     constexpr int WARM = Taps<INTERP>::PLANES_BEFORE + Taps<INTERP>::PLANES_AFTER;
-    if (chunks > 1) z_chunk = (z_chunk + WARM + PPS - 1) / PPS * PPS - WARM;
-    chunks = (nz + z_chunk - 1) / z_chunk;
+    constexpr int RESIDENT = INTERP == VT_LINEAR ? 4 : 3;  // __launch_bounds__ of the kernel
+    constexpr int STARTUP = 8;
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long slots = (long long)sms * RESIDENT, per_chunk = (long long)tiles * P.n_mats;
+    int chunks = 1, z_chunk = nz;
+    long long best_cost = -1;
+    for (int c = 1; c <= 64 && (c == 1 || nz / c >= 16); c++) {
+        int zc = (nz + c - 1) / c;
+        if (c > 1) zc = (zc + WARM + PPS - 1) / PPS * PPS - WARM;  // a whole number of stages per chunk
+        if (zc < 1) break;
+        const int cc = (nz + zc - 1) / zc;
+        const long long waves = (per_chunk * cc + slots - 1) / slots;
+        const long long cost = waves * (zc + WARM + STARTUP);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            chunks = cc;
+            z_chunk = zc;
+        }
+    }
+    if (const char *e = getenv("VT_SLICE_CHUNKS")) {  // tuning knob
+        if (atoi(e) > 0) {
+            z_chunk = (nz + atoi(e) - 1) / atoi(e);
+            chunks = (nz + z_chunk - 1) / z_chunk;
+        }
+    }
     dim3 grid(tiles, chunks, P.n_mats);
     if (chunks > 65535 || P.n_mats > 65535) return VT_ERR_UNSUPPORTED;
     const bool tma = tma_ok(P) && !(P.flags & VT_STAGE_CP_ASYNC);
