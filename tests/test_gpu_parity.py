@@ -265,6 +265,36 @@ def test_brick_family(vt, shape, interp):
         assert N.affine_plan(v2.data_ptr(), odd, odd, mats['rot_general'], interp) == 'gather'
 
 
+@pytest.mark.parametrize('mode', MODES)
+def test_host_pipeline(vt, mode):
+    """numpy in -> numpy out on volumes deep enough for the chunked upload/prefilter/resample/download pipeline
+    (>= 64 planes: several chunks): same result as the device-resident path and as the oracle, for matrices that
+    can stream (axis-0 rotations, with and without an integer shift along axis 0) and for one that cannot."""
+    import torch
+    shape = (100, 40, 52)
+    rng = np.random.default_rng(23)
+    vol = rng.random(shape, dtype=np.float32)
+    r = _range(vol, mode)
+    c = _center(shape)
+    tm = vt.utils.transform_matrix
+    mats = {'rot45': tm(rotation=(0, 45, 0), rotation_order='rzxz', center=c),
+            'rot30_shift_z+7': tm(rotation=(0, 30, 0), rotation_order='rzxz', center=c, translation=(7, 1.5, -2)),
+            'rot30_shift_z-9': tm(rotation=(0, 30, 0), rotation_order='rzxz', center=c, translation=(-9, 0, 0.25)),
+            'full_affine': _matrices(vt, shape)['full_affine']}
+    dvol = torch.from_numpy(vol).cuda()
+    for name, m in mats.items():
+        got = vt.affine(vol, m, interpolation=mode, device='gpu:0')          # host path (pipelined)
+        dev = torch.zeros(shape, device='cuda')
+        vt.affine(dvol, m, interpolation=mode, output=dev, device='gpu:0')   # device path
+        want = oracle.affine(vol, m, mode)
+        assert _err(got, want, r) <= TOL[mode], (mode, name, _err(got, want, r))
+        assert _err(got, dev.cpu().numpy(), r) <= 1e-6, (mode, name, _err(got, dev.cpu().numpy(), r))
+    # numpy output= buffer: voxels outside the source are written as zeros on this path too
+    out = np.full(shape, 5.0, dtype=np.float32)
+    vt.affine(vol, mats['rot45'], interpolation=mode, output=out, device='gpu:0')
+    assert _err(out, oracle.affine(vol, mats['rot45'], mode), r) <= TOL[mode]
+
+
 def test_output_semantics(vt):
     """output= given: written in place, out-of-bounds voxels keep their contents, returns None
     (transforms.py:207-210, :224-226); input arrays are never modified."""

@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -18,6 +19,10 @@ int vt_slice_supported(const VtResampleParams &P, int interp);                  
 int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter.cu
 int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
                      float *d_ws, size_t ws_bytes, cudaStream_t st);  // vt_prefilter_win.cu
+int vt_prefilter_xy_range(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
+                          int z0, int z1, cudaStream_t st);  // vt_prefilter_win.cu
+int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, int z0, int z1, int chunks,
+                         cudaStream_t st);  // vt_prefilter_win.cu
 
 static std::atomic<long long> g_launches{0};
 void vt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -25,6 +30,8 @@ void vt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed)
 // ---------------------------------------------------------------------------------------------------
 // per-kernel device timing
 // ---------------------------------------------------------------------------------------------------
+#define VT_HOST_MAX_CHUNKS 16
+
 namespace {
 struct ProfRec {
     int id;
@@ -338,7 +345,8 @@ struct vt_host_ctx {
     cudaStream_t st_in, st_k, st_out;
     float *d_src, *d_dst, *d_coef, *d_ws;
     size_t cap_src, cap_dst, cap_coef, cap_ws;
-    cudaEvent_t ev_in, ev_k;
+    cudaEvent_t ev_k;
+    cudaEvent_t ev_in[VT_HOST_MAX_CHUNKS];
 };
 
 int vt_host_ctx_create(int device, vt_host_ctx **out)
@@ -354,8 +362,8 @@ int vt_host_ctx_create(int device, vt_host_ctx **out)
     VT_CUDA(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     VT_CUDA(cudaStreamCreateWithFlags(&c->st_k, cudaStreamNonBlocking));
     VT_CUDA(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
-    VT_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     VT_CUDA(cudaEventCreateWithFlags(&c->ev_k, cudaEventDisableTiming));
+    for (int i = 0; i < VT_HOST_MAX_CHUNKS; i++) VT_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
     *out = c;
     return VT_OK;
 }
@@ -371,13 +379,24 @@ int vt_host_ctx_destroy(vt_host_ctx *c)
     cudaFree(c->d_dst);
     cudaFree(c->d_coef);
     cudaFree(c->d_ws);
-    cudaEventDestroy(c->ev_in);
     cudaEventDestroy(c->ev_k);
+    for (int i = 0; i < VT_HOST_MAX_CHUNKS; i++) cudaEventDestroy(c->ev_in[i]);
     cudaStreamDestroy(c->st_in);
     cudaStreamDestroy(c->st_k);
     cudaStreamDestroy(c->st_out);
     delete c;
     return VT_OK;
+}
+
+// dense rows -> rows padded to `row` floats (pad columns zero); one thread per destination element
+__global__ void vt_pad_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int row, size_t rows)
+{
+    const size_t n = rows * (size_t)row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (unsigned)row;
+        const int x = (int)(i - r * (unsigned)row);
+        dst[i] = x < w ? src[r * (size_t)w + x] : 0.0f;
+    }
 }
 
 static int ensure(float **p, size_t *cap, size_t bytes)
@@ -391,53 +410,116 @@ static int ensure(float **p, size_t *cap, size_t bytes)
     return VT_OK;
 }
 
+// Pipeline of the host-buffer path.  The volume is uploaded in z-chunks on the copy stream; as each chunk lands the
+// compute stream runs the XY prefilter of its planes (planes are independent), the Z prefilter of every plane whose
+// 12-plane look-ahead is now complete, the resampling of every output plane whose input planes are final, and the
+// download stream ships those output planes.  Upload and download overlap (PCIe is full duplex), so a call costs
+// about one upload plus a two-chunk tail instead of upload + kernels + download.  The early resampling needs a
+// matrix of the slice family (output plane z reads input planes z + t0 - 1 .. z + t0 + 1); for a general matrix
+// every output plane can read any input plane, so the resampling waits for the whole volume and only the download
+// is overlapped (in z-slabs).
 int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s2, float *h_dst, int o0, int o1, int o2,
                        const float *h_m16, int interp, int prefilter, unsigned flags)
 {
     if (!c || !h_src || !h_dst || !h_m16) return VT_ERR_INVALID_ARG;
     if (s0 < 1 || s1 < 1 || s2 < 1 || o0 < 1 || o1 < 1 || o2 < 1) return VT_ERR_INVALID_ARG;
+    if (interp != VT_LINEAR && interp != VT_CUBIC_TEX && interp != VT_CUBIC_SIMPLE) return VT_ERR_INVALID_ARG;
     DeviceGuard g(c->device);
     if (g.status) return g.status;
-    const size_t nsrc = (size_t)s0 * s1 * s2, plane_out = (size_t)o1 * o2;
+    const size_t plane_in = (size_t)s1 * s2, plane_out = (size_t)o1 * o2;
     // device copies keep their rows padded to 16 bytes so that the resampling kernels can stage with TMA whatever
     // the width is; the upload itself does the padding (2-D copy), the prefilter writes padded rows directly
     const long long row = ((long long)s2 + 3) / 4 * 4, plane = row * s1;
     int rc = ensure(&c->d_dst, &c->cap_dst, (size_t)o0 * plane_out * 4);
     if (rc) return rc;
-    const float *sampled;
+    rc = ensure(&c->d_coef, &c->cap_coef, (size_t)plane * s0 * 4);
+    if (rc) return rc;
+    // an unfiltered volume whose rows are not a multiple of 16 bytes is uploaded densely and padded on the device
+    // (a 2-D copy with 1000-byte rows runs at a seventh of the PCIe rate)
+    const bool pad = !prefilter && row != s2;
+    if (prefilter || pad) {
+        rc = ensure(&c->d_src, &c->cap_src, plane_in * s0 * 4);
+        if (rc) return rc;
+    }
     if (prefilter) {
-        rc = ensure(&c->d_src, &c->cap_src, nsrc * 4);
-        if (rc) return rc;
-        rc = ensure(&c->d_coef, &c->cap_coef, (size_t)plane * s0 * 4);
-        if (rc) return rc;
-        // upload (the source is needed whole before any output plane can be gathered under a general affine map)
-        VT_CUDA(cudaMemcpyAsync(c->d_src, h_src, nsrc * 4, cudaMemcpyHostToDevice, c->st_k));
         rc = ensure(&c->d_ws, &c->cap_ws, (size_t)plane * s0 * 4);
         if (rc) return rc;
-        rc = vt_prefilter_ws_f32(c->d_src, c->d_coef, s0, s1, s2, row, plane, c->d_ws, c->cap_ws, 0, -1, c->st_k);
-        if (rc) return rc;
-        sampled = c->d_coef;
-    } else {
-        rc = ensure(&c->d_src, &c->cap_src, (size_t)plane * s0 * 4);
-        if (rc) return rc;
-        VT_CUDA(cudaMemcpy2DAsync(c->d_src, (size_t)row * 4, h_src, (size_t)s2 * 4, (size_t)s2 * 4, (size_t)s0 * s1,
-                                  cudaMemcpyHostToDevice, c->st_k));
-        sampled = c->d_src;
     }
-    // output=None semantics (transforms.py:207-210): skipped voxels are zero -> fused as VT_OOB_ZERO.
-    // z-slabs: the kernel of slab i+1 overlaps the download of slab i.
+    // output=None semantics (transforms.py:207-210): skipped voxels are zero -> fused as VT_OOB_ZERO
     const unsigned fl = (flags & ~1u) | VT_OOB_ZERO;
-    int nslab = o0 >= 8 ? 8 : 1;
-    for (int sl = 0; sl < nslab; sl++) {
-        const int z0 = (int)((long long)o0 * sl / nslab), z1 = (int)((long long)o0 * (sl + 1) / nslab);
-        if (z1 <= z0) continue;
-        rc = vt_affine_strided_f32(sampled, s0, s1, s2, row, plane, c->d_dst, o0, o1, o2, 0, h_m16, 1, interp, fl, z0, z1, -1,
-                                   c->st_k);
-        if (rc) return rc;
-        VT_CUDA(cudaEventRecord(c->ev_k, c->st_k));
-        VT_CUDA(cudaStreamWaitEvent(c->st_out, c->ev_k, 0));
-        VT_CUDA(cudaMemcpyAsync(h_dst + (size_t)z0 * plane_out, c->d_dst + (size_t)z0 * plane_out,
-                                (size_t)(z1 - z0) * plane_out * 4, cudaMemcpyDeviceToHost, c->st_out));
+    // can output planes be produced before the whole input is there?
+    VtResampleParams P;
+    rc = fill_params(P, c->d_coef, s0, s1, s2, row, plane, c->d_dst, o0, o1, o2, 0, fl, 0, o0);
+    if (rc) return rc;
+    copy_mats(P, h_m16, 0, 1);
+    const bool slice = choose_family(P, interp, fl) == 3;
+    const int t0 = slice ? (int)P.mats[0].r[0][3] : 0;
+    const int margin = interp == VT_LINEAR ? 0 : 1;
+    const int KZ = 12;  // look-ahead of the Z prefilter (vt_prefilter_win.cu)
+
+    // chunk count: 4-8 chunks of >= 32 planes (measured on B200 / PCIe 5 x16: 250^3 filt_bspline 2.41 ms with one
+    // chunk, 1.83 ms with 4-8, no better with 16 -- per-chunk event and launch latencies start to show)
+    int nch = s0 / 32;
+    if (nch > 8) nch = 8;
+    if (const char *e = getenv("VT_HOST_CHUNKS")) nch = atoi(e);  // tuning knob
+    if (nch > VT_HOST_MAX_CHUNKS) nch = VT_HOST_MAX_CHUNKS;
+    if (nch < 1) nch = 1;
+    // 1) the whole upload, chunk by chunk, on the copy stream
+    for (int i = 0; i < nch; i++) {
+        const int h0 = (int)((long long)s0 * i / nch), h1 = (int)((long long)s0 * (i + 1) / nch);
+        float *up = (prefilter || pad) ? c->d_src : c->d_coef;  // dense either way
+        VT_CUDA(cudaMemcpyAsync(up + (size_t)h0 * plane_in, h_src + (size_t)h0 * plane_in,
+                                (size_t)(h1 - h0) * plane_in * 4, cudaMemcpyHostToDevice, c->st_in));
+        VT_CUDA(cudaEventRecord(c->ev_in[i], c->st_in));
+    }
+    // 2) kernels behind it on the compute stream, downloads behind those on the download stream
+    int z_done = 0, o_done = 0;
+    for (int i = 0; i < nch; i++) {
+        const int h0 = (int)((long long)s0 * i / nch), h1 = (int)((long long)s0 * (i + 1) / nch);
+        VT_CUDA(cudaStreamWaitEvent(c->st_k, c->ev_in[i], 0));
+        int ready = h1;  // sampled planes [0, ready) are final
+        if (prefilter) {
+            rc = vt_prefilter_xy_range(c->d_src, c->d_ws, s0, s1, s2, row, plane, h0, h1, c->st_k);
+            if (rc == VT_ERR_UNSUPPORTED) return rc;  // (rows too long for the windowed kernels: not on this path)
+            if (rc) return rc;
+            const int zn = h1 == s0 ? s0 : h1 - KZ;
+            if (zn > z_done) {
+                rc = vt_prefilter_z_range(c->d_ws, c->d_coef, s0, (size_t)plane, z_done, zn, nch > 1 ? 1 : 0, c->st_k);
+                if (rc) return rc;
+                z_done = zn;
+            }
+            ready = z_done;
+        } else if (pad) {
+            const size_t rows = (size_t)(h1 - h0) * s1;
+            const size_t n = rows * (size_t)row;
+            const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+            vt_pad_rows_kernel<<<blocks, 256, 0, c->st_k>>>(c->d_src + (size_t)h0 * plane_in, c->d_coef + (size_t)h0 * plane,
+                                                           s2, (int)row, rows);
+            vt_count_launch();
+            VT_CUDA(cudaGetLastError());
+        }
+        int on = o_done;
+        if (ready == s0) on = o0;
+        else if (slice) {
+            const long long lim = (long long)ready - t0 - margin;
+            on = (int)(lim < o_done ? o_done : (lim > o0 ? o0 : lim));
+        }
+        if (on <= o_done) continue;
+        // a general matrix produces everything at the end: cut it into slabs so that the download still overlaps
+        const int pieces = (!slice && on - o_done >= 8) ? 8 : 1;
+        const int base = o_done, span = on - o_done;
+        for (int pc = 0; pc < pieces; pc++) {
+            const int z0 = base + (int)((long long)span * pc / pieces), z1 = base + (int)((long long)span * (pc + 1) / pieces);
+            if (z1 <= z0) continue;
+            rc = vt_affine_strided_f32(c->d_coef, s0, s1, s2, row, plane, c->d_dst, o0, o1, o2, 0, h_m16, 1, interp, fl, z0,
+                                       z1, -1, c->st_k);
+            if (rc) return rc;
+            VT_CUDA(cudaEventRecord(c->ev_k, c->st_k));
+            VT_CUDA(cudaStreamWaitEvent(c->st_out, c->ev_k, 0));
+            VT_CUDA(cudaMemcpyAsync(h_dst + (size_t)z0 * plane_out, c->d_dst + (size_t)z0 * plane_out,
+                                    (size_t)(z1 - z0) * plane_out * 4, cudaMemcpyDeviceToHost, c->st_out));
+        }
+        o_done = on;
     }
     VT_CUDA(cudaStreamSynchronize(c->st_out));
     VT_CUDA(cudaStreamSynchronize(c->st_k));

@@ -136,12 +136,12 @@ __device__ __forceinline__ void x_pass(float *tb, int xc, const float (&cf)[SEG]
 template <int NT>
 __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restrict__ src, float *__restrict__ dst, int H,
                                                           int W, long long dst_row, long long dst_plane, int y_chunk,
-                                                          int x_strip)
+                                                          int x_strip, int z_first)
 {
     constexpr int L = NT / RB;   // chunks (X-pass lanes) per row
     constexpr int P = L * SEG;   // tile row pitch in floats (= NT)
     extern __shared__ __align__(16) float smem[];  // two tiles [RB][P]
-    const int z = blockIdx.z;
+    const int z = z_first + blockIdx.z;
     const int x0 = blockIdx.x * x_strip, x1 = min(x0 + x_strip, W);  // columns written by this CTA
     const int xa = max(x0 - HX, 0), xb = min(x1 + HX, W);            // columns staged (X warm-up on both sides)
     const int sw = xb - xa;
@@ -260,12 +260,12 @@ constexpr int Z_THREADS = 128;
 
 // src may equal dst (in place): no __restrict__ here
 __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src, float *dst, int D, size_t cols,
-                                                                int z_chunk)
+                                                                int z_chunk, int z_begin, int z_end)
 {
     const size_t col = (size_t)blockIdx.x * Z_THREADS + threadIdx.x;
     if (col >= cols) return;
-    const int zc0 = blockIdx.y * z_chunk;          // this CTA emits planes [zc0, zc1)
-    const int zc1 = min(zc0 + z_chunk, D);
+    const int zc0 = z_begin + blockIdx.y * z_chunk;  // this CTA emits planes [zc0, zc1)
+    const int zc1 = min(zc0 + z_chunk, z_end);
     const float *s = src + col;
     float *d = dst + col;
 
@@ -273,8 +273,9 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
     float prev;
     int zw;            // plane index of cp[0]
     // ---- start-up: fill cp[0..K) ----
-    if (zc0 == 0) {
-        // exact start of the line (InitialCausalCoefficient, bspline.h:2-19)
+    if (zc0 <= K) {
+        // the start of the line is within reach: exact start (InitialCausalCoefficient, bspline.h:2-19), then the
+        // plain recursion up to the chunk
         float first[12];  // loaded together (independent), then summed in the reference's order
 #pragma unroll
         for (int k = 0; k < 12; k++) first[k] = k < D ? s[(size_t)k * cols] : 0.0f;
@@ -285,17 +286,17 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
             zn = __fmul_rn(zn, kPole);
         }
         prev = __fmul_rn(kLambda, sum);
-        zw = 0;
-        cp[0] = prev;
+        for (int zz = 1; zz < zc0; zz++) prev = causal_step(s[(size_t)zz * cols], prev);
+        zw = zc0;
 #pragma unroll
-        for (int k = 1; k < K; k++) {
+        for (int k = 0; k < K; k++) {
             const int zz = zw + k;
-            if (zz < D) prev = causal_step(s[(size_t)zz * cols], prev);
+            if (zz > 0 && zz < D) prev = causal_step(s[(size_t)zz * cols], prev);
             cp[k] = prev;
         }
     } else {
         // warm-up K planes before the chunk, then the first K planes of the chunk
-        const int zs = zc0 - K;  // >= 0 because chunks are >= K planes long
+        const int zs = zc0 - K;  // > 0
         prev = __fmul_rn(kWarm, s[(size_t)zs * cols]);
 #pragma unroll
         for (int k = 1; k < K; k++) prev = causal_step(s[(size_t)(zs + k) * cols], prev);
@@ -373,24 +374,76 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
 int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);  // vt_prefilter.cu
 
 template <int NT>
-int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long dst_row, long long dst_plane, cudaStream_t st)
+int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long dst_row, long long dst_plane, int z0, int z1,
+              cudaStream_t st)
 {
     const int x_strip = W <= NT ? W : NT - 2 * HX;
     const int strips = (W + x_strip - 1) / x_strip;
     const size_t smem = (size_t)2 * RB * NT * sizeof(float);
+    const int nz = z1 - z0;
     // y-chunks: enough CTAs to fill the GPU, chunks of at least 64 rows (each pays 2*K rows of warm-up / look-ahead)
-    int chunks = (200 + D * strips - 1) / (D * strips);
+    int chunks = (200 + nz * strips - 1) / (nz * strips);
     const int max_chunks = H / 64 > 0 ? H / 64 : 1;
     if (chunks > max_chunks) chunks = max_chunks;
     if (const char *e = getenv("VT_XY_CHUNKS")) chunks = atoi(e) > 0 ? atoi(e) : chunks;  // tuning knob
     int y_chunk = (H + chunks - 1) / chunks;
     chunks = (H + y_chunk - 1) / y_chunk;
-    if (D > 65535 || chunks > 65535) return VT_ERR_UNSUPPORTED;
+    if (nz > 65535 || chunks > 65535) return VT_ERR_UNSUPPORTED;
     // per device, so not cached in a static: a process may drive several GPUs
     VT_CUDA(cudaFuncSetAttribute(prefilter_xy_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VtProf prof(VT_K_PREFILTER_FUSED, st);
-    prefilter_xy_kernel<NT><<<dim3(strips, chunks, D), NT, smem, st>>>(d_src, d_dst, H, W, dst_row, dst_plane, y_chunk,
-                                                                      x_strip);
+    prefilter_xy_kernel<NT><<<dim3(strips, chunks, nz), NT, smem, st>>>(d_src, d_dst, H, W, dst_row, dst_plane, y_chunk,
+                                                                       x_strip, z0);
+    return VT_OK;
+}
+
+// X and Y passes of planes [z0, z1): d_src (dense) -> d_dst (padded strides).  Planes are independent.
+int vt_prefilter_xy_range(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
+                          int z0, int z1, cudaStream_t st)
+{
+    if (dst_row - d2 > 32) return VT_ERR_UNSUPPORTED;
+    if (z1 <= z0) return VT_OK;
+    int rc;
+    if (d2 <= 128) rc = launch_xy<128>(d_src, d_dst, d0, d1, d2, dst_row, dst_plane, z0, z1, st);
+    else if (d2 <= 256) rc = launch_xy<256>(d_src, d_dst, d0, d1, d2, dst_row, dst_plane, z0, z1, st);
+    else rc = launch_xy<512>(d_src, d_dst, d0, d1, d2, dst_row, dst_plane, z0, z1, st);
+    if (rc) return rc;
+    vt_count_launch();
+    VT_CUDA(cudaGetLastError());
+    return VT_OK;
+}
+
+// Z pass producing planes [z0, z1) of d_dst from the XY-filtered volume d_src (depth d0, `cols` columns per plane).
+// It reads planes [z0 - K, z1 + K) of d_src and nothing else (z0 must be 0 or > K).  d_src == d_dst (in place) is only valid for the whole range in one
+// chunk; out of place the range is cut into `chunks` z-chunks (0 = choose).
+int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, int z0, int z1, int chunks, cudaStream_t st)
+{
+    if (z1 <= z0) return VT_OK;
+    // planes the kernel may read: everything up to K past the range (a pipelined caller has not produced the
+    // rest of d_src yet); the anticausal restart at that artificial end is the usual |z|^12-accurate stand-in
+    const int d_avail = z1 + K < d0 ? z1 + K : d0;
+    const size_t bx = (cols + Z_THREADS - 1) / Z_THREADS;
+    if (bx > 0x7fffffffull || cols > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
+    const int nz = z1 - z0;
+    if (d_src == d_dst) {
+        if (z0 != 0 || z1 != d0) return VT_ERR_INVALID_ARG;
+        chunks = 1;
+    } else if (chunks <= 0) {
+        // aim at >= ~300 000 threads, chunks of at least 64 planes (each pays 2*K planes of warm-up / look-ahead)
+        chunks = (int)((300000 + cols - 1) / cols);
+        const int max_chunks = nz / 64 > 0 ? nz / 64 : 1;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (const char *e = getenv("VT_Z_CHUNKS")) chunks = atoi(e) > 0 ? atoi(e) : chunks;  // tuning knob
+    }
+    int z_chunk = ((nz + chunks - 1) / chunks + ZB - 1) / ZB * ZB;
+    chunks = (nz + z_chunk - 1) / z_chunk;
+    if (chunks > 65535) return VT_ERR_UNSUPPORTED;
+    {
+        VtProf prof(VT_K_PREFILTER_Z, st);
+        prefilter_z_kernel<<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>(d_src, d_dst, d_avail, cols, z_chunk, z0, z1);
+    }
+    vt_count_launch();
+    VT_CUDA(cudaGetLastError());
     return VT_OK;
 }
 
@@ -400,37 +453,10 @@ int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long d
 int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
                      float *d_ws, size_t ws_bytes, cudaStream_t st)
 {
-    const int D = d0, H = d1, W = d2;
-    if (dst_row - W > 32) return VT_ERR_UNSUPPORTED;
     const size_t cols = (size_t)dst_plane;  // columns of the (padded) plane: pad columns hold zeros and stay zero
-    const size_t bx = (cols + Z_THREADS - 1) / Z_THREADS;
-    if (bx > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
-    // z-chunks: aim at >= ~300 000 threads, chunks of at least 64 planes (each pays 2*K planes of warm-up/look-ahead)
-    int chunks = 1;
-    if (d_ws && ws_bytes >= cols * (size_t)D * sizeof(float) && d_ws != d_dst && d_ws != d_src) {
-        chunks = (int)((300000 + cols - 1) / cols);
-        const int max_chunks = D / 64 > 0 ? D / 64 : 1;
-        if (chunks > max_chunks) chunks = max_chunks;
-        if (const char *e = getenv("VT_Z_CHUNKS")) chunks = atoi(e) > 0 ? atoi(e) : chunks;  // tuning knob
-    }
-    float *xy_out = chunks > 1 ? d_ws : d_dst;
-    int rc;
-    if (W <= 128) rc = launch_xy<128>(d_src, xy_out, D, H, W, dst_row, dst_plane, st);
-    else if (W <= 256) rc = launch_xy<256>(d_src, xy_out, D, H, W, dst_row, dst_plane, st);
-    else rc = launch_xy<512>(d_src, xy_out, D, H, W, dst_row, dst_plane, st);
+    const bool have_ws = d_ws && ws_bytes >= cols * (size_t)d0 * sizeof(float) && d_ws != d_dst && d_ws != d_src;
+    float *xy_out = have_ws ? d_ws : d_dst;
+    int rc = vt_prefilter_xy_range(d_src, xy_out, d0, d1, d2, dst_row, dst_plane, 0, d0, st);
     if (rc) return rc;
-    vt_count_launch();
-    VT_CUDA(cudaGetLastError());
-    {
-        // in place the sweep must be one chunk: a neighbouring chunk's warm-up would read planes this one has
-        // already overwritten
-        int z_chunk = ((D + chunks - 1) / chunks + ZB - 1) / ZB * ZB;
-        chunks = (D + z_chunk - 1) / z_chunk;
-        if (chunks > 65535) return VT_ERR_UNSUPPORTED;
-        VtProf prof(VT_K_PREFILTER_Z, st);
-        prefilter_z_kernel<<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>(xy_out, d_dst, D, cols, z_chunk);
-    }
-    vt_count_launch();
-    VT_CUDA(cudaGetLastError());
-    return VT_OK;
+    return vt_prefilter_z_range(xy_out, d_dst, d0, cols, 0, d0, 0, st);
 }
