@@ -122,12 +122,9 @@ __device__ __forceinline__ float cubic_simple_brick(const Brick &b, float x, flo
     const float fx0 = floorf(cgx), fy0 = floorf(cgy), fz0 = floorf(cgz);
     const float fx = __fsub_rn(cgx, fx0), fy = __fsub_rn(cgy, fy0), fz = __fsub_rn(cgz, fz0);
     float wx[4], wy[4], wz[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        wx[k] = vt_bspline(__fsub_rn((float)(k - 1), fx));
-        wy[k] = vt_bspline(__fsub_rn((float)(k - 1), fy));
-        wz[k] = vt_bspline(__fsub_rn((float)(k - 1), fz));
-    }
+    vt_bspline4(fx, wx);
+    vt_bspline4(fy, wy);
+    vt_bspline4(fz, wz);
     const float *q = b.at((int)fz0 - 1, (int)fy0 - 1, (int)fx0 - 1);
     float r = 0.0f;
 #pragma unroll

@@ -111,12 +111,9 @@ __device__ __forceinline__ float cubic_simple(const SrcView &s, float x, float y
     const float fx = __fsub_rn(cgx, fx0), fy = __fsub_rn(cgy, fy0), fz = __fsub_rn(cgz, fz0);
     const int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
     float wx[4], wy[4], wz[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        wx[k] = vt_bspline(__fsub_rn((float)(k - 1), fx));
-        wy[k] = vt_bspline(__fsub_rn((float)(k - 1), fy));
-        wz[k] = vt_bspline(__fsub_rn((float)(k - 1), fz));
-    }
+    vt_bspline4(fx, wx);
+    vt_bspline4(fy, wy);
+    vt_bspline4(fz, wz);
     const bool interior = iz >= 1 && iy >= 1 && ix >= 1 && iz + 2 < s.s0 && iy + 2 < s.s1 && ix + 2 < s.s2;
     float result = 0.0f;
     if (interior) {

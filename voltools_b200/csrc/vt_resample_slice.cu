@@ -141,11 +141,8 @@ struct Taps<VT_CUBIC_SIMPLE> {
         const float fx0 = floorf(cgx), fy0 = floorf(cgy);
         const float fx = __fsub_rn(cgx, fx0), fy = __fsub_rn(cgy, fy0);
         float wx[4], wy[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            wx[k] = vt_bspline(__fsub_rn((float)(k - 1), fx));
-            wy[k] = vt_bspline(__fsub_rn((float)(k - 1), fy));
-        }
+        vt_bspline4(fx, wx);
+        vt_bspline4(fy, wy);
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
