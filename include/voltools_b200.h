@@ -123,6 +123,25 @@ int vt_affine_strided_f32(const float *d_src, int s0, int s1, int s2, long long 
                           float *d_dst, int o0, int o1, int o2, long long dst_batch_stride, const float *h_mats, int n_mats,
                           int interp, unsigned flags, int z_begin, int z_end, int device, void *stream);
 
+/*
+ * Texture family: the sampled volume as a 3-D CUDA array behind a texture object with the reference's descriptor
+ * (voltools/transforms.py:184-199, voltools/volume.py:37-50: float32 channel, border addressing, linear filter,
+ * unnormalised coordinates).  For VT_LINEAR and VT_CUBIC_TEX under a GENERAL matrix the hardware unit beats its
+ * software emulation (results are the unit's own, i.e. the reference's, bit for bit); matrices of the slice family
+ * and VT_CUBIC_SIMPLE stay on vt_affine_f32.  The handle owns the array (the one place besides vt_host_ctx where the
+ * library allocates device memory); vt_tex_create(d_src != NULL) also uploads (one 8 B/voxel device pass, stream
+ * ordered), vt_tex_upload re-uploads a volume of the same shape.
+ */
+typedef struct vt_tex vt_tex;
+int vt_tex_create(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,
+                  int device, void *stream, vt_tex **tex);
+int vt_tex_upload(vt_tex *tex, const float *d_src, long long src_row_stride, long long src_plane_stride, void *stream);
+int vt_tex_destroy(vt_tex *tex);
+/* the `transform` kernel launch (voltools/transforms.py:212, volume.py:78) on a texture handle; arguments as
+ * vt_affine_f32 (VT_WEIGHTS_EXACT and VT_CUBIC_SIMPLE are not available here) */
+int vt_affine_tex_f32(const vt_tex *tex, float *d_dst, int o0, int o1, int o2, long long dst_batch_stride,
+                      const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin, int z_end, void *stream);
+
 /* which kernel family vt_affine_f32 would run for these arguments: 1 = gather, 2 = brick, 3 = slice */
 int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d_src, const float *h_mats,
                    int n_mats, int interp, unsigned flags, int *family);

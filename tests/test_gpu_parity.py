@@ -339,6 +339,84 @@ def test_static_volume_and_batch(vt):
         assert _err(out.cpu().numpy(), oracle.affine(vol, vt.utils.rotation_matrix((0, 0, 10)), mode), r) <= TOL[mode]
 
 
+@pytest.mark.parametrize('shape', [(20, 24, 28), (33, 47, 45), (64, 64, 64)])
+@pytest.mark.parametrize('interp', [0, 1])
+def test_texture_family(vt, shape, interp):
+    """General matrices through a hardware texture object (vt_tex_* of the C ABI): the unit's own arithmetic, so
+    the oracle's texture model, the software-emulating kernels and this path must all agree to float32 rounding;
+    OOB policies, padded sources, batches and z-ranges behave as on the other families."""
+    import torch
+    N = vt._native
+    rng = np.random.default_rng(31)
+    vol_np = rng.random(shape, dtype=np.float32)
+    row = N.padded_row(shape[2])
+    padded = torch.zeros((shape[0], shape[1], row), device='cuda')
+    padded[:, :, :shape[2]] = torch.from_numpy(vol_np).cuda()
+    strides = (row, shape[1] * row)
+    tex = N.Texture(padded.data_ptr(), shape, strides, 0, torch.cuda.current_stream().cuda_stream)
+    mode = ['linear', 'bspline'][interp]
+    mats = _matrices(vt, shape)
+    for name, m in mats.items():
+        for flag in (N.OOB_ZERO, N.OOB_SKIP):
+            a = torch.full(shape, -7.0, device='cuda')
+            b = torch.full(shape, -7.0, device='cuda')
+            tex.affine(a.data_ptr(), shape, m, interp, flag)
+            N.affine(padded.data_ptr(), shape, b.data_ptr(), shape, m, interp, flag | N.KERNEL_GATHER, src_strides=strides)
+            a, b = a.cpu().numpy(), b.cpu().numpy()
+            assert np.array_equal(a == -7.0, b == -7.0), (name, 'skipped sets differ')
+            assert _err(a, b, 1.0) <= 1e-6, (name, _err(a, b, 1.0))
+        want = oracle.affine(vol_np, m, mode)
+        assert _err(np.where(a == -7.0, 0, a), want, 1.0) <= 1e-6, name
+    # batch + z-range
+    ms = [mats['rot_general'], mats['full_affine'], mats['downscale']]
+    out = torch.zeros((3,) + shape, device='cuda')
+    ref = torch.zeros((3,) + shape, device='cuda')
+    tex.affine(out.data_ptr(), shape, ms, interp, N.OOB_ZERO, z_range=(3, 11))
+    N.affine(padded.data_ptr(), shape, ref.data_ptr(), shape, ms, interp, N.OOB_ZERO | N.KERNEL_GATHER, z_range=(3, 11),
+             src_strides=strides)
+    assert float((out - ref).abs().max()) <= 1e-6
+    assert float(out[:, :3].abs().max()) == 0 and float(out[:, 11:].abs().max()) == 0
+    # re-upload of another volume of the same shape
+    vol2 = torch.rand(shape, device='cuda')
+    tex.upload(vol2.data_ptr())
+    tex.affine(out[0].data_ptr(), shape, ms[0], interp, N.OOB_ZERO)
+    N.affine(vol2.data_ptr(), shape, ref[0].data_ptr(), shape, ms[0], interp, N.OOB_ZERO | N.KERNEL_GATHER)
+    assert float((out[0] - ref[0]).abs().max()) <= 1e-6
+    tex.close()
+    # cubic_simple has no texture path
+    t2 = N.Texture(vol2.data_ptr(), shape)
+    with pytest.raises(RuntimeError):
+        t2.affine(out[0].data_ptr(), shape, ms[0], 2, N.OOB_ZERO)
+
+
+def test_static_volume_switches_to_texture(vt):
+    """A StaticVolume that keeps getting general matrices moves to the texture family after TEXTURE_AFTER of them;
+    results before and after the switch agree to float32 rounding, slice-family matrices never switch."""
+    import torch
+    shape = (36, 40, 44)
+    vol = np.random.default_rng(9).random(shape, dtype=np.float32)
+    c = _center(shape)
+    for mode in ('linear', 'filt_bspline'):
+        sv = vt.StaticVolume(vol, interpolation=mode, device='gpu:0')
+        r = _range(vol, mode)
+        mats = [vt.utils.transform_matrix(rotation=(10 + a, 20 + 2 * a, 30 - a), rotation_order='rzxz', center=c)
+                for a in range(sv.TEXTURE_AFTER + 4)]
+        first = sv.affine(mats[3])
+        assert getattr(sv, '_tex', None) is None
+        batch = sv.affine_many(mats).cpu().numpy()     # crosses the threshold: texture family
+        assert getattr(sv, '_tex', None) is not None
+        assert _err(batch[3], first, r) <= 1e-6
+        for k in (0, 7, len(mats) - 1):
+            assert _err(batch[k], oracle.affine(vol, mats[k], mode), r) <= TOL[mode]
+        again = sv.affine(mats[3])                      # single launches use it too from now on
+        assert np.array_equal(again, batch[3])
+        rot = sv.transform(rotation=(0, 30, 0))         # slice family: unaffected
+        assert _err(rot, oracle.affine(vol, vt.utils.transform_matrix(rotation=(0, 30, 0), center=c), mode), r) <= TOL[mode]
+    sv = vt.StaticVolume(vol, interpolation='bspline_simple', device='gpu:0')
+    sv.affine_many([vt.utils.transform_matrix(rotation=(10, 20, 30 + a), center=c) for a in range(20)])
+    assert getattr(sv, '_tex', None) is None
+
+
 def test_z_slabs_compose(vt):
     """z-slab sharding: disjoint slabs written by separate calls reproduce the single-call result exactly."""
     import torch

@@ -68,6 +68,22 @@ def main():
                         continue
                     print(f'{n}^3 {mname} {iname} {fname}: {ms:.3f} ms  {nvox / ms / 1e6:.1f} Gvox/s  '
                           f'({8 * nvox / ms / 1e6 / 6549.1 * 100:.1f}% roofline)')
+        # texture family (general matrices, linear / cubic_tex): upload cost and kernel
+        ms_up = timeit(lambda: _native.Texture(srcp.data_ptr(), shape, strides, 0, st).close(), iters=3, warm=1)
+        tex = _native.Texture(srcp.data_ptr(), shape, strides, 0, st)
+        print(f'{n}^3 texture create+upload+destroy: {ms_up:.3f} ms')
+        ms_up = timeit(lambda: tex.upload(srcp.data_ptr(), strides, st), iters=5, warm=1)
+        print(f'{n}^3 texture upload only: {ms_up:.3f} ms  ({8 * nvox / ms_up / 1e6:.0f} GB/s)')
+        for mname, m in mats.items():
+            for interp, iname in ((0, 'linear'), (1, 'cubic_tex')):
+                ms = timeit(lambda: tex.affine(dst.data_ptr(), shape, m, interp, _native.OOB_ZERO, stream=st))
+                ref = torch.zeros(shape, device='cuda')
+                _native.affine(srcp.data_ptr(), shape, ref.data_ptr(), shape, m, interp, _native.OOB_ZERO | _native.KERNEL_GATHER,
+                               stream=st, src_strides=strides)
+                err = float((ref - dst).abs().max())
+                print(f'{n}^3 {mname} {iname} tex: {ms:.3f} ms  {nvox / ms / 1e6:.1f} Gvox/s  '
+                      f'({8 * nvox / ms / 1e6 / 6549.1 * 100:.1f}% roofline)  max|tex - gather| = {err:.2e}')
+        tex.close()
         if oracle.ref_gpu_available() and n <= 512 and '--ref' in sys.argv:
             for mname, m in mats.items():
                 for mode in ('linear', 'bspline', 'bspline_simple', 'filt_bspline'):

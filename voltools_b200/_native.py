@@ -54,6 +54,10 @@ def lib():
         L.vt_affine_strided_f32.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i, _i,
                                             ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _i, _vp]
         L.vt_affine_plan.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _f32p, _i, _i, ctypes.c_uint, ctypes.POINTER(_i)]
+        L.vt_tex_create.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _i, _vp, ctypes.POINTER(_vp)]
+        L.vt_tex_upload.argtypes = [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _vp]
+        L.vt_tex_destroy.argtypes = [_vp]
+        L.vt_affine_tex_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _vp]
         L.vt_host_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
         L.vt_host_ctx_destroy.argtypes = [_vp]
         L.vt_host_affine_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f32p, _i, _i, ctypes.c_uint]
@@ -151,6 +155,42 @@ def affine_plan(src_ptr, src_shape, dst_shape, matrices, interp, flags=0):
     check(lib().vt_affine_plan(*map(int, src_shape), *map(int, dst_shape), src_ptr, mp, len(m), interp, flags,
                                ctypes.byref(fam)))
     return {1: 'gather', 2: 'brick', 3: 'slice'}[fam.value]
+
+
+class Texture:
+    """Owner of a vt_tex: the sampled volume as a 3-D CUDA array + texture object (texture kernel family)."""
+
+    def __init__(self, src_ptr, shape, src_strides=None, device=-1, stream=0):
+        self.shape = tuple(int(v) for v in shape)
+        if src_strides is None:
+            src_strides = (self.shape[2], self.shape[1] * self.shape[2])
+        self._h = _vp()
+        check(lib().vt_tex_create(src_ptr, *self.shape, int(src_strides[0]), int(src_strides[1]), device, stream,
+                                  ctypes.byref(self._h)))
+
+    def upload(self, src_ptr, src_strides=None, stream=0):
+        if src_strides is None:
+            src_strides = (self.shape[2], self.shape[1] * self.shape[2])
+        check(lib().vt_tex_upload(self._h, src_ptr, int(src_strides[0]), int(src_strides[1]), stream))
+
+    def affine(self, dst_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None, stream=0):
+        m, mp = _mats(matrices)
+        if batch_stride is None:
+            batch_stride = int(dst_shape[0]) * int(dst_shape[1]) * int(dst_shape[2])
+        z0, z1 = (0, dst_shape[0]) if z_range is None else z_range
+        check(lib().vt_affine_tex_f32(self._h, dst_ptr, *map(int, dst_shape), batch_stride, mp, len(m), interp, flags,
+                                      z0, z1, stream))
+
+    def close(self):
+        if self._h:
+            lib().vt_tex_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class HostContext:

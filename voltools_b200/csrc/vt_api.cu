@@ -24,6 +24,18 @@ int vt_prefilter_xy_range(const float *d_src, float *d_dst, int d0, int d1, int 
 int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, int z0, int z1, int chunks,
                          cudaStream_t st);  // vt_prefilter_win.cu
 
+struct vt_tex;
+int vt_launch_tex(const VtResampleParams &P, const vt_tex *t, int interp, cudaStream_t st);            // vt_resample_tex.cu
+int vt_tex_create_impl(int s0, int s1, int s2, int device, vt_tex **out);                              // vt_resample_tex.cu
+int vt_tex_upload_impl(vt_tex *t, const float *d_src, long long row, long long plane, cudaStream_t st);  // vt_resample_tex.cu
+int vt_tex_destroy_impl(vt_tex *t);                                                                    // vt_resample_tex.cu
+struct vt_tex {  // layout shared with vt_resample_tex.cu
+    cudaArray_t arr;
+    cudaTextureObject_t tex;
+    int s0, s1, s2;
+    int device;
+};
+
 static std::atomic<long long> g_launches{0};
 void vt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -45,7 +57,7 @@ long long g_prof_n[VT_K_COUNT];
 const char *const g_prof_names[VT_K_COUNT] = {
     "prefilter_x", "prefilter_y", "prefilter_z", "prefilter_fused", "gather_linear", "gather_cubic_tex",
     "gather_cubic_simple", "brick_linear", "brick_cubic_tex", "brick_cubic_simple", "slice_linear",
-    "slice_cubic_tex", "slice_cubic_simple"};
+    "slice_cubic_tex", "slice_cubic_simple", "tex_linear", "tex_cubic"};
 
 void prof_drain_locked()
 {
@@ -335,6 +347,69 @@ int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int 
 {
     return vt_affine_strided_f32(d_src, s0, s1, s2, s2, (long long)s1 * s2, d_dst, o0, o1, o2, dst_batch_stride, h_mats,
                                  n_mats, interp, flags, z_begin, z_end, device, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// texture family
+// ---------------------------------------------------------------------------------------------------
+int vt_tex_create(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,
+                  int device, void *stream, vt_tex **out)
+{
+    if (!out) return VT_ERR_INVALID_ARG;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    if (device < 0) VT_CUDA(cudaGetDevice(&device));
+    vt_tex *t = nullptr;
+    int rc = vt_tex_create_impl(s0, s1, s2, device, &t);
+    if (rc) return rc;
+    if (d_src) {
+        rc = vt_tex_upload_impl(t, d_src, src_row_stride, src_plane_stride, (cudaStream_t)stream);
+        if (rc) {
+            vt_tex_destroy_impl(t);
+            return rc;
+        }
+    }
+    *out = t;
+    return VT_OK;
+}
+
+int vt_tex_upload(vt_tex *t, const float *d_src, long long src_row_stride, long long src_plane_stride, void *stream)
+{
+    if (!t) return VT_ERR_INVALID_ARG;
+    DeviceGuard g(t->device);
+    if (g.status) return g.status;
+    return vt_tex_upload_impl(t, d_src, src_row_stride, src_plane_stride, (cudaStream_t)stream);
+}
+
+int vt_tex_destroy(vt_tex *t)
+{
+    if (!t) return VT_OK;
+    DeviceGuard g(t->device);
+    return vt_tex_destroy_impl(t);
+}
+
+int vt_affine_tex_f32(const vt_tex *t, float *d_dst, int o0, int o1, int o2, long long dst_batch_stride,
+                      const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin, int z_end, void *stream)
+{
+    if (!t || !h_mats || n_mats < 0) return VT_ERR_INVALID_ARG;
+    if (interp != VT_LINEAR && interp != VT_CUBIC_TEX) return VT_ERR_INVALID_ARG;
+    if (flags & VT_WEIGHTS_EXACT) return VT_ERR_UNSUPPORTED;  // the unit's weights are what they are
+    if (n_mats == 0) return VT_OK;
+    VtResampleParams P;
+    float dummy;  // fill_params wants a source pointer; this family reads the texture
+    int rc = fill_params(P, &dummy, t->s0, t->s1, t->s2, t->s2, (long long)t->s1 * t->s2, d_dst, o0, o1, o2,
+                         dst_batch_stride, flags, z_begin, z_end);
+    if (rc) return rc;
+    DeviceGuard g(t->device);
+    if (g.status) return g.status;
+    for (int first = 0; first < n_mats; first += VT_MAX_BATCH) {
+        const int count = (n_mats - first) < VT_MAX_BATCH ? (n_mats - first) : VT_MAX_BATCH;
+        copy_mats(P, h_mats, first, count);
+        P.dst = d_dst + (size_t)first * dst_batch_stride;
+        rc = vt_launch_tex(P, t, interp, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return VT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/voltools_b200.h"
 
 #define VT_CUDA(x)                                  \
@@ -58,6 +59,8 @@ enum VtKernelId {
     VT_K_SLICE_LINEAR,
     VT_K_SLICE_CUBIC_TEX,
     VT_K_SLICE_CUBIC_SIMPLE,
+    VT_K_TEX_LINEAR,
+    VT_K_TEX_CUBIC,
     VT_K_COUNT
 };
 struct VtProf {

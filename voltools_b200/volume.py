@@ -92,6 +92,35 @@ class StaticVolume:
         self._coeffs = coeffs
         return self
 
+    # -- kernel family choice ---------------------------------------------------------------------------
+    #: general-matrix transforms of one StaticVolume after which the texture family takes over.  Creating the CUDA
+    #: array costs ~9 ms (cudaMalloc3DArray) + one 8 B/voxel upload; per 512^3 transform it then saves 0.3 ms
+    #: (linear, 340 vs 193 Gvox/s) or 0.55 ms (bspline / filt_bspline, 66 vs 52 Gvox/s) over the brick kernels.
+    TEXTURE_AFTER = 16
+
+    def _launch(self, dst_ptr, m, flags, stream):
+        """One launch set for the matrices `m` (K, 4, 4) on the resident volume.
+
+        Matrices of the slice family (rotations about axis 0 ...) always run the plane-marching kernels.  For the
+        two interpolators that ARE the texture unit (linear, bspline / filt_bspline) a general matrix runs on a
+        hardware texture object once this volume has seen TEXTURE_AFTER such transforms -- the reference keeps the
+        same second copy (volume.py:37-50); until then, and always for *_simple, the shared-memory brick kernels."""
+        use_tex = False
+        if self._interp in (_native.LINEAR, _native.CUBIC_TEX) and getattr(self, '_tex', None) is not False:
+            if _native.affine_plan(self._coeffs.data_ptr(), self.shape, self.shape, m, self._interp) != 'slice':
+                self._general = getattr(self, '_general', 0) + len(m)
+                use_tex = getattr(self, '_tex', None) is not None or self._general >= self.TEXTURE_AFTER
+        if use_tex and getattr(self, '_tex', None) is None:
+            try:
+                self._tex = _native.Texture(self._coeffs.data_ptr(), self.shape, self._strides, self._dev, stream)
+            except RuntimeError:
+                self._tex, use_tex = False, False  # extent beyond the 3-D texture limits / no memory: stay on bricks
+        if use_tex:
+            self._tex.affine(dst_ptr, self.shape, m, self._interp, flags, stream=stream)
+        else:
+            _native.affine(self._coeffs.data_ptr(), self.shape, dst_ptr, self.shape, m, self._interp, flags,
+                           device=self._dev, stream=stream, src_strides=self._strides)
+
     # -- transforms ---------------------------------------------------------------------------------------
     def affine(self, transform_m: np.ndarray, profile: bool = False, output=None) -> Union[np.ndarray, None]:
         """volume.py:61-101."""
@@ -107,11 +136,9 @@ class StaticVolume:
             stream = _stream(self._dev)
             if vout is None:
                 out_t = torch.empty(self.shape, dtype=torch.float32, device=f'cuda:{self._dev}')
-                _native.affine(self._coeffs.data_ptr(), self.shape, out_t.data_ptr(), self.shape, m, self._interp,
-                               _native.OOB_ZERO, device=self._dev, stream=stream, src_strides=self._strides)
+                self._launch(out_t.data_ptr(), m[None], _native.OOB_ZERO, stream)
             else:
-                _native.affine(self._coeffs.data_ptr(), self.shape, vout.ptr, self.shape, m, self._interp,
-                               _native.OOB_SKIP, device=self._dev, stream=stream, src_strides=self._strides)
+                self._launch(vout.ptr, m[None], _native.OOB_SKIP, stream)
             if profile:
                 t1.record()
                 t1.synchronize()
@@ -139,8 +166,7 @@ class StaticVolume:
                     raise ValueError(f'output shape {vout.shape} does not match {(k,) + self.shape}')
                 out_t, ptr = None, vout.ptr
                 flags = _native.OOB_ZERO if zero_fill else _native.OOB_SKIP
-            _native.affine(self._coeffs.data_ptr(), self.shape, ptr, self.shape, m, self._interp, flags,
-                           device=self._dev, stream=stream, src_strides=self._strides)
+            self._launch(ptr, m, flags, stream)
         return out_t
 
     def transform(self, scale: Union[float, Tuple[float, float, float], np.ndarray] = None,
