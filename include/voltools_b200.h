@@ -124,6 +124,19 @@ int vt_affine_strided_f32(const float *d_src, int s0, int s1, int s2, long long 
                           int interp, unsigned flags, int z_begin, int z_end, int device, void *stream);
 
 /*
+ * Streaming form of the windowed prefilter, for callers that pipeline it with an upload or a broadcast (the library's
+ * own host path, the multi-GPU layer): X and Y passes of sample planes [xy_begin, xy_end) of d_src into the workspace
+ * (planes are independent), then the Z pass producing coefficient planes [z_begin, z_end) of d_dst from the workspace.
+ * The Z pass reads workspace planes [z_begin - 12, z_end + 12) (clipped to the volume), so those must have been
+ * produced by this or an earlier call.  Workspace and d_dst use the same padded strides; all
+ * three buffers are distinct.  Covering [0, d0) with consecutive calls gives the coefficients of
+ * vt_prefilter_strided_f32 (variant 0) to ~1e-7 of their range.
+ */
+int vt_prefilter_planes_f32(const float *d_src, float *d_workspace, float *d_dst, int d0, int d1, int d2,
+                            long long dst_row_stride, long long dst_plane_stride, int xy_begin, int xy_end, int z_begin,
+                            int z_end, int device, void *stream);
+
+/*
  * Texture family: the sampled volume as a 3-D CUDA array behind a texture object with the reference's descriptor
  * (voltools/transforms.py:184-199, voltools/volume.py:37-50: float32 channel, border addressing, linear filter,
  * unnormalised coordinates).  For VT_LINEAR and VT_CUBIC_TEX under a GENERAL matrix the hardware unit beats its

@@ -148,6 +148,29 @@ def test_prefilter_windows_large(vt):
         assert float((rec[inner] - src[inner]).abs().max()) <= 2e-5
 
 
+@pytest.mark.parametrize('shape,chunks', [((100, 40, 52), 3), ((64, 33, 70), 8), ((150, 20, 250), 5), ((13, 16, 18), 3)])
+def test_prefilter_streaming(vt, shape, chunks):
+    """vt_prefilter_planes_f32 fed chunk by chunk (the multi-GPU layer's pipelined prepare, with its own plan) gives
+    the coefficients of the one-shot prefilter, including chunk boundaries inside the first 12 planes."""
+    import torch
+    from voltools_b200 import multigpu
+    N = vt._native
+    st = torch.cuda.current_stream().cuda_stream
+    src = torch.rand(shape, device='cuda', generator=torch.Generator('cuda').manual_seed(11))
+    row = N.padded_row(shape[2])
+    strides = (row, shape[1] * row)
+    ws = torch.full((shape[0], shape[1], row), float('nan'), device='cuda')   # planes not yet produced are poison
+    got = torch.full((shape[0], shape[1], row), float('nan'), device='cuda')
+    for xy0, xy1, z0, z1 in multigpu.stream_plan(shape[0], True, chunks):
+        N.prefilter_planes(src.data_ptr(), ws.data_ptr(), got.data_ptr(), shape, strides, (xy0, xy1), (z0, z1), 0, st)
+    ref = src.clone()
+    N.prefilter(ref.data_ptr(), shape, 0, st, variant=1)
+    r = float(ref.max() - ref.min())
+    assert not bool(torch.isnan(got).any())
+    assert float((got[:, :, :shape[2]] - ref).abs().max()) / r <= 1e-6
+    assert float(got[:, :, shape[2]:].abs().max() if row > shape[2] else 0.0) == 0.0
+
+
 def _slice_matrices(vt, shape):
     c = _center(shape)
     tm = vt.utils.transform_matrix

@@ -14,6 +14,19 @@ from voltools_b200 import multigpu
 from voltools_b200.utils import transform_matrix
 
 
+def test_stream_plan_covers_the_volume_in_order():
+    for d0 in (1, 13, 64, 100, 250, 512, 1024):
+        for filtered in (False, True):
+            for chunks in (None, 1, 3, 8):
+                plan = multigpu.stream_plan(d0, filtered, chunks)
+                assert plan[0][0] == 0 and plan[-1][1] == d0 and plan[0][2] == 0 and plan[-1][3] == d0
+                for (a0, a1, z0, z1), (b0, b1, y0, y1) in zip(plan, plan[1:]):
+                    assert a1 == b0 and z1 == y0 and z0 <= z1
+                for xy0, xy1, z0, z1 in plan:
+                    # the Z pass may only touch planes whose XY passes are done, 12 planes of look-ahead included
+                    assert z1 <= xy1 and (not filtered or z1 == d0 or z1 <= xy1 - multigpu.PREFILTER_LOOKAHEAD or z1 == z0)
+
+
 def test_partitions_cover_everything_once():
     for n in (0, 1, 2, 7, 180, 181, 1024):
         for world in (1, 2, 3, 4, 8):
@@ -34,6 +47,17 @@ class OracleEngine:
         import torch
         v = oracle.prefilter(volume) if interpolation.startswith('filt') else np.asarray(volume, np.float32)
         return torch.from_numpy(np.ascontiguousarray(v)), v.shape[2]
+
+    def describe(self, volume, interpolation):
+        return tuple(int(v) for v in volume.shape), int(volume.shape[2])
+
+    def prepare_stream(self, volume, interpolation, buffer, plan):
+        coef, _ = self.prepare(volume, interpolation)
+
+        def step(i):
+            _, _, z0, z1 = plan[i]
+            buffer[z0:z1].copy_(coef[z0:z1])
+        return step
 
     def empty(self, shape):
         import torch

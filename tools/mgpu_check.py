@@ -15,7 +15,7 @@ from voltools_b200 import multigpu  # noqa: E402
 rank, local, world = int(os.environ['RANK']), int(os.environ['LOCAL_RANK']), int(os.environ['WORLD_SIZE'])
 torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
-shape = (61, 70, 90)
+shape = (140, 70, 90)  # deep enough for the pipelined prepare + broadcast to use several z-chunks
 vol = np.random.default_rng(3).random(shape, dtype=np.float32)
 c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
 mats = [vt.utils.transform_matrix(rotation=(0, a, 0), center=c) for a in range(0, 180, 12)]
@@ -23,14 +23,16 @@ for mode in ('filt_bspline', 'linear', 'bspline_simple'):
     outs, idx = multigpu.sweep(vol if rank == 0 else None, mats, mode)
     sv = vt.StaticVolume(vol, interpolation=mode, device=f'gpu:{local}')
     ref = sv.affine_many([mats[i] for i in idx])
-    assert torch.equal(outs, ref), (mode, rank)
+    # streamed prefilter (z-chunks) vs one-shot prefilter: same coefficients to ~1e-7 of their range
+    tol = 1e-6 * float(sv.coefficients.max() - sv.coefficients.min()) if mode.startswith('filt') else 0.0
+    assert float((outs - ref).abs().max()) <= tol, (mode, rank, float((outs - ref).abs().max()))
     m = vt.utils.transform_matrix(rotation=(20, 30, 40), translation=(1, -2, 0.5), center=c)
     slab, (z0, z1) = multigpu.zslab_affine(vol if rank == 0 else None, m, mode)
     full = sv.affine_many([m])[0]
-    assert torch.equal(slab, full[z0:z1]), (mode, rank, z0, z1)
+    assert float((slab - full[z0:z1]).abs().max()) <= tol, (mode, rank, z0, z1)
     whole = multigpu.gather_slabs(slab)
     if rank == 0:
-        assert torch.equal(whole, full)
+        assert float((whole - full).abs().max()) <= tol
 dist.barrier()
 if rank == 0:
     print(f'multi-GPU check OK on {world} ranks')

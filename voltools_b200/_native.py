@@ -54,6 +54,8 @@ def lib():
         L.vt_affine_strided_f32.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i, _i,
                                             ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _i, _vp]
         L.vt_affine_plan.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _f32p, _i, _i, ctypes.c_uint, ctypes.POINTER(_i)]
+        L.vt_prefilter_planes_f32.argtypes = [_vp, _vp, _vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i,
+                                              _i, _i, _vp]
         L.vt_tex_create.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _i, _vp, ctypes.POINTER(_vp)]
         L.vt_tex_upload.argtypes = [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _vp]
         L.vt_tex_destroy.argtypes = [_vp]
@@ -133,6 +135,14 @@ def prefilter(src_ptr, shape, device=-1, stream=0, variant=0, dst_ptr=None, dst_
     check(lib().vt_prefilter_ws_f32(src_ptr, dst, shape[0], shape[1], shape[2], row, plane, ws_ptr, ws_bytes, variant,
                                     device, stream))
     del ws
+
+
+def prefilter_planes(src_ptr, ws_ptr, dst_ptr, shape, dst_strides, xy_range, z_range, device=-1, stream=0):
+    """Streaming prefilter step (vt_prefilter_planes_f32): XY passes of sample planes xy_range into the workspace,
+    Z pass of coefficient planes z_range from the workspace into dst."""
+    check(lib().vt_prefilter_planes_f32(src_ptr, ws_ptr, dst_ptr, int(shape[0]), int(shape[1]), int(shape[2]),
+                                        int(dst_strides[0]), int(dst_strides[1]), int(xy_range[0]), int(xy_range[1]),
+                                        int(z_range[0]), int(z_range[1]), device, stream))
 
 
 def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None,

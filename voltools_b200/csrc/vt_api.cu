@@ -294,6 +294,23 @@ int vt_prefilter_ws_f32(const float *d_src, float *d_dst, int d0, int d1, int d2
     return vt_prefilter_seq(d_dst, d0, d1, d2, st);
 }
 
+int vt_prefilter_planes_f32(const float *d_src, float *d_workspace, float *d_dst, int d0, int d1, int d2,
+                            long long dst_row_stride, long long dst_plane_stride, int xy_begin, int xy_end, int z_begin,
+                            int z_end, int device, void *stream)
+{
+    if (!d_src || !d_workspace || !d_dst || d0 < 1 || d1 < 1 || d2 < 1) return VT_ERR_INVALID_ARG;
+    if (dst_row_stride < d2 || dst_plane_stride < dst_row_stride * d1) return VT_ERR_INVALID_ARG;
+    if (d_workspace == d_dst || d_workspace == (float *)d_src || d_dst == (float *)d_src) return VT_ERR_INVALID_ARG;
+    if (xy_begin < 0 || xy_end > d0 || xy_begin > xy_end || z_begin < 0 || z_end > d0 || z_begin > z_end)
+        return VT_ERR_INVALID_ARG;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    int rc = vt_prefilter_xy_range(d_src, d_workspace, d0, d1, d2, dst_row_stride, dst_plane_stride, xy_begin, xy_end,
+                                   (cudaStream_t)stream);
+    if (rc) return rc;
+    return vt_prefilter_z_range(d_workspace, d_dst, d0, (size_t)dst_plane_stride, z_begin, z_end, 1, (cudaStream_t)stream);
+}
+
 int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, int variant, int device, void *stream)
 {
     return vt_prefilter_strided_f32(d_src, d_dst, d0, d1, d2, d2, (long long)d1 * d2, variant, device, stream);

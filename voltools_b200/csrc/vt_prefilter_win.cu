@@ -414,7 +414,7 @@ int vt_prefilter_xy_range(const float *d_src, float *d_dst, int d0, int d1, int 
 }
 
 // Z pass producing planes [z0, z1) of d_dst from the XY-filtered volume d_src (depth d0, `cols` columns per plane).
-// It reads planes [z0 - K, z1 + K) of d_src and nothing else (z0 must be 0 or > K).  d_src == d_dst (in place) is only valid for the whole range in one
+// It reads planes [z0 - K, z1 + K) of d_src and nothing else (from plane 0 when z0 <= K).  d_src == d_dst (in place) is only valid for the whole range in one
 // chunk; out of place the range is cut into `chunks` z-chunks (0 = choose).
 int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, int z0, int z1, int chunks, cudaStream_t st)
 {

@@ -12,6 +12,10 @@ shards along the two axes that are independent by construction (SURVEY.md sectio
     volume: 4 GiB at 1024^3, trivial next to 180 GB of HBM, and it makes any matrix valid without computing
     per-slab input footprints).
 
+The prepare + broadcast step is pipelined in z-chunks (`stream_plan`): while NCCL ships the coefficient planes that
+are already final, the root's compute stream prefilters the next chunk (vt_prefilter_planes_f32), so the root-side
+cost is max(prefilter, broadcast) instead of their sum.
+
 Both take an `engine` so that the orchestration (partitioning, metadata + buffer broadcast, result placement) can be
 exercised on CPU with the gloo backend and the oracle as the compute engine (tests/test_multigpu.py); the default
 engine is the CUDA library and there is no CPU fallback in the product path.
@@ -35,6 +39,25 @@ def split_slabs(d0: int, world: int, rank: int) -> Tuple[int, int]:
     return r.start, r.stop
 
 
+PREFILTER_LOOKAHEAD = 12  # planes of look-ahead of the Z prefilter (vt_prefilter_win.cu: K)
+
+
+def stream_plan(d0: int, filtered: bool, chunks: int = None) -> List[Tuple[int, int, int, int]]:
+    """z-chunks of the pipelined prepare + broadcast, identical on every rank: [(xy0, xy1, z0, z1)].
+    Step i runs the XY prefilter of sample planes [xy0, xy1) and makes resident-buffer planes [z0, z1) final (the
+    Z prefilter trails the XY passes by its look-ahead); [z0, z1) is what gets broadcast after step i."""
+    d0 = int(d0)
+    if chunks is None:
+        chunks = max(1, min(8, d0 // 64))
+    plan, done = [], 0
+    for i in range(chunks):
+        h0, h1 = d0 * i // chunks, d0 * (i + 1) // chunks
+        zn = h1 if (not filtered or h1 == d0) else max(done, h1 - PREFILTER_LOOKAHEAD)
+        plan.append((h0, h1, done, zn))
+        done = zn
+    return plan
+
+
 class CudaEngine:
     """The product engine: StaticVolume on the rank's GPU."""
 
@@ -49,6 +72,38 @@ class CudaEngine:
         from .volume import StaticVolume
         sv = StaticVolume(volume, interpolation=interpolation, device=f'gpu:{self.dev}')
         return sv.coefficient_buffer, sv.shape[2]
+
+    def describe(self, volume, interpolation):
+        """Root only: (shape of the resident buffer, true width) without touching the data."""
+        from . import _native
+        d0, d1, d2 = (int(v) for v in volume.shape)
+        return (d0, d1, _native.padded_row(d2)), d2
+
+    def prepare_stream(self, volume, interpolation, buffer, plan):
+        """Root only: returns step(i), which enqueues (on the current stream) the work that makes planes
+        plan[i][2]:plan[i][3] of `buffer` final."""
+        from . import _native
+        from ._native import INTERPOLATIONS
+        torch = self.torch
+        _, filtered = INTERPOLATIONS[interpolation]
+        raw = torch.as_tensor(volume, dtype=torch.float32, device=self.device).contiguous() \
+            if not isinstance(volume, np.ndarray) else torch.from_numpy(np.ascontiguousarray(volume, np.float32)).to(self.device)
+        shape = tuple(int(v) for v in raw.shape)
+        row = int(buffer.shape[2])
+        strides = (row, shape[1] * row)
+        ws = torch.empty_like(buffer) if filtered else None
+
+        def step(i):
+            xy0, xy1, z0, z1 = plan[i]
+            with torch.cuda.device(self.dev):
+                if filtered:
+                    _native.prefilter_planes(raw.data_ptr(), ws.data_ptr(), buffer.data_ptr(), shape, strides, (xy0, xy1),
+                                             (z0, z1), self.dev, torch.cuda.current_stream(self.dev).cuda_stream)
+                elif z1 > z0:
+                    buffer[z0:z1, :, :shape[2]].copy_(raw[z0:z1])
+                    if row != shape[2]:
+                        buffer[z0:z1, :, shape[2]:].zero_()
+        return step
 
     def empty(self, shape):
         return self.torch.empty(shape, dtype=self.torch.float32, device=self.device)
@@ -75,14 +130,27 @@ class CudaEngine:
         return out
 
 
-def _broadcast_buffer(engine, dist, group, src, buffer, meta):
-    """Ships (shape of the resident buffer, true width) then the buffer itself from `src` to every rank."""
-    box = [meta]
+def _prepare_and_broadcast(engine, dist, group, src, volume, interpolation):
+    """Root: upload + prefilter; everyone: receive the resident buffer.  Pipelined in z-chunks: the broadcast of the
+    planes that are final runs (async, on the communicator's stream) while the root prefilters the next chunk.
+    Returns (buffer, width) on every rank."""
+    rank = dist.get_rank(group)
+    filtered = interpolation.startswith('filt')
+    box = [engine.describe(volume, interpolation) if rank == src else None]
     dist.broadcast_object_list(box, src=src, group=group)
     buf_shape, width = box[0]
-    if buffer is None:
-        buffer = engine.empty(tuple(buf_shape))
-    dist.broadcast(buffer, src=src, group=group)  # NCCL over NVLink / NVSwitch on a GPU node
+    buffer = engine.empty(tuple(buf_shape))
+    plan = stream_plan(buf_shape[0], filtered)
+    step = engine.prepare_stream(volume, interpolation, buffer, plan) if rank == src else None
+    works = []
+    for i, (_, _, z0, z1) in enumerate(plan):
+        if step is not None:
+            step(i)
+        if z1 > z0:
+            # NCCL over NVLink / NVSwitch on a GPU node; ordered after the work enqueued so far on this stream
+            works.append(dist.broadcast(buffer[z0:z1], src=src, group=group, async_op=True))
+    for w in works:
+        w.wait()
     return buffer, width
 
 
@@ -99,11 +167,7 @@ def sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = 'filt_bsp
         import torch
         engine = CudaEngine(torch.cuda.current_device())
     mats = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
-    buffer, meta = None, None
-    if rank == src:
-        buffer, width = engine.prepare(volume, interpolation)
-        meta = (tuple(buffer.shape), int(width))
-    buffer, width = _broadcast_buffer(engine, dist, group, src, buffer, meta)
+    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation)
     mine = split_batch(len(mats), world, rank)
     out = engine.resample_many(buffer, width, interpolation, mats[mine.start:mine.stop]) if len(mine) else \
         engine.empty((0,) + tuple(buffer.shape[:2]) + (width,))
@@ -121,11 +185,7 @@ def zslab_affine(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline'
     if engine is None:
         import torch
         engine = CudaEngine(torch.cuda.current_device())
-    buffer, meta = None, None
-    if rank == src:
-        buffer, width = engine.prepare(volume, interpolation)
-        meta = (tuple(buffer.shape), int(width))
-    buffer, width = _broadcast_buffer(engine, dist, group, src, buffer, meta)
+    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation)
     z0, z1 = split_slabs(int(buffer.shape[0]), world, rank)
     m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(4, 4)
     return engine.resample_slab(buffer, width, interpolation, m, z0, z1), (z0, z1)
