@@ -376,7 +376,7 @@ def run_sweep(args, torch, vt, dev, barrier, reduce_max):
     mats = [vt.utils.transform_matrix(rotation=(0, i, 0), rotation_order='rzxz', center=c) for i in range(180)]
     vol = torch.rand(shape, device=f'cuda:{dev}', generator=torch.Generator(f'cuda:{dev}').manual_seed(7)) \
         if rank == 0 else None
-    mine = multigpu.split_batch(len(mats), world, rank)
+    mine = multigpu.split_strided(len(mats), world, rank)
     out = torch.empty((len(mine),) + shape, device=f'cuda:{dev}')
     eng = multigpu.CudaEngine(dev)
 

@@ -36,6 +36,8 @@ def test_partitions_cover_everything_once():
                 seen += list(blk)
                 assert len(blk) in (n // world, n // world + 1)
             assert seen == list(range(n))
+            strided = sorted(i for r in range(world) for i in multigpu.split_strided(n, world, r))
+            assert strided == list(range(n))
             z = [multigpu.split_slabs(n, world, r) for r in range(world)]
             assert z[0][0] == 0 and z[-1][1] == n and all(z[i][1] == z[i + 1][0] for i in range(world - 1))
 

@@ -5,7 +5,7 @@ shards along the two axes that are independent by construction (SURVEY.md sectio
 
   * a batch of transforms of one volume (the README's 180-angle `StaticVolume` sweep, README.md:26-27):
     `sweep()` -- the root rank uploads and prefilters once, ONE broadcast ships the coefficient buffer to every
-    rank over NVLink, then rank r resamples matrices `split_batch(K, world, r)`; outputs stay on the GPU that
+    rank over NVLink, then rank r resamples matrices `split_strided(K, world, r)` (round robin); outputs stay on the GPU that
     computed them.  No collective after the broadcast.
   * one large output volume: `zslab_affine()` -- same broadcast, then rank r produces output planes
     `split_slabs(d0, world, r)` with the z-range argument of the C ABI (every rank holds the whole coefficient
@@ -31,6 +31,13 @@ def split_batch(n_items: int, world: int, rank: int) -> range:
     base, extra = divmod(int(n_items), int(world))
     start = rank * base + min(rank, extra)
     return range(start, start + base + (1 if rank < extra else 0))
+
+
+def split_strided(n_items: int, world: int, rank: int) -> range:
+    """Round-robin share of a batch for `rank`: items rank, rank + world, ...  Used for rotation sweeps, where the
+    cost of a transform varies smoothly with the angle (shared-memory bank conflicts peak around 45 degrees), so
+    contiguous blocks of angles would leave the ranks unevenly loaded."""
+    return range(int(rank), int(n_items), int(world))
 
 
 def split_slabs(d0: int, world: int, rank: int) -> Tuple[int, int]:
@@ -168,8 +175,8 @@ def sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = 'filt_bsp
         engine = CudaEngine(torch.cuda.current_device())
     mats = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
     buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation)
-    mine = split_batch(len(mats), world, rank)
-    out = engine.resample_many(buffer, width, interpolation, mats[mine.start:mine.stop]) if len(mine) else \
+    mine = split_strided(len(mats), world, rank)
+    out = engine.resample_many(buffer, width, interpolation, mats[mine.start::world]) if len(mine) else \
         engine.empty((0,) + tuple(buffer.shape[:2]) + (width,))
     return out, list(mine)
 
