@@ -549,25 +549,44 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
     const int margin = interp == VT_LINEAR ? 0 : 1;
     const int KZ = 12;  // look-ahead of the Z prefilter (vt_prefilter_win.cu)
 
-    // chunk count: 4-8 chunks of >= 32 planes (measured on B200 / PCIe 5 x16: 250^3 filt_bspline 2.41 ms with one
-    // chunk, 1.83 ms with 4-8, no better with 16 -- per-chunk event and launch latencies start to show)
-    int nch = s0 / 32;
-    if (nch > 8) nch = 8;
-    if (const char *e = getenv("VT_HOST_CHUNKS")) nch = atoi(e);  // tuning knob
-    if (nch > VT_HOST_MAX_CHUNKS) nch = VT_HOST_MAX_CHUNKS;
-    if (nch < 1) nch = 1;
+    // Chunk plan: a handful of large chunks (>= 32 planes; measured on B200 / PCIe 5 x16 at 250^3 filt_bspline: 2.41 ms
+    // with one chunk, 1.83 ms with 4-8 equal ones, no better with 16 -- per-chunk event and launch latencies start to
+    // show), then a short tail of shrinking chunks: what is still to be downloaded after the last upload has landed is
+    // the last chunk plus the prefilter's look-ahead, and nothing overlaps that download.
+    int bounds[VT_HOST_MAX_CHUNKS + 1];
+    int nch = 0;
+    bounds[0] = 0;
+    {
+        const int tail[3] = {24, 16, 10};
+        const int tail_total = s0 >= 128 ? 50 : 0;
+        const int body = s0 - tail_total;
+        int nbody = body / 40;
+        if (nbody > 8) nbody = 8;
+        if (nbody < 1) nbody = 1;
+        if (const char *e = getenv("VT_HOST_CHUNKS")) nbody = atoi(e) > 0 ? (atoi(e) > 12 ? 12 : atoi(e)) : nbody;  // tuning knob
+        for (int i = 1; i <= nbody; i++) bounds[++nch] = (int)((long long)body * i / nbody);
+        if (tail_total)
+            for (int i = 0; i < 3; i++) { bounds[nch + 1] = bounds[nch] + tail[i]; nch++; }
+    }
+    static const bool debug = getenv("VT_HOST_DEBUG") != nullptr;  // prints the timeline of the three streams
+    cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (debug) {
+        for (auto &e : dbg) cudaEventCreate(&e);
+        cudaEventRecord(dbg[0], c->st_in);
+    }
     // 1) the whole upload, chunk by chunk, on the copy stream
     for (int i = 0; i < nch; i++) {
-        const int h0 = (int)((long long)s0 * i / nch), h1 = (int)((long long)s0 * (i + 1) / nch);
+        const int h0 = bounds[i], h1 = bounds[i + 1];
         float *up = (prefilter || pad) ? c->d_src : c->d_coef;  // dense either way
         VT_CUDA(cudaMemcpyAsync(up + (size_t)h0 * plane_in, h_src + (size_t)h0 * plane_in,
                                 (size_t)(h1 - h0) * plane_in * 4, cudaMemcpyHostToDevice, c->st_in));
         VT_CUDA(cudaEventRecord(c->ev_in[i], c->st_in));
     }
+    if (debug) cudaEventRecord(dbg[1], c->st_in);
     // 2) kernels behind it on the compute stream, downloads behind those on the download stream
     int z_done = 0, o_done = 0;
     for (int i = 0; i < nch; i++) {
-        const int h0 = (int)((long long)s0 * i / nch), h1 = (int)((long long)s0 * (i + 1) / nch);
+        const int h0 = bounds[i], h1 = bounds[i + 1];
         VT_CUDA(cudaStreamWaitEvent(c->st_k, c->ev_in[i], 0));
         int ready = h1;  // sampled planes [0, ready) are final
         if (prefilter) {
@@ -613,8 +632,21 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
         }
         o_done = on;
     }
+    if (debug) {
+        cudaEventRecord(dbg[2], c->st_k);
+        cudaEventRecord(dbg[3], c->st_out);
+    }
     VT_CUDA(cudaStreamSynchronize(c->st_out));
     VT_CUDA(cudaStreamSynchronize(c->st_k));
+    if (debug) {
+        float t1 = 0, t2 = 0, t3 = 0;
+        cudaEventElapsedTime(&t1, dbg[0], dbg[1]);
+        cudaEventElapsedTime(&t2, dbg[0], dbg[2]);
+        cudaEventElapsedTime(&t3, dbg[0], dbg[3]);
+        fprintf(stderr, "vt_host_affine_f32: %d chunks; since the first upload started: uploads done %.3f ms, kernels done "
+                        "%.3f ms, downloads done %.3f ms\n", nch, t1, t2, t3);
+        for (auto &e : dbg) cudaEventDestroy(e);
+    }
     return VT_OK;
 }
 

@@ -40,11 +40,18 @@ __device__ constexpr float kWarm = 5.9999995231628417969f / 1.267949223518371582
 
 constexpr int K = 12;  // warm-up / look-ahead length
 
+// One step of each recursion with the multiply by the new sample OFF the dependent chain: the chain is one FMA (4
+// cycles) per sample instead of the reference's FMUL -> FFMA / FSUB -> FMUL pairs (8).  Same value up to one
+// rounding per step (these kernels are the windowed variant: 1e-6 of the range, not bit parity; variant 1 keeps the
+// reference's exact operation order).
 __device__ __forceinline__ float causal_step(float s, float prev)
 {
-    return __fmaf_rn(s, kLambda, -__fmul_rn(prev, kNegPole));
+    return __fmaf_rn(kPole, prev, __fmul_rn(s, kLambda));
 }
-__device__ __forceinline__ float anticausal_step(float next, float c) { return __fmul_rn(kPole, __fsub_rn(next, c)); }
+__device__ __forceinline__ float anticausal_step(float next, float c)
+{
+    return __fmaf_rn(kPole, next, __fmul_rn(kNegPole, c));
+}
 
 // exact causal start of a line (InitialCausalCoefficient, bspline.h:2-19) over elements e[0], e[step], ...
 __device__ __forceinline__ float causal_init(const float *e, int n, int step)
@@ -63,6 +70,7 @@ __device__ __forceinline__ float causal_init(const float *e, int n, int step)
 // ---------------------------------------------------------------------------------------------------
 constexpr int RB = 16;   // rows per step
 constexpr int SEG = 16;  // X chunk: samples per thread in the X pass
+constexpr int NBUF = 3;  // staging tiles of the XY kernel
 constexpr int HX = 16;   // X halo of interior strips (>= K; a multiple of SEG keeps the Y pass's warps chunk-aligned)
 // powers of the pole: kPow[j] = z^j
 __device__ constexpr float kPow[17] = {1.0000000000e+00f,  -2.6794922352e-01f, 7.1796786384e-02f,  -1.9237893163e-02f,
@@ -129,7 +137,7 @@ __device__ __forceinline__ void x_pass(float *tb, int xc, const float (&cf)[SEG]
 }
 
 // One CTA walks down (a y-chunk of) one z-plane RB rows at a time.  Per step: the RB rows are staged into a
-// shared-memory tile with cp.async (double buffered: the next step's rows are in flight during this step's math),
+// shared-memory tile with cp.async (NBUF tiles: the next steps' rows are in flight during this step's math),
 // the X recursion runs on them with one (row, 16-sample chunk) task per thread (x_pass), then one thread per
 // column continues the Y recursion down the plane (causal value in a register, anticausal restart from K rows
 // ahead over a register window) and stores finished rows (coalesced).  NT = RB * L threads.
@@ -140,7 +148,7 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
 {
     constexpr int L = NT / RB;   // chunks (X-pass lanes) per row
     constexpr int P = L * SEG;   // tile row pitch in floats (= NT)
-    extern __shared__ __align__(16) float smem[];  // two tiles [RB][P]
+    extern __shared__ __align__(16) float smem[];  // NBUF tiles [RB][P]
     const int z = z_first + blockIdx.z;
     const int x0 = blockIdx.x * x_strip, x1 = min(x0 + x_strip, W);  // columns written by this CTA
     const int xa = max(x0 - HX, 0), xb = min(x1 + HX, W);            // columns staged (X warm-up on both sides)
@@ -166,26 +174,34 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
     const unsigned stage_dst = tile_s + 4u * (unsigned)tile_col(tid);
     const float *ycol = smem + tile_col(x0 + tid - xa);
 
-    auto stage = [&](int r0, int buf) {  // rows r0 .. r0+RB-1 -> tile[buf]; rows past rb and columns past sw: zeros
+    // rows r0 .. r0+RB-1 -> tile[buf]; rows past rb and columns past sw: zeros.  Always one commit group per call
+    // (empty once the rows are exhausted) so that "all but the newest NBUF-2 groups" is the step being consumed.
+    auto stage = [&](int r0, int buf) {
+        if (r0 < rb) {
 #pragma unroll
-        for (int i = 0; i < RB; i++)
-            vt_cp_async4(stage_dst + 4u * (unsigned)((buf * RB + i) * P), sp + (size_t)i * W, (stager && r0 + i < rb) ? 1u : 0u);
+            for (int i = 0; i < RB; i++)
+                vt_cp_async4(stage_dst + 4u * (unsigned)((buf * RB + i) * P), sp + (size_t)i * W,
+                             (stager && r0 + i < rb) ? 1u : 0u);
+        }
         vt_cp_async_commit();
         sp += (size_t)RB * W;
     };
 
-    stage(ra, 0);
+    // NBUF - 1 steps of rows are in flight ahead of the one being filtered: with 1-2 CTAs per SM a single step
+    // (16 KB) does not cover the HBM latency
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; i++) stage(ra + i * RB, i);
     float cp[K + RB];  // causal Y values of rows [r0 - K, r0 + RB)
 #pragma unroll
     for (int k = 0; k < K + RB; k++) cp[k] = 0.0f;
     float prev = 0.0f;
     int buf = 0;
 
-    for (int r0 = ra;; r0 += RB, buf ^= 1) {
+    for (int r0 = ra;; r0 += RB, buf = buf + 1 == NBUF ? 0 : buf + 1) {
         const int nrows = min(RB, rb - r0);  // <= 0 once the rows are exhausted (flush steps)
-        vt_cp_async_wait_all();
-        __syncthreads();  // tile[buf] has landed; the previous step's column sweep is done with tile[buf ^ 1]
-        if (r0 + RB < rb) stage(r0 + RB, buf ^ 1);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(NBUF - 2) : "memory");
+        __syncthreads();  // tile[buf] has landed; the previous step's column sweep is done with its tile
+        stage(r0 + (NBUF - 1) * RB, buf == 0 ? NBUF - 1 : buf - 1);  // refills the previous step's tile
         if (nrows > 0) x_pass<L>(smem + (buf * RB + xrow) * P + xc * SEG, xc, cf, xa == 0);
         __syncthreads();
         // ---- Y: one thread per column, rows r0 .. r0+nrows-1 enter the window ----
@@ -379,7 +395,7 @@ int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long d
 {
     const int x_strip = W <= NT ? W : NT - 2 * HX;
     const int strips = (W + x_strip - 1) / x_strip;
-    const size_t smem = (size_t)2 * RB * NT * sizeof(float);
+    const size_t smem = (size_t)NBUF * RB * NT * sizeof(float);
     const int nz = z1 - z0;
     // y-chunks: enough CTAs to fill the GPU, chunks of at least 64 rows (each pays 2*K rows of warm-up / look-ahead)
     int chunks = (200 + nz * strips - 1) / (nz * strips);

@@ -375,8 +375,6 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
     const float p2 = inplane_coord(M.r[2], (float)a1, (float)a2);
     // transforms.py:276-278 for the two in-plane axes
     const bool inplane = live && !(p2 < 0 || p1 < 0 || p2 >= (float)P.s2 || p1 >= (float)P.s1);
-    T taps;
-    if (inplane) taps.template init<RULE>(p1, p2, ylo, xlo, pitch);
     const size_t oplane = (size_t)P.o1 * P.o2;
 
     // input planes needed: q = z + t0 + d, d in [-PLANES_BEFORE, PLANES_AFTER]
@@ -413,6 +411,9 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
     // prologue: NSTAGE-1 stages in flight
 #pragma unroll
     for (int i = 0; i < NSTAGE - 1; i++) issue(q_first + i * PPS, srcq + (size_t)(i * PPS) * plane_bytes, (unsigned)i);
+    // the column's weights are computed while those first loads are in flight
+    T taps;
+    if (inplane) taps.template init<RULE>(p1, p2, ylo, xlo, pitch);
     float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // sliding window of per-plane sums
     unsigned cur = 0, fill = NSTAGE - 1;     // ring stage being consumed / refilled
     unsigned phase = 0;                      // mbarrier parity of stage `cur`
