@@ -534,3 +534,47 @@ def test_full_size_properties(vt, n):
     vt.affine(a, bwd, interpolation='filt_bspline_simple', output=b, device='gpu')
     core = (slice(n // 4, -n // 4),) * 3
     assert float((b[core] - smooth[core]).abs().max()) <= 1e-4
+
+
+def test_largest_config_1024(vt):
+    """BASELINE configs[4] size (1024^3, 4 GiB per volume): 32-bit index limits, strides and grid sizes of every
+    kernel family, through size-independent properties and family-vs-family agreement on a few output planes."""
+    import torch
+    N = vt._native
+    n = 1024
+    shape = (n, n, n)
+    if torch.cuda.mem_get_info()[0] < 40 * 2 ** 30:
+        pytest.skip('needs ~25 GiB of free device memory')
+    u = torch.rand(shape, device='cuda', generator=torch.Generator('cuda').manual_seed(3))
+    out = torch.empty_like(u)
+    eye = np.identity(4, dtype=np.float32)
+    vt.affine(u, eye, interpolation='linear', output=out, device='gpu')
+    assert torch.equal(out, u)
+    vt.affine(u, eye, interpolation='filt_bspline_simple', output=out, device='gpu')   # windowed prefilter, z-chunked
+    probe = (slice(500, 524), slice(16, -16), slice(16, -16))
+    assert float((out[probe] - u[probe]).abs().max()) <= 2e-5
+    last = (slice(n - 40, n - 16), slice(16, -16), slice(16, -16))
+    assert float((out[last] - u[last]).abs().max()) <= 2e-5
+    c = _center(shape)
+    general = vt.utils.transform_matrix(scale=(1.1, 0.9, 1.05), shear=(0.05, -0.03, 0.02), rotation=(30, 45, 60),
+                                        translation=(5.5, -3.25, 2.0), center=c)
+    rot = vt.utils.transform_matrix(rotation=(0, 45, 0), center=c)
+    zr = (1000, 1008)
+    ref = torch.zeros((8, n, n), device='cuda')
+    got = torch.zeros((8, n, n), device='cuda')
+    base = lambda t: t.data_ptr() - zr[0] * n * n * 4   # the ABI addresses plane z at dst + z*plane
+    tex = N.Texture(u.data_ptr(), shape)
+    for interp in (0, 1, 2):
+        for mat, fams in ((rot, (N.KERNEL_SLICE,)), (general, (N.KERNEL_BRICK, 'tex'))):
+            ref.zero_()
+            N.affine(u.data_ptr(), shape, base(ref), shape, mat, interp, N.OOB_ZERO | N.KERNEL_GATHER, z_range=zr)
+            for fam in fams:
+                got.fill_(-1.0)
+                if fam == 'tex':
+                    if interp == 2:
+                        continue
+                    tex.affine(base(got), shape, mat, interp, N.OOB_ZERO, z_range=zr)
+                else:
+                    N.affine(u.data_ptr(), shape, base(got), shape, mat, interp, N.OOB_ZERO | fam, z_range=zr)
+                assert float((got - ref).abs().max()) <= 1e-6, (interp, fam)
+    tex.close()
