@@ -382,7 +382,7 @@ def run_sweep(args, torch, vt, dev, barrier, reduce_max):
 
     def step():
         if world > 1:
-            outs, _ = multigpu.sweep(vol, mats, 'filt_bspline', src=0, engine=eng)
+            outs, _ = multigpu.sweep(vol, mats, 'filt_bspline', src=0, engine=eng, shape=shape)
         else:
             buf, width = eng.prepare(vol, 'filt_bspline')
             sv = vt.StaticVolume.from_coefficients(buf, 'filt_bspline', width)
@@ -418,7 +418,7 @@ def run_zslab(args, torch, vt, dev, barrier, reduce_max):
 
     def step():
         if world > 1:
-            multigpu.zslab_affine(vol, m, 'filt_bspline', src=0, engine=eng)
+            multigpu.zslab_affine(vol, m, 'filt_bspline', src=0, engine=eng, shape=shape)
         else:
             buf, width = eng.prepare(vol, 'filt_bspline')
             eng.resample_slab(buf, width, 'filt_bspline', m, 0, n)

@@ -27,6 +27,16 @@ def test_stream_plan_covers_the_volume_in_order():
                     assert z1 <= xy1 and (not filtered or z1 == d0 or z1 <= xy1 - multigpu.PREFILTER_LOOKAHEAD or z1 == z0)
 
 
+def test_streaming_margin():
+    c = np.array([10, 10, 10], np.float32)
+    rot = [transform_matrix(rotation=(0, a, 0), center=c) for a in (0, 30, 45)]
+    assert multigpu.streaming_margin(rot, 'linear') == 1 and multigpu.streaming_margin(rot, 'filt_bspline') == 2
+    shifted = rot + [transform_matrix(rotation=(0, 10, 0), center=c, translation=(-3, 0.5, 0))]   # t0 = +3
+    assert multigpu.streaming_margin(shifted, 'bspline') == 5
+    assert multigpu.streaming_margin([transform_matrix(rotation=(10, 20, 30), center=c)], 'linear') is None
+    assert multigpu.streaming_margin([transform_matrix(translation=(0.5, 0, 0))], 'linear') is None
+
+
 def test_partitions_cover_everything_once():
     for n in (0, 1, 2, 7, 180, 181, 1024):
         for world in (1, 2, 3, 4, 8):
@@ -52,6 +62,20 @@ class OracleEngine:
 
     def describe(self, volume, interpolation):
         return tuple(int(v) for v in volume.shape), int(volume.shape[2])
+
+    def describe_shape(self, shape):
+        return tuple(shape), shape[2]
+
+    def producer_stream(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def resample_many_range(self, buffer, width, interpolation, matrices, out, z0, z1):
+        import torch
+        v = buffer.numpy()[:, :, :width]
+        for k, m in enumerate(matrices):
+            full = oracle.affine(v, m, self._mode(interpolation), z_range=(z0, z1))
+            out[k, z0:z1] = torch.from_numpy(full[z0:z1].copy())
 
     def prepare_stream(self, volume, interpolation, buffer, plan):
         coef, _ = self.prepare(volume, interpolation)
@@ -95,6 +119,14 @@ def _worker(rank, world, init_file, outdir):
         # only the root has the samples
         out, idx = multigpu.sweep(vol if rank == 0 else None, mats, 'filt_bspline', src=0, engine=eng)
         np.savez(os.path.join(outdir, f'sweep_{rank}.npz'), out=out.numpy(), idx=np.array(idx))
+        # a taller volume in 3 z-chunks: resampling overlapped with the chunked broadcast (shape known everywhere)
+        tall = np.random.default_rng(43).random((40, 12, 14), dtype=np.float32)
+        ct = np.divide(np.subtract(tall.shape, 1), 2, dtype=np.float32)
+        mats_t = [transform_matrix(rotation=(0, a, 0), center=ct, translation=(t, 0.5, 0)) for a, t in
+                  ((0, 0), (30, 2), (77, -3), (120, 0), (45, 1))]
+        out_t, idx_t = multigpu.sweep(tall if rank == 0 else None, mats_t, 'filt_bspline', src=0, engine=eng,
+                                      shape=tall.shape, chunks=3, overlap=True)
+        np.savez(os.path.join(outdir, f'tall_{rank}.npz'), out=out_t.numpy(), idx=np.array(idx_t))
         m = transform_matrix(rotation=(20, 30, 40), translation=(1, -2, 0.5), center=c)
         slab, (z0, z1) = multigpu.zslab_affine(vol if rank == 0 else None, m, 'bspline_simple', src=0, engine=eng)
         full = multigpu.gather_slabs(slab, dst=0)
@@ -122,6 +154,17 @@ def test_sweep_and_zslab_two_ranks_gloo():
                 assert np.array_equal(o, oracle.affine(vol, mats[int(i)], 'filt_bspline'))
                 seen.append(int(i))
         assert sorted(seen) == list(range(len(mats)))
+        tall = np.random.default_rng(43).random((40, 12, 14), dtype=np.float32)
+        ct = np.divide(np.subtract(tall.shape, 1), 2, dtype=np.float32)
+        mats_t = [transform_matrix(rotation=(0, a, 0), center=ct, translation=(t, 0.5, 0)) for a, t in
+                  ((0, 0), (30, 2), (77, -3), (120, 0), (45, 1))]
+        seen = []
+        for r in range(world):
+            z = np.load(os.path.join(d, f'tall_{r}.npz'))
+            for o, i in zip(z['out'], z['idx']):
+                assert np.array_equal(o, oracle.affine(tall, mats_t[int(i)], 'filt_bspline')), (r, int(i))
+                seen.append(int(i))
+        assert sorted(seen) == list(range(len(mats_t)))
         m = transform_matrix(rotation=(20, 30, 40), translation=(1, -2, 0.5), center=c)
         want = oracle.affine(vol, m, 'bspline_simple')
         z0 = np.load(os.path.join(d, 'slab_0.npz'))

@@ -20,7 +20,7 @@ vol = np.random.default_rng(3).random(shape, dtype=np.float32)
 c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
 mats = [vt.utils.transform_matrix(rotation=(0, a, 0), center=c) for a in range(0, 180, 12)]
 for mode in ('filt_bspline', 'linear', 'bspline_simple'):
-    outs, idx = multigpu.sweep(vol if rank == 0 else None, mats, mode)
+    outs, idx = multigpu.sweep(vol if rank == 0 else None, mats, mode, overlap=(mode != 'linear'))
     sv = vt.StaticVolume(vol, interpolation=mode, device=f'gpu:{local}')
     ref = sv.affine_many([mats[i] for i in idx])
     # streamed prefilter (z-chunks) vs one-shot prefilter: same coefficients to ~1e-7 of their range

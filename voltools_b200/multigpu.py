@@ -86,6 +86,18 @@ class CudaEngine:
         d0, d1, d2 = (int(v) for v in volume.shape)
         return (d0, d1, _native.padded_row(d2)), d2
 
+    def describe_shape(self, shape):
+        from . import _native
+        return (shape[0], shape[1], _native.padded_row(shape[2])), shape[2]
+
+    def producer_stream(self):
+        """Context: a side stream (ordered after the current one) for the prefilter steps and the broadcasts."""
+        torch = self.torch
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(torch.cuda.current_stream(self.device))
+        return torch.cuda.stream(self._side)
+
     def prepare_stream(self, volume, interpolation, buffer, plan):
         """Root only: returns step(i), which enqueues (on the current stream) the work that makes planes
         plan[i][2]:plan[i][3] of `buffer` final."""
@@ -120,6 +132,16 @@ class CudaEngine:
         sv = StaticVolume.from_coefficients(buffer, interpolation, width)
         return sv.affine_many(matrices)
 
+    def resample_many_range(self, buffer, width, interpolation, matrices, out, z0, z1):
+        """Output planes [z0, z1) of every matrix into `out` (K, d0, d1, width); out-of-bounds voxels are zeroed."""
+        from . import _native
+        from .volume import StaticVolume
+        sv = StaticVolume.from_coefficients(buffer, interpolation, width)
+        with self.torch.cuda.device(self.dev):
+            _native.affine(buffer.data_ptr(), sv.shape, out.data_ptr(), sv.shape, matrices, sv._interp, _native.OOB_ZERO,
+                           z_range=(z0, z1), device=self.dev,
+                           stream=self.torch.cuda.current_stream(self.dev).cuda_stream, src_strides=sv._strides)
+
     def resample_slab(self, buffer, width, interpolation, matrix, z0, z1):
         from . import _native
         from .volume import StaticVolume
@@ -137,36 +159,71 @@ class CudaEngine:
         return out
 
 
-def _prepare_and_broadcast(engine, dist, group, src, volume, interpolation):
+def _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape=None, on_planes=None, chunks=None):
     """Root: upload + prefilter; everyone: receive the resident buffer.  Pipelined in z-chunks: the broadcast of the
     planes that are final runs (async, on the communicator's stream) while the root prefilters the next chunk.
+    `shape`: the volume's shape if every rank knows it (saves the metadata broadcast, a host round trip).
+    `on_planes(buffer, width, ready)`: called on every rank each time planes [0, ready) of the buffer have arrived
+    (stream-ordered: work enqueued from it runs after them), so that consumers can start before the rest is there.
     Returns (buffer, width) on every rank."""
     rank = dist.get_rank(group)
     filtered = interpolation.startswith('filt')
-    box = [engine.describe(volume, interpolation) if rank == src else None]
-    dist.broadcast_object_list(box, src=src, group=group)
-    buf_shape, width = box[0]
+    if shape is not None:
+        buf_shape, width = engine.describe_shape(tuple(int(v) for v in shape))
+    else:
+        box = [engine.describe(volume, interpolation) if rank == src else None]
+        dist.broadcast_object_list(box, src=src, group=group)
+        buf_shape, width = box[0]
     buffer = engine.empty(tuple(buf_shape))
-    plan = stream_plan(buf_shape[0], filtered)
-    step = engine.prepare_stream(volume, interpolation, buffer, plan) if rank == src else None
+    plan = stream_plan(buf_shape[0], filtered, chunks)
+    # The producer side (root: prefilter steps; everyone: the broadcasts) is enqueued from a side stream: a collective
+    # is ordered after whatever its issuing stream already holds, so issuing it from the consumer's stream would make
+    # broadcast i+1 wait for the resampling of chunk i.
     works = []
-    for i, (_, _, z0, z1) in enumerate(plan):
-        if step is not None:
-            step(i)
-        if z1 > z0:
-            # NCCL over NVLink / NVSwitch on a GPU node; ordered after the work enqueued so far on this stream
-            works.append(dist.broadcast(buffer[z0:z1], src=src, group=group, async_op=True))
-    for w in works:
-        w.wait()
+    with engine.producer_stream():
+        step = engine.prepare_stream(volume, interpolation, buffer, plan) if rank == src else None
+        for i, (_, _, z0, z1) in enumerate(plan):
+            if step is not None:
+                step(i)
+            if z1 > z0:
+                # NCCL over NVLink / NVSwitch on a GPU node
+                works.append((dist.broadcast(buffer[z0:z1], src=src, group=group, async_op=True), z1))
+    for w, z1 in works:
+        w.wait()  # the consumer's stream waits for these planes; the host does not
+        if on_planes is not None:
+            on_planes(buffer, width, z1)
     return buffer, width
 
 
+def streaming_margin(matrices: np.ndarray, interpolation: str):
+    """If every matrix leaves axis 0 alone up to an integer shift t0 (the slice family of the kernels: rotations
+    about axis 0 ...), output plane z only reads sampled planes z + t0 - m .. z + t0 + m (m = 0 linear, 1 cubic).
+    Returns the number of sampled planes that must have arrived beyond output plane z (max t0 + m + 1), or None if
+    some matrix mixes axis 0 with the others -- then nothing can be resampled before the whole volume is there."""
+    m = np.asarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
+    if not (np.all(m[:, 0, 0] == 1) and np.all(m[:, 0, 1:3] == 0) and np.all(m[:, 1:3, 0] == 0)):
+        return None
+    t0 = m[:, 0, 3]
+    if not np.all(t0 == np.floor(t0)) or np.any(np.abs(t0) > 16384):
+        return None
+    return int(t0.max()) + (0 if interpolation == 'linear' else 1) + 1
+
+
 def sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = 'filt_bspline', src: int = 0, group=None,
-          engine=None):
+          engine=None, shape=None, chunks=None, overlap: bool = False):
     """Batch of transforms of one volume, split across the ranks of `group`.
 
     volume: the samples on rank `src` (numpy / device array), ignored elsewhere (may be None).
+    shape:  the volume's shape, if every rank knows it (skips a metadata broadcast).
+    chunks: z-chunks of the pipelined prepare + broadcast (default: `stream_plan`'s choice).
     Returns (outputs, indices): `outputs[i]` is the volume for `matrices[indices[i]]`, resident on this rank.
+
+    overlap=True: when all of this rank's matrices are of the slice family (the README's rotation sweep), the
+    resampling is overlapped with the broadcast: as each z-chunk of coefficients arrives, the output planes it
+    completes are produced for every matrix of the rank (z-range launches), so only the first chunk's latency is
+    exposed.  Measured on B200s (256^3, 180 angles): the extra launches and warm-up planes of the z-range pieces cost
+    more than the ~0.2 ms of broadcast they hide (2 GPUs: 445 vs 469 Gvox/s, 8 GPUs: 1355 vs 1483), so it is off by
+    default; it pays when the broadcast is long against the resampling (few matrices per rank, large volumes).
     """
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -174,15 +231,32 @@ def sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = 'filt_bsp
         import torch
         engine = CudaEngine(torch.cuda.current_device())
     mats = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
-    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation)
     mine = split_strided(len(mats), world, rank)
-    out = engine.resample_many(buffer, width, interpolation, mats[mine.start::world]) if len(mine) else \
+    my_mats = mats[mine.start::world]
+    margin = streaming_margin(my_mats, interpolation) if (overlap and len(mine)) else None
+    state = {'out': None, 'done': 0}
+
+    def on_planes(buffer, width, ready):
+        d0 = int(buffer.shape[0])
+        if state['out'] is None:
+            state['out'] = engine.empty((len(mine),) + tuple(buffer.shape[:2]) + (width,))
+        upto = d0 if ready >= d0 else max(state['done'], min(d0, ready - margin))
+        if upto > state['done']:
+            engine.resample_many_range(buffer, width, interpolation, my_mats, state['out'], state['done'], upto)
+            state['done'] = upto
+
+    streaming = overlap and margin is not None and hasattr(engine, 'resample_many_range')
+    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape,
+                                           on_planes if streaming else None, chunks)
+    if streaming:
+        return state['out'], list(mine)
+    out = engine.resample_many(buffer, width, interpolation, my_mats) if len(mine) else \
         engine.empty((0,) + tuple(buffer.shape[:2]) + (width,))
     return out, list(mine)
 
 
 def zslab_affine(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline', src: int = 0, group=None,
-                 engine=None):
+                 engine=None, shape=None):
     """One transform of one (large) volume, the output split into z-slabs across the ranks of `group`.
 
     Returns (slab, (z0, z1)): this rank's output planes, resident on this rank.
@@ -192,7 +266,7 @@ def zslab_affine(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline'
     if engine is None:
         import torch
         engine = CudaEngine(torch.cuda.current_device())
-    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation)
+    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape)
     z0, z1 = split_slabs(int(buffer.shape[0]), world, rank)
     m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(4, 4)
     return engine.resample_slab(buffer, width, interpolation, m, z0, z1), (z0, z1)
