@@ -15,6 +15,7 @@ Workloads (BASELINE.json `configs`, inputs per SURVEY.md section 8d):
   sweep   configs[2]: StaticVolume 256^3 filt_bspline, 180-angle sweep; rank 0 prefilters, one NCCL broadcast of
           the coefficient volume, the angles are split across ranks (strong scaling).
   modes   all five interpolation modes at 512^3 (rot45 and full affine) -> reported under "modes" (1 GPU).
+  project rotate-and-project at 512^3: StaticVolume.project_many vs transform + sum(axis=0) (1 GPU).
 
 `value` is device-resident throughput (inputs already in HBM, CUDA events); `e2e` is the same batch through the
 same public call with pinned HOST arrays in and out (H2D + kernels + D2H inside the timed region).
@@ -39,6 +40,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = 'Gvoxels/s'
+E2E_THREADS = 2  # host threads issuing the e2e leg's independent transform() calls (PCIe duplex overlap)
 ROT45 = dict(rotation=(0, 45, 0), rotation_order='rzxz')
 FULL_AFFINE = dict(scale=(1.1, 0.9, 1.05), shear=(0.05, -0.03, 0.02), rotation=(30, 45, 60), rotation_order='rzxz',
                    translation=(5.5, -3.25, 2.0))
@@ -294,20 +296,38 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
         h.copy_(v)
     np_vols, np_outs = [h.numpy() for h in h_vols], [h.numpy() for h in h_outs]
 
-    def step_e2e():
-        for v, o in zip(np_vols, np_outs):
-            vt.transform(v, interpolation=interp, output=o, device=device, **kw)
+    def one_e2e(i):
+        vt.transform(np_vols[i], interpolation=interp, output=np_outs[i], device=device, **kw)
 
+    # The batch's volumes are independent, so the public call is made from E2E_THREADS host threads (ctypes releases
+    # the GIL inside the library): one call's upload overlaps another's download on the full-duplex PCIe link.  The
+    # single-thread figure (calls strictly one after another) is reported next to it.
+    from concurrent.futures import ThreadPoolExecutor
     e2e_steps = max(2, min(args.steps, 5))
-    step_e2e()
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_by_threads = {}
+    for nthreads in (1, E2E_THREADS):
+        pool = ThreadPoolExecutor(nthreads) if nthreads > 1 else None
+
+        def step_e2e():
+            if pool is None:
+                for i in range(batch):
+                    one_e2e(i)
+            else:
+                list(pool.map(one_e2e, range(batch)))
+
         step_e2e()
-    torch.cuda.synchronize()
-    e2e_sec = reduce_max(time.perf_counter() - t0)
-    barrier()
+        step_e2e()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        e2e_by_threads[nthreads] = reduce_max(time.perf_counter() - t0)
+        barrier()
+        if pool is not None:
+            pool.shutdown()
+    e2e_sec = e2e_by_threads[E2E_THREADS]
     e2e_value = world * vox_step * e2e_steps / e2e_sec / 1e9
     # the host path must agree with the device path
     err = float((torch.from_numpy(np_outs[0]).to(f'cuda:{dev}') - outs[0]).abs().max())
@@ -325,7 +345,9 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
                    'samples': clk['samples']},
         'e2e': {'value': e2e_value, 'unit': METRIC, 'h2d_bytes_per_step': vox_step * 4, 'd2h_bytes_per_step': vox_step * 4,
                 'steps': e2e_steps, 'ms_per_step': e2e_sec / e2e_steps * 1e3,
-                'call': 'same call with pinned numpy arrays for volume and output'},
+                'call': f'same call with pinned numpy arrays for volume and output, issued from {E2E_THREADS} host threads '
+                        '(independent volumes)', 'host_threads': E2E_THREADS,
+                'single_thread_value': world * vox_step * e2e_steps / e2e_by_threads[1] / 1e9},
         'gpu_launches': int(launches),
         'roofline': roofline,
     }
@@ -361,6 +383,49 @@ def run_modes(args, torch, vt, dev):
             bytes_per_vox = 16 if mode.startswith('filt') else 8
             res[f'{mode}/{mname}'] = {'ms': ms, 'gvox_s': n ** 3 / ms / 1e6,
                                       'roofline_frac': bytes_per_vox * n ** 3 / (ms * 1e-3) / 1e9 / peak}
+    return res
+
+
+def run_project(args, torch, vt, dev):
+    """Rotate-and-project: StaticVolume.project_many against the reference's way of doing it
+    (transform into a device array, then sum over axis 0), per mode, for a tilt about axis 0 (the reference example's
+    matrix family) and for a general matrix.  Gvox/s counts the voxels of the transformed volume that is summed."""
+    n = args.size
+    shape = (n, n, n)
+    c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+    mats = {'tilt30_axis0': vt.utils.transform_matrix(rotation=(30, 0, 0), rotation_order='sxyz', center=c),
+            'full_affine': vt.utils.transform_matrix(center=c, **FULL_AFFINE)}
+    src = torch.rand(shape, device=f'cuda:{dev}')
+    dst = torch.zeros(shape, device=f'cuda:{dev}')
+    proj = torch.zeros((1, n, n), device=f'cuda:{dev}')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f'cuda:{dev}')
+
+    def med(fn):
+        ts = []
+        for it in range(args.warmup + args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            if it >= args.warmup:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    res = {}
+    for mode in ('linear', 'filt_bspline', 'filt_bspline_simple'):
+        sv = vt.StaticVolume(src, interpolation=mode, device=f'gpu:{dev}')
+        for mname, m in mats.items():
+            def unfused():
+                dst.zero_()
+                sv.affine(m, output=dst)
+                return dst.sum(dim=0)
+            ms_u = med(unfused)
+            ms_f = med(lambda: sv.project_many([m], output=proj))
+            err = float((proj[0].double() - unfused().double()).abs().max()) / (float(dst.max() - dst.min()) * n)
+            res[f'{mode}/{mname}'] = {'fused_ms': ms_f, 'transform_then_sum_ms': ms_u, 'speedup': ms_u / ms_f,
+                                      'fused_gvox_s': n ** 3 / ms_f / 1e6, 'max_err_of_scale': err}
     return res
 
 
@@ -441,7 +506,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes', 'sweep', 'zslab'])
+    ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes', 'sweep', 'zslab', 'project'])
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--batch', type=int, default=None, help='volumes per step (default 8; smaller only for profiling)')
@@ -482,6 +547,11 @@ def main():
         res = run_modes(args, torch, vt, dev)
         if rank == 0:
             print(json.dumps({'metric': METRIC, 'workload': f'modes {args.size}^3', 'modes': res}))
+        return
+    if args.workload == 'project':
+        res = run_project(args, torch, vt, dev)
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'workload': f'rotate-and-project {args.size}^3', 'project': res}))
         return
     if args.workload in ('sweep', 'zslab'):
         if world == 1:  # single-process: the helpers still want a process group for get_rank()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 3
+#define VT_ABI_VERSION 4
 
 /* status codes: 0 ok; 1..99 library errors; 1000+e = cudaError_t e; 2000+e = CUresult e */
 #define VT_OK 0
@@ -154,6 +154,30 @@ int vt_tex_destroy(vt_tex *tex);
  * vt_affine_f32 (VT_WEIGHTS_EXACT and VT_CUBIC_SIMPLE are not available here) */
 int vt_affine_tex_f32(const vt_tex *tex, float *d_dst, int o0, int o1, int o2, long long dst_batch_stride,
                       const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin, int z_end, void *stream);
+
+/*
+ * Rotate-and-project: the transformed volume summed over axis 0, without ever writing the volume -- what
+ * examples/projections.py:20-26 computes as `static_volume.transform(rotation=...).sum(axis=0)` (a transform kernel launch,
+ * an N*4 B store, and a reduction that reads it back).  d_proj receives n_mats images of shape (o1, o2), image k at
+ * d_proj + k*proj_batch_stride (elements), fully overwritten:
+ *        proj_k[a1][a2] = sum over a0 in [z_begin, z_end) of transform_k(src)[a0][a1][a2],   out-of-bounds voxels adding 0
+ * (so z-slabs computed on different GPUs add up to the full projection).  Other arguments as vt_affine_strided_f32; the
+ * VT_OOB_* bits are ignored.
+ *   - matrices that leave axis 0 alone (the example's `rotation=(i,0,0), 'sxyz'`; every tilt about axis 0): by linearity the
+ *     in-plane interpolation is applied once to sums of input planes -- one 4 B/voxel read of the source and a 2-D resample.
+ *     Needs the caller-owned workspace of vt_project_workspace_bytes(s0,s1,s2) bytes; deterministic.
+ *   - any other matrix (or no workspace): the brick / gather kernels accumulate each thread's run along axis 0 in a
+ *     register and add it to the image with red.global.add.f32 (summation order, hence the last bits, vary run to run).
+ * Float32 summation order differs from transform-then-sum by ~1e-7 of the projection's range either way.
+ * vt_project_tex_f32: the same on a texture handle (general matrices, VT_LINEAR / VT_CUBIC_TEX).
+ */
+size_t vt_project_workspace_bytes(int s0, int s1, int s2);
+int vt_project_strided_f32(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,
+                           float *d_proj, int o0, int o1, int o2, long long proj_batch_stride, const float *h_mats,
+                           int n_mats, int interp, unsigned flags, int z_begin, int z_end, void *d_workspace,
+                           size_t workspace_bytes, int device, void *stream);
+int vt_project_tex_f32(const vt_tex *tex, float *d_proj, int o0, int o1, int o2, long long proj_batch_stride,
+                       const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin, int z_end, void *stream);
 
 /* which kernel family vt_affine_f32 would run for these arguments: 1 = gather, 2 = brick, 3 = slice */
 int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d_src, const float *h_mats,

@@ -60,6 +60,12 @@ def lib():
         L.vt_tex_upload.argtypes = [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _vp]
         L.vt_tex_destroy.argtypes = [_vp]
         L.vt_affine_tex_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _vp]
+        L.vt_project_workspace_bytes.restype = ctypes.c_size_t
+        L.vt_project_workspace_bytes.argtypes = [_i, _i, _i]
+        L.vt_project_strided_f32.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i, _i,
+                                             ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _vp, ctypes.c_size_t,
+                                             _i, _vp]
+        L.vt_project_tex_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _vp]
         L.vt_host_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
         L.vt_host_ctx_destroy.argtypes = [_vp]
         L.vt_host_affine_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f32p, _i, _i, ctypes.c_uint]
@@ -68,7 +74,7 @@ def lib():
         L.vt_profile_kernel_name.restype = ctypes.c_char_p
         L.vt_profile_kernel_name.argtypes = [_i]
         L.vt_profile_read.argtypes = [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
-        if L.vt_abi_version() != 3:
+        if L.vt_abi_version() != 4:
             raise RuntimeError('libvoltools_b200.so ABI version mismatch')
         _lib = L
     return _lib
@@ -159,6 +165,24 @@ def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, ba
                                       stream))
 
 
+def project_workspace_bytes(src_shape):
+    return lib().vt_project_workspace_bytes(*map(int, src_shape))
+
+
+def project(src_ptr, src_shape, proj_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None,
+            device=-1, stream=0, src_strides=None, workspace_ptr=None, workspace_bytes=0):
+    """Sum over axis 0 of the transformed volume (vt_project_strided_f32): K images of dst_shape[1:] at proj_ptr."""
+    m, mp = _mats(matrices)
+    if batch_stride is None:
+        batch_stride = int(dst_shape[1]) * int(dst_shape[2])
+    z0, z1 = (0, dst_shape[0]) if z_range is None else z_range
+    if src_strides is None:
+        src_strides = (int(src_shape[2]), int(src_shape[1]) * int(src_shape[2]))
+    check(lib().vt_project_strided_f32(src_ptr, *map(int, src_shape), int(src_strides[0]), int(src_strides[1]), proj_ptr,
+                                       *map(int, dst_shape), batch_stride, mp, len(m), interp, flags, z0, z1,
+                                       workspace_ptr, workspace_bytes, device, stream))
+
+
 def affine_plan(src_ptr, src_shape, dst_shape, matrices, interp, flags=0):
     m, mp = _mats(matrices)
     fam = _i(0)
@@ -190,6 +214,14 @@ class Texture:
         z0, z1 = (0, dst_shape[0]) if z_range is None else z_range
         check(lib().vt_affine_tex_f32(self._h, dst_ptr, *map(int, dst_shape), batch_stride, mp, len(m), interp, flags,
                                       z0, z1, stream))
+
+    def project(self, proj_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None, stream=0):
+        m, mp = _mats(matrices)
+        if batch_stride is None:
+            batch_stride = int(dst_shape[1]) * int(dst_shape[2])
+        z0, z1 = (0, dst_shape[0]) if z_range is None else z_range
+        check(lib().vt_project_tex_f32(self._h, proj_ptr, *map(int, dst_shape), batch_stride, mp, len(m), interp, flags,
+                                       z0, z1, stream))
 
     def close(self):
         if self._h:

@@ -16,6 +16,8 @@ int vt_launch_brick(const VtResampleParams &P, int interp, cudaStream_t st);    
 int vt_brick_supported(const VtResampleParams &P, int interp);                  // vt_resample_brick.cu
 int vt_launch_slice(VtResampleParams &P, int interp, cudaStream_t st);          // vt_resample_slice.cu
 int vt_slice_supported(const VtResampleParams &P, int interp);                  // vt_resample_slice.cu
+size_t vt_slice_project_workspace_bytes(int s0, int s1, int s2);                                   // vt_resample_slice.cu
+int vt_launch_slice_project(VtResampleParams &P, int interp, float *d_workspace, cudaStream_t st);  // vt_resample_slice.cu
 int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter.cu
 int vt_prefilter_win(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row, long long dst_plane,
                      float *d_ws, size_t ws_bytes, cudaStream_t st);  // vt_prefilter_win.cu
@@ -57,7 +59,7 @@ long long g_prof_n[VT_K_COUNT];
 const char *const g_prof_names[VT_K_COUNT] = {
     "prefilter_x", "prefilter_y", "prefilter_z", "prefilter_fused", "gather_linear", "gather_cubic_tex",
     "gather_cubic_simple", "brick_linear", "brick_cubic_tex", "brick_cubic_simple", "slice_linear",
-    "slice_cubic_tex", "slice_cubic_simple", "tex_linear", "tex_cubic"};
+    "slice_cubic_tex", "slice_cubic_simple", "tex_linear", "tex_cubic", "plane_sum", "project_2d"};
 
 void prof_drain_locked()
 {
@@ -364,6 +366,88 @@ int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int 
 {
     return vt_affine_strided_f32(d_src, s0, s1, s2, s2, (long long)s1 * s2, d_dst, o0, o1, o2, dst_batch_stride, h_mats,
                                  n_mats, interp, flags, z_begin, z_end, device, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rotate-and-project
+// ---------------------------------------------------------------------------------------------------
+size_t vt_project_workspace_bytes(int s0, int s1, int s2)
+{
+    if (s0 < 1 || s1 < 1 || s2 < 1) return 0;
+    return vt_slice_project_workspace_bytes(s0, s1, s2);
+}
+
+int vt_project_strided_f32(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,
+                           float *d_proj, int o0, int o1, int o2, long long proj_batch_stride, const float *h_mats,
+                           int n_mats, int interp, unsigned flags, int z_begin, int z_end, void *d_workspace,
+                           size_t workspace_bytes, int device, void *stream)
+{
+    if (!h_mats || n_mats < 0) return VT_ERR_INVALID_ARG;
+    if (interp != VT_LINEAR && interp != VT_CUBIC_TEX && interp != VT_CUBIC_SIMPLE) return VT_ERR_INVALID_ARG;
+    if (proj_batch_stride < (long long)o1 * o2) return VT_ERR_INVALID_ARG;
+    if (n_mats == 0) return VT_OK;
+    // OOB voxels add nothing to a sum: the OOB policy bits are meaningless here
+    flags &= ~(unsigned)VT_OOB_ZERO;
+    VtResampleParams P;
+    int rc = fill_params(P, d_src, s0, s1, s2, src_row_stride, src_plane_stride, d_proj, o0, o1, o2, proj_batch_stride, flags,
+                         z_begin, z_end);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool have_ws = d_workspace && workspace_bytes >= vt_slice_project_workspace_bytes(s0, s1, s2);
+    for (int first = 0; first < n_mats; first += VT_MAX_BATCH) {
+        const int count = (n_mats - first) < VT_MAX_BATCH ? (n_mats - first) : VT_MAX_BATCH;
+        copy_mats(P, h_mats, first, count);
+        P.dst = d_proj + (size_t)first * proj_batch_stride;
+        P.flags = flags;
+        int family = choose_family(P, interp, flags);
+        if (family < 0) return VT_ERR_UNSUPPORTED;
+        if (family == 3 && have_ws) {
+            rc = vt_launch_slice_project(P, interp, (float *)d_workspace, st);
+        } else {
+            // general matrices (or no workspace): the resampling kernels add into the zeroed image
+            if (family == 3) family = vt_brick_supported(P, interp) ? 2 : 1;
+            if (o0 > 0 && z_end > z_begin) {
+                // one memset per image keeps a padded proj_batch_stride intact
+                for (int k = 0; k < count; k++)
+                    VT_CUDA(cudaMemsetAsync(P.dst + (size_t)k * proj_batch_stride, 0, (size_t)o1 * o2 * sizeof(float), st));
+            }
+            P.flags = flags | VT_INTERNAL_PROJECT;
+            rc = family == 2 ? vt_launch_brick(P, interp, st) : vt_launch_gather(P, interp, st);
+        }
+        if (rc) return rc;
+    }
+    return VT_OK;
+}
+
+int vt_project_tex_f32(const vt_tex *t, float *d_proj, int o0, int o1, int o2, long long proj_batch_stride,
+                       const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin, int z_end, void *stream)
+{
+    if (!t || !h_mats || n_mats < 0) return VT_ERR_INVALID_ARG;
+    if (interp != VT_LINEAR && interp != VT_CUBIC_TEX) return VT_ERR_INVALID_ARG;
+    if (flags & VT_WEIGHTS_EXACT) return VT_ERR_UNSUPPORTED;
+    if (proj_batch_stride < (long long)o1 * o2) return VT_ERR_INVALID_ARG;
+    if (n_mats == 0) return VT_OK;
+    flags = (flags & ~(unsigned)VT_OOB_ZERO) | VT_INTERNAL_PROJECT;
+    VtResampleParams P;
+    float dummy;
+    int rc = fill_params(P, &dummy, t->s0, t->s1, t->s2, t->s2, (long long)t->s1 * t->s2, d_proj, o0, o1, o2,
+                         proj_batch_stride, flags, z_begin, z_end);
+    if (rc) return rc;
+    DeviceGuard g(t->device);
+    if (g.status) return g.status;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int first = 0; first < n_mats; first += VT_MAX_BATCH) {
+        const int count = (n_mats - first) < VT_MAX_BATCH ? (n_mats - first) : VT_MAX_BATCH;
+        copy_mats(P, h_mats, first, count);
+        P.dst = d_proj + (size_t)first * proj_batch_stride;
+        for (int k = 0; k < count; k++)
+            VT_CUDA(cudaMemsetAsync(P.dst + (size_t)k * proj_batch_stride, 0, (size_t)o1 * o2 * sizeof(float), st));
+        rc = vt_launch_tex(P, t, interp, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return VT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

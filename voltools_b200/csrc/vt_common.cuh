@@ -33,6 +33,10 @@ struct VtResampleParams {
     VtMat mats[VT_MAX_BATCH];
 };
 
+// internal flag (not part of the C ABI's flag set): the general-matrix kernels ADD each thread's voxels along axis 0
+// into a projection image (P.dst = n_mats images of o1 x o2, zeroed by the caller) instead of storing them
+#define VT_INTERNAL_PROJECT 0x1000u
+
 void vt_count_launch(int n = 1);
 
 // 3-D float32 tensor map (dims/strides fastest axis first, strides in bytes for axes 1 and 2), no swizzle, zeros out
@@ -61,6 +65,8 @@ enum VtKernelId {
     VT_K_SLICE_CUBIC_SIMPLE,
     VT_K_TEX_LINEAR,
     VT_K_TEX_CUBIC,
+    VT_K_PLANE_SUM,
+    VT_K_PROJECT_2D,
     VT_K_COUNT
 };
 struct VtProf {

@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(NT, 3)
     __syncthreads();  // the barrier is initialised before anyone polls it
     vt_mbar_wait(bar, 0);
     if (!live) return;
+    const bool project = (P.flags & VT_INTERNAL_PROJECT) != 0;  // sum along axis 0 instead of storing
+    float acc = 0.0f;
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
         const int a0 = a0_0 + tz * VPT + v;
@@ -208,15 +210,17 @@ __global__ void __launch_bounds__(NT, 3)
         const float p2 = vt_row_finish(M.r[2], vt_row_base(M.r[2], fa0, fa1), fa2);
         // transforms.py:276-278
         if (p2 < 0 || p1 < 0 || p0 < 0 || p2 >= f2 || p1 >= f1 || p0 >= f0) {
-            if (OOB_ZERO) dst[(size_t)a0 * oplane] = 0.0f;
+            if (OOB_ZERO && !project) dst[(size_t)a0 * oplane] = 0.0f;
             continue;
         }
         float r;
         if (INTERP == VT_LINEAR) r = tex3d_brick<RULE>(b, p2, p1, p0);
         else if (INTERP == VT_CUBIC_TEX) r = cubic_tex_brick<RULE>(b, p2, p1, p0);
         else r = cubic_simple_brick(b, p2, p1, p0);
-        dst[(size_t)a0 * oplane] = r;
+        if (project) acc += r;
+        else dst[(size_t)a0 * oplane] = r;
     }
+    if (project && acc != 0.0f) atomicAdd(dst, acc);
 }
 
 // brick dimensions needed by the batch (max over matrices), or false if some matrix needs more than fits

@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(TX *TY) vt_gather_kernel(const __grid_constant
     const float fa1 = (float)a1, fa2 = (float)a2;
     const int zlo = P.z_begin + zt * TZ;
     const int zhi = min(zlo + TZ, P.z_end);
+    const bool project = (P.flags & VT_INTERNAL_PROJECT) != 0;  // sum along axis 0 instead of storing
+    float acc = 0.0f;
     for (int a0 = zlo; a0 < zhi; a0++) {
         const float fa0 = (float)a0;
         const float p0 = vt_row_finish(M.r[0], vt_row_base(M.r[0], fa0, fa1), fa2);
@@ -169,15 +171,17 @@ __global__ void __launch_bounds__(TX *TY) vt_gather_kernel(const __grid_constant
         const size_t o = ((size_t)a0 * P.o1 + a1) * P.o2 + a2;
         // transforms.py:276-278
         if (p2 < 0 || p1 < 0 || p0 < 0 || p2 >= f2 || p1 >= f1 || p0 >= f0) {
-            if (OOB_ZERO) dst[o] = 0.0f;
+            if (OOB_ZERO && !project) dst[o] = 0.0f;
             continue;
         }
         float r;
         if (INTERP == VT_LINEAR) r = tex3d_emul<RULE>(s, p2, p1, p0);
         else if (INTERP == VT_CUBIC_TEX) r = cubic_tex<RULE>(s, p2, p1, p0);
         else r = cubic_simple(s, p2, p1, p0);
-        dst[o] = r;
+        if (project) acc += r;
+        else dst[o] = r;
     }
+    if (project && acc != 0.0f) atomicAdd(dst + (size_t)a1 * P.o2 + a2, acc);
 }
 
 template <int INTERP, int RULE>

@@ -644,6 +644,194 @@ int launch1(VtResampleParams &P, cudaStream_t st)
     return launch2<INTERP, 0>(P, st);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// rotate-and-project (the reference's examples/projections.py:20-26 transforms the volume and
+// then sums it over axis 0).  For a slice-family matrix the resampling is a fixed in-plane operator applied to every
+// input plane plus three fixed axis-0 weights, so by linearity the sum over axis 0 of the transformed volume is that
+// in-plane operator applied ONCE to sums of input planes:
+//      proj = A(sum of planes V-1) + B(sum of planes V) + C(sum of planes V+1),
+// V = the input planes at the centre of an in-bounds output plane, planes outside the source counting as zero (border
+// mode), and (A, B, C) the interpolator's per-plane weight sets (linear: B only; cubic_simple: the same 16 taps times
+// B(-1), B(0), B(1); cubic_tex: the three integer-weighted sets of Taps<VT_CUBIC_TEX>).  Cost: one read of the source
+// (4 B/voxel, no output volume) + a 2-D resample, instead of o0 resampled planes written and read back.
+// Float32 summation order differs from transform-then-sum (~1e-7 of the projection's range).
+// ---------------------------------------------------------------------------------------------------
+constexpr int PS_NT = 128;   // threads per CTA of the plane-sum kernel, along x
+constexpr int PS_PAD = 2;    // zero border (texels) around the summed planes: cubic footprints reach -2 .. s+1
+constexpr int PS_UNROLL = 8;
+
+struct VtPlaneRanges {
+    int b0, b1;  // V = [b0, b1): centre planes; A sums [b0-1, b1-1) and C sums [b0+1, b1+1), both clipped to the source
+};
+
+// partial[chunk][3][s1][s2] = sums of the source planes of z-chunk `chunk` that fall in the A / B / C ranges
+__global__ void __launch_bounds__(PS_NT)
+    vt_plane_sum_kernel(const float *__restrict__ src, int s0, int s1, int s2, long long src_row, long long src_plane,
+                        VtPlaneRanges R, int z_chunk, float *__restrict__ partial)
+{
+    const int x = blockIdx.x * PS_NT + threadIdx.x, y = blockIdx.y, c = blockIdx.z;
+    if (x >= s2) return;
+    // planes any of the three ranges needs: [b0-1, b1+1) clipped
+    const int lo = max(R.b0 - 1, 0), hi = min(R.b1 + 1, s0);
+    const int q0 = lo + c * z_chunk, q1 = min(q0 + z_chunk, hi);
+    const float *p = src + (size_t)q0 * src_plane + (size_t)y * src_row + x;
+    float sa = 0.0f, sb = 0.0f, sc = 0.0f;
+    int q = q0;
+    for (; q + PS_UNROLL <= q1; q += PS_UNROLL) {
+        float v[PS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PS_UNROLL; u++) v[u] = __ldg(p + (size_t)u * src_plane);
+#pragma unroll
+        for (int u = 0; u < PS_UNROLL; u++) {
+            const int qq = q + u;
+            if (qq >= R.b0 - 1 && qq < R.b1 - 1) sa += v[u];
+            if (qq >= R.b0 && qq < R.b1) sb += v[u];
+            if (qq >= R.b0 + 1 && qq < R.b1 + 1) sc += v[u];
+        }
+        p += (size_t)PS_UNROLL * src_plane;
+    }
+    for (; q < q1; q++) {
+        const float v = __ldg(p);
+        if (q >= R.b0 - 1 && q < R.b1 - 1) sa += v;
+        if (q >= R.b0 && q < R.b1) sb += v;
+        if (q >= R.b0 + 1 && q < R.b1 + 1) sc += v;
+        p += src_plane;
+    }
+    const size_t n = (size_t)s1 * s2, o = (size_t)y * s2 + x;
+    float *out = partial + (size_t)c * 3 * n;
+    out[o] = sa;
+    out[n + o] = sb;
+    out[2 * n + o] = sc;
+}
+
+// sums[k][PS_PAD + y][PS_PAD + x] = sum over chunks of partial[chunk][k][y][x] (fixed order: deterministic);
+// linear keeps its single sum (B) in plane 0, the cubic modes A, B, C in planes 0, 1, 2
+__global__ void __launch_bounds__(PS_NT)
+    vt_plane_sum_finish_kernel(const float *__restrict__ partial, int chunks, int s1, int s2, int linear, int pitch, int pe,
+                               float *__restrict__ sums)
+{
+    const int x = blockIdx.x * PS_NT + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+    if (x >= s2) return;
+    const size_t n = (size_t)s1 * s2;
+    const float *p = partial + (size_t)(linear ? 1 : k) * n + (size_t)y * s2 + x;
+    float s = 0.0f;
+    for (int c = 0; c < chunks; c++) s += __ldg(p + (size_t)c * 3 * n);
+    sums[(size_t)k * pe + (size_t)(PS_PAD + y) * pitch + (PS_PAD + x)] = s;
+}
+
+// one thread per projection pixel (a1, a2) and matrix: the interpolators' in-plane part on the summed planes
+template <int INTERP, int RULE>
+__global__ void __launch_bounds__(NT)
+    vt_project2d_kernel(const __grid_constant__ VtResampleParams P, const float *__restrict__ sums, int pitch, int pe)
+{
+    using T = Taps<INTERP>;
+    const int a2 = blockIdx.x * TS + (threadIdx.x & (TS - 1)), a1 = blockIdx.y * TS + (threadIdx.x / TS);
+    const int mat = blockIdx.z;
+    if (a1 >= P.o1 || a2 >= P.o2) return;
+    const VtMat &M = P.mats[mat];
+    const float p1 = inplane_coord(M.r[1], (float)a1, (float)a2);
+    const float p2 = inplane_coord(M.r[2], (float)a1, (float)a2);
+    float r = 0.0f;
+    // transforms.py:276-278 for the two in-plane axes (axis 0 is in the plane ranges)
+    if (!(p2 < 0 || p1 < 0 || p2 >= (float)P.s2 || p1 >= (float)P.s1)) {
+        T taps;
+        taps.template init<RULE>(p1, p2, -PS_PAD, -PS_PAD, pitch);
+        if constexpr (INTERP == VT_LINEAR) {
+            float o[T::PPS];
+            taps.planes(sums, pe, o);
+            r = o[0];
+        } else if constexpr (INTERP == VT_CUBIC_SIMPLE) {
+            float ab[T::PPS], bc[T::PPS];
+            taps.planes(sums, pe, ab);
+            taps.planes(sums + pe, pe, bc);
+            r = fmaf(taps.wz2, bc[1], fmaf(taps.wz1, ab[1], __fmul_rn(taps.wz0, ab[0])));
+        } else {
+            float qa[T::PPS], qb[T::PPS], qc[T::PPS], ra[T::PPS], rb[T::PPS], rc[T::PPS];
+            taps.planes3(sums, pe, qa, qb, qc);
+            taps.planes3(sums + pe, pe, ra, rb, rc);
+            r = (qa[0] + qb[1]) + rc[1];
+        }
+    }
+    P.dst[(size_t)mat * P.dst_batch_stride + (size_t)a1 * P.o2 + a2] = r;
+}
+
+struct ProjectLayout {
+    int pitch, pe, chunks, z_chunk;
+    size_t partial_floats, sums_floats;
+};
+ProjectLayout project_layout(int s0, int s1, int s2)
+{
+    ProjectLayout L;
+    L.pitch = (s2 + 2 * PS_PAD + 3) / 4 * 4;
+    L.pe = L.pitch * (s1 + 2 * PS_PAD);
+    // enough threads in flight to cover the HBM latency: ~600 K, each with PS_UNROLL loads outstanding
+    const long long cols = (long long)s1 * s2;
+    long long c = (600000 + cols - 1) / cols;
+    const int span = s0 + 2;
+    if (c > span / PS_UNROLL) c = span / PS_UNROLL;
+    if (c > 64) c = 64;
+    if (c < 1) c = 1;
+    L.z_chunk = (span + (int)c - 1) / (int)c;
+    L.chunks = (span + L.z_chunk - 1) / L.z_chunk;
+    L.partial_floats = (size_t)L.chunks * 3 * (size_t)cols;
+    L.sums_floats = (size_t)4 * L.pe;  // 4 planes: Taps<VT_LINEAR>::planes reads a stage of four
+    return L;
+}
+
+template <int INTERP, int RULE>
+int project2(VtResampleParams &P, float *ws, cudaStream_t st)
+{
+    const ProjectLayout L = project_layout(P.s0, P.s1, P.s2);
+    float *partial = ws, *sums = ws + L.partial_floats;
+    // matrices with the same integer shift along axis 0 share their plane sums
+    for (int first = 0; first < P.n_mats;) {
+        const float t0f = P.mats[first].r[0][3];
+        int count = 1;
+        while (first + count < P.n_mats && P.mats[first + count].r[0][3] == t0f) count++;
+        const int t0 = (int)t0f;
+        VtPlaneRanges R;
+        R.b0 = max(0, P.z_begin + t0);
+        R.b1 = min(P.s0, P.z_end + t0);
+        if (R.b1 < R.b0) R.b1 = R.b0;
+        VT_CUDA(cudaMemsetAsync(sums, 0, L.sums_floats * sizeof(float), st));
+        const int lo = max(R.b0 - 1, 0), hi = min(R.b1 + 1, P.s0);
+        if (R.b1 > R.b0 && hi > lo) {
+            const int zc = (hi - lo + L.chunks - 1) / L.chunks;
+            const int chunks = (hi - lo + zc - 1) / zc;
+            {
+                VtProf prof(VT_K_PLANE_SUM, st);
+                dim3 grid((P.s2 + PS_NT - 1) / PS_NT, P.s1, chunks);
+                vt_plane_sum_kernel<<<grid, PS_NT, 0, st>>>(P.src, P.s0, P.s1, P.s2, P.src_row, P.src_plane, R, zc, partial);
+            }
+            dim3 grid2((P.s2 + PS_NT - 1) / PS_NT, P.s1, INTERP == VT_LINEAR ? 1 : 3);
+            vt_plane_sum_finish_kernel<<<grid2, PS_NT, 0, st>>>(partial, chunks, P.s1, P.s2, INTERP == VT_LINEAR ? 1 : 0,
+                                                                 L.pitch, L.pe, sums);
+            vt_count_launch(2);
+        }
+        VtResampleParams Q = P;
+        Q.n_mats = count;
+        for (int k = 0; k < count; k++) Q.mats[k] = P.mats[first + k];
+        Q.dst = P.dst + (size_t)first * P.dst_batch_stride;
+        {
+            VtProf prof(VT_K_PROJECT_2D, st);
+            dim3 grid((P.o2 + TS - 1) / TS, (P.o1 + TS - 1) / TS, count);
+            vt_project2d_kernel<INTERP, RULE><<<grid, NT, 0, st>>>(Q, sums, L.pitch, L.pe);
+        }
+        vt_count_launch();
+        VT_CUDA(cudaGetLastError());
+        first += count;
+    }
+    return VT_OK;
+}
+
+template <int INTERP>
+int project1(VtResampleParams &P, float *ws, cudaStream_t st)
+{
+    if (INTERP != VT_CUBIC_SIMPLE && (P.flags & VT_WEIGHTS_EXACT)) return project2<INTERP, 2>(P, ws, st);
+    return project2<INTERP, 0>(P, ws, st);
+}
+
 }  // namespace
 
 int vt_slice_supported(const VtResampleParams &P, int interp) { return slice_ok(P, interp) ? 1 : 0; }
@@ -655,6 +843,24 @@ int vt_launch_slice(VtResampleParams &P, int interp, cudaStream_t st)
         case VT_LINEAR: return launch1<VT_LINEAR>(P, st);
         case VT_CUBIC_TEX: return launch1<VT_CUBIC_TEX>(P, st);
         case VT_CUBIC_SIMPLE: return launch1<VT_CUBIC_SIMPLE>(P, st);
+    }
+    return VT_ERR_INVALID_ARG;
+}
+
+size_t vt_slice_project_workspace_bytes(int s0, int s1, int s2)
+{
+    const ProjectLayout L = project_layout(s0, s1, s2);
+    return (L.partial_floats + L.sums_floats) * sizeof(float);
+}
+
+// P.dst = n_mats projections of o1 x o2 (P.dst_batch_stride apart); sums output planes [z_begin, z_end)
+int vt_launch_slice_project(VtResampleParams &P, int interp, float *d_workspace, cudaStream_t st)
+{
+    if (P.o1 <= 0 || P.o2 <= 0 || P.n_mats <= 0) return VT_OK;
+    switch (interp) {
+        case VT_LINEAR: return project1<VT_LINEAR>(P, d_workspace, st);
+        case VT_CUBIC_TEX: return project1<VT_CUBIC_TEX>(P, d_workspace, st);
+        case VT_CUBIC_SIMPLE: return project1<VT_CUBIC_SIMPLE>(P, d_workspace, st);
     }
     return VT_ERR_INVALID_ARG;
 }

@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(NT) vt_tex_kernel(const __grid_constant__ VtRe
     const float fa1 = (float)a1, fa2 = (float)a2;
     float *__restrict__ dst = P.dst + (size_t)mat * P.dst_batch_stride + ((size_t)a1 * P.o2 + a2);
     const size_t oplane = (size_t)P.o1 * P.o2;
+    const bool project = (P.flags & VT_INTERNAL_PROJECT) != 0;  // sum along axis 0 instead of storing
+    float acc = 0.0f;
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
         const int a0 = a0_0 + v;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(NT) vt_tex_kernel(const __grid_constant__ VtRe
         const float p2 = vt_row_finish(M.r[2], vt_row_base(M.r[2], fa0, fa1), fa2);
         // transforms.py:276-278
         if (p2 < 0 || p1 < 0 || p0 < 0 || p2 >= f2 || p1 >= f1 || p0 >= f0) {
-            if (OOB_ZERO) dst[(size_t)a0 * oplane] = 0.0f;
+            if (OOB_ZERO && !project) dst[(size_t)a0 * oplane] = 0.0f;
             continue;
         }
         float r;
@@ -92,8 +94,10 @@ __global__ void __launch_bounds__(NT) vt_tex_kernel(const __grid_constant__ VtRe
             t001 = __fmaf_rn(g0y, t001, __fmul_rn(g1y, t011));
             r = __fmaf_rn(g0z, t000, __fmul_rn(g1z, t001));
         }
-        dst[(size_t)a0 * oplane] = r;
+        if (project) acc += r;
+        else dst[(size_t)a0 * oplane] = r;
     }
+    if (project && acc != 0.0f) atomicAdd(dst, acc);
 }
 
 template <int INTERP>

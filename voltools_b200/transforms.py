@@ -13,6 +13,7 @@ Extension: with a numpy `volume`, `output=` may also be a float32 C-contiguous n
 then completely overwritten (out-of-bounds voxels = 0, like output=None) straight from the device and the function
 returns None -- this saves the host-side copy of the result.
 """
+import threading
 from typing import Tuple, Union
 
 import numpy as np
@@ -25,7 +26,9 @@ _INTERPOLATIONS = _native.INTERPOLATIONS
 AVAILABLE_INTERPOLATIONS = list(_INTERPOLATIONS.keys())
 AVAILABLE_DEVICES = utils.get_available_devices()
 
-_host_ctx = {}
+# numpy-in / numpy-out contexts (pinned staging + device buffers), one per host thread and device: transform() may be
+# called from several threads at once, and two calls in flight overlap one's upload with the other's download
+_host_tls = threading.local()
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -148,6 +151,24 @@ def rotate(volume, rotation: Tuple[float, float, float], rotation_units: str = '
     return affine(volume, m, interpolation, reshape, profile, output, device)
 
 
+def project(volume,
+            scale: Union[float, Tuple[float, float, float], np.ndarray] = None,
+            shear: Union[float, Tuple[float, float, float], np.ndarray] = None,
+            rotation: Union[Tuple[float, float, float], np.ndarray] = None,
+            rotation_units: str = 'deg', rotation_order: str = 'rzxz',
+            translation: Union[Tuple[float, float, float], np.ndarray] = None,
+            center: Union[Tuple[float, float, float], np.ndarray] = None,
+            interpolation: str = 'linear',
+            device: str = 'gpu'):
+    """`transform(volume, ...).sum(axis=0)` fused (examples/projections.py:44-47): the transformed volume is never
+    written.  Returns the (d1, d2) projection as a numpy array.  For many projections of one volume use
+    StaticVolume.project / project_many (the volume is uploaded and prefiltered once)."""
+    from .volume import StaticVolume
+    _check_args(interpolation, device)
+    return StaticVolume(volume, interpolation=interpolation, device=device).project(
+        scale, shear, rotation, rotation_units, rotation_order, translation, center)
+
+
 def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', reshape: bool = False,
            profile: bool = False, output=None, device: str = 'gpu'):
     """GPU branch of transforms.py:109-229."""
@@ -199,9 +220,12 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
             # numpy in -> numpy out (transforms.py:180-223): pipelined host path inside the library
             src = np.ascontiguousarray(volume, dtype=np.float32)
             result = output if host_out else np.empty(shape, dtype=np.float32)
-            ctx = _host_ctx.get(dev)
+            ctxs = getattr(_host_tls, 'ctx', None)
+            if ctxs is None:
+                ctxs = _host_tls.ctx = {}
+            ctx = ctxs.get(dev)
             if ctx is None:
-                ctx = _host_ctx[dev] = _native.HostContext(dev)
+                ctx = ctxs[dev] = _native.HostContext(dev)
             ctx.affine(src, result, m, interp, needs_prefilter)
             if host_out:
                 result = None

@@ -169,6 +169,79 @@ class StaticVolume:
             self._launch(ptr, m, flags, stream)
         return out_t
 
+    # -- rotate-and-project (examples/projections.py:20-26: `transform(...).sum(axis=0)`, fused) ----------
+    def _project(self, ptr, m, z_range, stream):
+        torch = _torch()
+        use_tex = getattr(self, '_tex', None) not in (None, False) and \
+            self._interp in (_native.LINEAR, _native.CUBIC_TEX) and \
+            _native.affine_plan(self._coeffs.data_ptr(), self.shape, self.shape, m, self._interp) != 'slice'
+        if use_tex:
+            self._tex.project(ptr, self.shape, m, self._interp, z_range=z_range, stream=stream)
+            return
+        ws = getattr(self, '_project_ws', None)
+        if ws is None:
+            ws = self._project_ws = torch.empty(_native.project_workspace_bytes(self.shape), dtype=torch.uint8,
+                                                device=f'cuda:{self._dev}')
+        _native.project(self._coeffs.data_ptr(), self.shape, ptr, self.shape, m, self._interp, z_range=z_range,
+                        device=self._dev, stream=stream, src_strides=self._strides, workspace_ptr=ws.data_ptr(),
+                        workspace_bytes=ws.numel())
+
+    def project_many(self, matrices: Sequence[np.ndarray], output=None, z_range=None):
+        """Projections along axis 0 of the volume transformed by each of K matrices: what the reference computes as
+        `static_volume.affine(m).sum(axis=0)` per matrix, without writing (or reading back) the transformed volumes.
+
+        Matrices that leave axis 0 alone -- every tilt `rotation=(i, 0, 0), rotation_order='sxyz'` of the reference's
+        example -- cost ONE read of the resident volume plus a 2-D resample per matrix; other matrices run the
+        resampling kernels with a register accumulator and one atomic add per thread.
+
+        output: None -> returns a new torch CUDA tensor (K, d1, d2); a (K, d1, d2) device array -> overwritten,
+        returns None.  z_range=(z0, z1) sums output planes z0..z1-1 only (partial projections of z-slabs add up).
+        """
+        torch = _torch()
+        m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
+        pshape = (len(m), self.shape[1], self.shape[2])
+        with torch.cuda.device(self._dev):
+            if output is None:
+                out_t = torch.empty(pshape, dtype=torch.float32, device=f'cuda:{self._dev}')
+                ptr = out_t.data_ptr()
+            else:
+                vout = _device_view(output, 'output')
+                if vout.shape != pshape:
+                    raise ValueError(f'output shape {vout.shape} does not match {pshape}')
+                out_t, ptr = None, vout.ptr
+            self._project(ptr, m, z_range, _stream(self._dev))
+        return out_t
+
+    def affine_project(self, transform_m: np.ndarray, output=None) -> Union[np.ndarray, None]:
+        """`self.affine(transform_m).sum(axis=0)` fused: returns the (d1, d2) projection as numpy, like affine(); or
+        overwrites the (d1, d2) device array `output` and returns None."""
+        m = np.ascontiguousarray(transform_m, dtype=np.float32).reshape(1, 4, 4)
+        if output is None:
+            return self.project_many(m)[0].cpu().numpy()
+        vout = _device_view(output, 'output')
+        if vout.shape != self.shape[1:]:
+            raise ValueError(f'output shape {vout.shape} does not match {self.shape[1:]}')
+        with _torch().cuda.device(self._dev):
+            self._project(vout.ptr, m, None, _stream(self._dev))
+        return None
+
+    def project(self, scale: Union[float, Tuple[float, float, float], np.ndarray] = None,
+                shear: Union[float, Tuple[float, float, float], np.ndarray] = None,
+                rotation: Union[Tuple[float, float, float], np.ndarray] = None,
+                rotation_units: str = 'deg', rotation_order: str = 'rzxz',
+                translation: Union[Tuple[float, float, float], np.ndarray] = None,
+                center: Union[Tuple[float, float, float], np.ndarray] = None,
+                output=None) -> Union[np.ndarray, None]:
+        """`self.transform(...same arguments...).sum(axis=0)` fused (arguments as volume.py:103-113)."""
+        if center is None:
+            center = np.divide(np.subtract(self.shape, 1), 2, dtype=np.float32)
+        if isinstance(scale, float):
+            scale = (scale, scale, scale)
+        if isinstance(shear, float):
+            shear = (shear, shear, shear)
+        m = transform_matrix(scale, shear, rotation, rotation_units, rotation_order, translation, center)
+        return self.affine_project(m, output)
+
     def transform(self, scale: Union[float, Tuple[float, float, float], np.ndarray] = None,
                   shear: Union[float, Tuple[float, float, float], np.ndarray] = None,
                   rotation: Union[Tuple[float, float, float], np.ndarray] = None,
