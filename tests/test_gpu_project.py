@@ -128,7 +128,7 @@ def test_project_vs_reference_kernels(vt):
         sv = vt.StaticVolume(vol, interpolation=mode, device='gpu:0')
         for angle in (-60, 12):
             m = vt.utils.transform_matrix(rotation=(angle, 0, 0), rotation_order='sxyz', center=c)
-            want = oracle.transform_ref_gpu(vol, m, mode).astype(np.float64).sum(axis=0)
+            want = oracle.transform_ref_gpu(vol, m, mode)[0].astype(np.float64).sum(axis=0)
             got = sv.affine_project(m)
             # per-voxel tolerance of the mode (2e-3 for the 8-bit-weight modes) -- observed ~1e-7
             assert float(np.abs(got - want).max()) / _scale(vol, mode) <= 1e-5, (mode, angle)
@@ -142,3 +142,19 @@ def test_module_level_project(vt):
     want = oracle.affine(vol, m, 'filt_bspline').astype(np.float64).sum(axis=0)
     assert got.shape == shape[1:]
     assert float(np.abs(got - want).max()) / _scale(vol, 'filt_bspline') <= TOL
+
+
+def test_host_path_from_several_threads(vt):
+    """transform() with numpy in / numpy out from concurrent host threads (one host context per thread, uploads chained
+    per device): every result equals the single-threaded one bit for bit."""
+    from concurrent.futures import ThreadPoolExecutor
+    shape = (136, 60, 68)
+    rng = np.random.default_rng(11)
+    vols = [rng.random(shape, dtype=np.float32) for _ in range(6)]
+    kw = dict(rotation=(0, 33, 0), rotation_order='rzxz', interpolation='filt_bspline', device='gpu:0')
+    want = [vt.transform(v, **kw) for v in vols]
+    with ThreadPoolExecutor(3) as pool:
+        for _ in range(3):
+            got = list(pool.map(lambda v: vt.transform(v, **kw), vols))
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w)

@@ -66,3 +66,20 @@ t0 = time.perf_counter()
 for _ in range(100):
     vt.utils.transform_matrix(rotation=(0, 45, 0), rotation_order='rzxz', center=c)
 print(f'transform_matrix: {(time.perf_counter() - t0) * 10:.3f} ms')
+
+# independent volumes through transform() from T host threads (each thread has its own host context)
+from concurrent.futures import ThreadPoolExecutor  # noqa: E402
+B = 8
+vs = [torch.rand(shape).pin_memory().numpy() for _ in range(B)]
+os_ = [torch.empty(shape).pin_memory().numpy() for _ in range(B)]
+kw = dict(rotation=(0, 45, 0), rotation_order='rzxz')
+for T in (1, 2, 3, 4):
+    pool = ThreadPoolExecutor(T)
+
+    def step():
+        list(pool.map(lambda i: vt.transform(vs[i], interpolation='filt_bspline', output=os_[i], device='gpu:0', **kw),
+                      range(B)))
+    ms = wall(step, it=4) / B
+    print(f'{n}^3 filt_bspline rot45, {B} volumes from {T} host threads: {ms:.3f} ms per volume -> '
+          f'{n ** 3 / ms / 1e6:.2f} Gvox/s')
+    pool.shutdown()

@@ -56,6 +56,29 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// How a warp's 32 lanes tile the CTA's 16 x 16 columns: 2 x 16, 4 x 8 or 8 x 4 (rows x columns).  Lanes land on bank
+// (y*pitch + x) mod 32 of their footprint origin and the pitch is a multiple of 4 (TMA rows are multiples of 16 bytes),
+// so which shape spreads a warp over the most banks depends on the matrix: at 0 and 90 degrees 2 x 16 puts its two rows
+// on the same 16 banks (2 wavefronts per load) where 4 x 8 with pitch = 8 mod 32 / 4 mod 32 is conflict free.  The host
+// picks the pitch (per launch when it is the TMA box width) and the shape (per matrix, P.aux bits 6-7) from a bank
+// simulation (pitch_cost); over a 180-angle sweep that is 1.66 wavefronts
+// per load instead of 1.96 (45 degrees stays at 1.97 under every shape and pitch).
+constexpr int N_LAYOUTS = 3;
+__host__ __device__ __forceinline__ void lane_pos(int tid, int layout, int &ty, int &tx)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    if (layout == 0) {
+        ty = tid >> 4;
+        tx = tid & 15;
+    } else if (layout == 1) {
+        ty = 4 * (warp >> 1) + (lane >> 3);
+        tx = 8 * (warp & 1) + (lane & 7);
+    } else {
+        ty = 8 * (warp >> 2) + (lane >> 2);
+        tx = 4 * (warp & 3) + (lane & 3);
+    }
+}
+
 // in-plane coordinate of a column, reference recipe (transforms.py:264-274) with the a0 term dropped: it is an
 // exact no-op because M[r][0] == 0 (fma(a0, 0, t) == t).
 __host__ __device__ __forceinline__ float inplane_coord(const float *row, float a1, float a2)
@@ -303,7 +326,8 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
     const int tile_y = blockIdx.x / ntx, tile_x = blockIdx.x - tile_y * ntx;
     const int mat = blockIdx.z;
     const VtMat &M = P.mats[mat];
-    const int pitch = TMA ? G.box_w : (int)P.aux[mat];
+    const int pitch = TMA ? G.box_w : (int)(P.aux[mat] & 63);
+    const int layout = (int)(P.aux[mat] >> 6);
     const unsigned stage_bytes = G.stage_bytes;
     const int pe = G.plane_elems;
     const int t0 = (int)M.r[0][3];
@@ -368,7 +392,8 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
     const size_t plane_bytes = (size_t)P.src_plane * sizeof(float);
 
     // this thread's column
-    const int ty = tid / TS, tx = tid - ty * TS;
+    int ty, tx;
+    lane_pos(tid, layout, ty, tx);
     const int a1 = a1_0 + ty, a2 = a2_0 + tx;
     const bool live = a1 < P.o1 && a2 < P.o2;
     const float p1 = inplane_coord(M.r[1], (float)a1, (float)a2);
@@ -499,16 +524,20 @@ bool slice_ok(const VtResampleParams &P, int interp)
 // position; lanes land on bank (y*pitch + x) mod 32.  The host picks the pitch (cp.async variant: per matrix; TMA
 // variant: the box width) with the fewest bank conflicts over a few sample warps.
 // bank conflicts of one warp's first tap for a given shared-memory pitch (see choose_pitch)
-int pitch_cost(const VtMat &M, int pitch)
+constexpr int PITCH_SAMPLES = 6;
+int pitch_cost(const VtMat &M, int pitch, int layout)
 {
     int cost = 0;
-    for (int sample = 0; sample < 4; sample++) {
-        const int a1_0 = 16 * (1 + 3 * sample) + 2 * sample, a2_0 = 16 * (2 + 5 * sample);
+    for (int sample = 0; sample < PITCH_SAMPLES; sample++) {
+        // tiles spread over the image, different warps of the CTA
+        const int a1_0 = 16 * (1 + 3 * sample), a2_0 = 16 * (2 + 5 * sample);
         unsigned char count[32] = {0};
         int first_addr[32];
         int worst = 0;
         for (int lane = 0; lane < 32; lane++) {
-            const int a1 = a1_0 + lane / 16, a2 = a2_0 + lane % 16;
+            int ty, tx;
+            lane_pos(32 * ((3 * sample) & 7) + lane, layout, ty, tx);
+            const int a1 = a1_0 + ty, a2 = a2_0 + tx;
             const int y = (int)floorf(inplane_coord(M.r[1], (float)a1, (float)a2) - 0.5f);
             const int x = (int)floorf(inplane_coord(M.r[2], (float)a1, (float)a2) - 0.5f);
             const int addr = y * pitch + x + (1 << 20);
@@ -579,14 +608,37 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         }
         const int need_h = min(BMAX, (int)floorf(ext_y + 0.1f) + 6), need_w = min(BMAX, (int)floorf(ext_x + 0.1f) + 6);
         // + 3: the box start is rounded down to a multiple of 4 texels (16-byte aligned start address)
-        int best_w = (need_w + 3 + 3) / 4 * 4, best_cost = 1 << 30;
+        // the box width is the shared-memory pitch of every matrix of the launch; each matrix then takes its best shape
+        // Cost of a width, in SM cycles per output voxel and plane: shared-memory wavefronts of the taps (one per clock)
+        // + the staged footprint through the L2 -> SM path (~64 B/clk; the linear kernel sits at 74 % of L2 throughput,
+        // so a wider box must buy more than it costs there).
+        constexpr int TAPS = INTERP == VT_LINEAR ? 4 : 16;
+        int best_w = (need_w + 3 + 3) / 4 * 4;
+        float best_cost = 1e30f;
+        unsigned char shape[VT_MAX_BATCH];
         for (int w = (need_w + 3 + 3) / 4 * 4; w <= need_w + 3 + 12 && w <= PITCH_MAX; w += 4) {
-            const int c = pitch_cost(P.mats[0], w) + pitch_cost(P.mats[P.n_mats / 2], w);
-            if (c < best_cost) {
-                best_cost = c;
+            float total = (float)P.n_mats * (float)(w * need_h) * (4.0f / 64.0f / (float)NT);
+            unsigned char sh[VT_MAX_BATCH];
+            for (int k = 0; k < P.n_mats; k++) {
+                int bc = 1 << 30;
+                for (int layout = 0; layout < N_LAYOUTS; layout++) {
+                    const int c = pitch_cost(P.mats[k], w, layout);
+                    if (c < bc) {
+                        bc = c;
+                        sh[k] = (unsigned char)layout;
+                    }
+                }
+                total += (float)(TAPS * bc) / (float)(PITCH_SAMPLES * 32);
+            }
+            if (total < best_cost) {
+                best_cost = total;
                 best_w = w;
+                memcpy(shape, sh, sizeof sh);
             }
         }
+        const char *force = getenv("VT_SLICE_LAYOUT");  // tuning knob
+        for (int k = 0; k < P.n_mats; k++)
+            P.aux[k] = (unsigned char)((force ? atoi(force) % N_LAYOUTS : shape[k]) << 6);
         G.box_w = best_w;
         G.box_h = need_h;
         G.plane_elems = G.box_w * G.box_h;  // a box of depth PPS lands as PPS densely packed planes
@@ -598,15 +650,17 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         if (rc) return rc;
     } else {
         for (int k = 0; k < P.n_mats; k++) {
-            int best = 33, best_cost = 1 << 30;
-            for (int pitch = PITCH_MIN; pitch <= PITCH_MAX; pitch++) {
-                const int c = pitch_cost(P.mats[k], pitch);
-                if (c < best_cost) {
-                    best_cost = c;
-                    best = pitch;
+            int best = 33, best_layout = 0, best_cost = 1 << 30;
+            for (int pitch = PITCH_MIN; pitch <= PITCH_MAX; pitch++)
+                for (int layout = 0; layout < N_LAYOUTS; layout++) {
+                    const int c = pitch_cost(P.mats[k], pitch, layout);
+                    if (c < best_cost) {
+                        best_cost = c;
+                        best = pitch;
+                        best_layout = layout;
+                    }
                 }
-            }
-            P.aux[k] = (unsigned char)best;
+            P.aux[k] = (unsigned char)(best | (best_layout << 6));
         }
         G.plane_elems = STAGE;
         G.stage_bytes = PPS * STAGE * 4;
