@@ -236,9 +236,28 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
     vols = [torch.rand(shape, generator=gen, device=f'cuda:{dev}', dtype=torch.float32) for _ in range(batch)]
     outs = [torch.zeros(shape, device=f'cuda:{dev}', dtype=torch.float32) for _ in range(batch)]
 
+    # The batch's volumes are independent: the calls are issued round-robin on `args.streams` CUDA streams (the API is
+    # stream-ordered on torch's current stream), so one volume's small kernels (250 CTAs do not fill 148 SMs x 2-3
+    # resident CTAs) overlap the next volume's.  The timed region starts and ends on the default stream, which the
+    # side streams fork from and join back into every step.
+    main_stream = torch.cuda.current_stream(dev)
+    side = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else []
+
+    def step_on(streams):
+        if not streams:
+            for v, o in zip(vols, outs):
+                vt.transform(v, interpolation=interp, output=o, device=device, **kw)
+            return
+        for s in streams:
+            s.wait_stream(main_stream)
+        for i, (v, o) in enumerate(zip(vols, outs)):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                vt.transform(v, interpolation=interp, output=o, device=device, **kw)
+        for s in streams:
+            main_stream.wait_stream(s)
+
     def step():
-        for v, o in zip(vols, outs):
-            vt.transform(v, interpolation=interp, output=o, device=device, **kw)
+        step_on(side)
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -258,11 +277,16 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
     sec = reduce_max(sec)
     vox_step = batch * n ** 3
     value = world * vox_step * args.steps / sec / 1e9
+    single_stream_value = value
+    if side:
+        sec1 = reduce_max(timed(torch, lambda: step_on([]), args.steps, 2, barrier))
+        single_stream_value = world * vox_step * args.steps / sec1 / 1e9
 
-    # per-kernel durations over the same K steps (CUDA events inside the library, on the launch stream)
+    # per-kernel durations over the same K steps (CUDA events inside the library, on the launch stream), with the
+    # calls on ONE stream so that each kernel is timed alone
     _native.profile_enable(True)
     for _ in range(args.steps):
-        step()
+        step_on([])
     torch.cuda.synchronize()
     prof = _native.profile_read()
     _native.profile_enable(False)
@@ -340,7 +364,8 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
         'config': {'workload': cfg['name'], 'voxels_per_step_per_gpu': vox_step, 'parallelism': f'dp{world}',
                    'l2': 'inputs larger than L2: 8 distinct volumes per step (500 MB in + 500 MB out per GPU)',
                    'call': "voltools_b200.transform(vol, rotation=(0,45,0), rotation_order='rzxz', "
-                           "interpolation='filt_bspline', output=out, device='gpu:X')"},
+                           "interpolation='filt_bspline', output=out, device='gpu:X')",
+                   'cuda_streams': max(1, args.streams), 'single_stream_value': single_stream_value},
         'clocks': {'sm_mhz': clk['sm_mhz'], 'sm_max_mhz': clk['sm_max_mhz'], 'reasons': clk['reasons'],
                    'samples': clk['samples']},
         'e2e': {'value': e2e_value, 'unit': METRIC, 'h2d_bytes_per_step': vox_step * 4, 'd2h_bytes_per_step': vox_step * 4,
@@ -509,6 +534,7 @@ def main():
     ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes', 'sweep', 'zslab', 'project'])
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--streams', type=int, default=2, help="CUDA streams the step's independent volumes are issued on")
     ap.add_argument('--batch', type=int, default=None, help='volumes per step (default 8; smaller only for profiling)')
     args = ap.parse_args()
     cfg = dict(CFG1)
