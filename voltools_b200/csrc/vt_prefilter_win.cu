@@ -274,53 +274,91 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
 constexpr int ZB = 16;  // planes emitted per step
 constexpr int Z_THREADS = 128;
 
-// src may equal dst (in place): no __restrict__ here
-__global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src, float *dst, int D, size_t cols,
-                                                                int z_chunk, int z_begin, int z_end)
+// The sweep is instruction bound (ncu: 83 % issue-active), so a thread takes TWO adjacent columns as a packed pair
+// (V = vt_f2): 64-bit loads and stores and FFMA2 / FMUL2 (two IEEE fp32 operations per lane and instruction) halve
+// the instruction count per voxel.  V = float is the same code for planes with an odd number of columns.
+template <typename V>
+struct ZOps;
+template <>
+struct ZOps<float> {
+    static constexpr int W = 1;
+    static __device__ __forceinline__ float zero() { return 0.0f; }
+    static __device__ __forceinline__ float mulc(float c, float x) { return __fmul_rn(c, x); }
+    static __device__ __forceinline__ float fmac(float c, float x, float y) { return __fmaf_rn(c, x, y); }
+};
+template <>
+struct ZOps<vt_f2> {
+    static constexpr int W = 2;
+    static __device__ __forceinline__ vt_f2 zero() { return 0ull; }
+    static __device__ __forceinline__ vt_f2 mulc(float c, vt_f2 x)
+    {
+        vt_f2 r;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(vt_pk(c, c)), "l"(x));
+        return r;
+    }
+    static __device__ __forceinline__ vt_f2 fmac(float c, vt_f2 x, vt_f2 y) { return vt_fma2(vt_pk(c, c), x, y); }
+};
+template <typename V>
+__device__ __forceinline__ V causal_step_v(V s, V prev)
 {
+    return ZOps<V>::fmac(kPole, prev, ZOps<V>::mulc(kLambda, s));
+}
+template <typename V>
+__device__ __forceinline__ V anticausal_step_v(V next, V c)
+{
+    return ZOps<V>::fmac(kPole, next, ZOps<V>::mulc(kNegPole, c));
+}
+
+// src may equal dst (in place): no __restrict__ here.  `cols` = columns per plane in units of V.
+template <typename V>
+__global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const V *src, V *dst, int D, size_t cols, int z_chunk,
+                                                                int z_begin, int z_end)
+{
+    using O = ZOps<V>;
     const size_t col = (size_t)blockIdx.x * Z_THREADS + threadIdx.x;
     if (col >= cols) return;
     const int zc0 = z_begin + blockIdx.y * z_chunk;  // this CTA emits planes [zc0, zc1)
     const int zc1 = min(zc0 + z_chunk, z_end);
-    const float *s = src + col;
-    float *d = dst + col;
+    const V *s = src + col;
+    V *d = dst + col;
 
-    float cp[K + ZB];  // causal values of planes [zw, zw + K + ZB)
-    float prev;
+    V cp[K + ZB];  // causal values of planes [zw, zw + K + ZB)
+    V prev;
     int zw;            // plane index of cp[0]
     // ---- start-up: fill cp[0..K) ----
     if (zc0 <= K) {
         // the start of the line is within reach: exact start (InitialCausalCoefficient, bspline.h:2-19), then the
         // plain recursion up to the chunk
-        float first[12];  // loaded together (independent), then summed in the reference's order
+        V first[12];  // loaded together (independent), then summed in the reference's order
 #pragma unroll
-        for (int k = 0; k < 12; k++) first[k] = k < D ? s[(size_t)k * cols] : 0.0f;
-        float zn = kPole, sum = first[0];
+        for (int k = 0; k < 12; k++) first[k] = k < D ? s[(size_t)k * cols] : O::zero();
+        float zn = kPole;
+        V sum = first[0];
 #pragma unroll
         for (int k = 0; k < 12; k++) {
-            if (k < D) sum = __fmaf_rn(zn, first[k], sum);
+            if (k < D) sum = O::fmac(zn, first[k], sum);
             zn = __fmul_rn(zn, kPole);
         }
-        prev = __fmul_rn(kLambda, sum);
-        for (int zz = 1; zz < zc0; zz++) prev = causal_step(s[(size_t)zz * cols], prev);
+        prev = O::mulc(kLambda, sum);
+        for (int zz = 1; zz < zc0; zz++) prev = causal_step_v<V>(s[(size_t)zz * cols], prev);
         zw = zc0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int zz = zw + k;
-            if (zz > 0 && zz < D) prev = causal_step(s[(size_t)zz * cols], prev);
+            if (zz > 0 && zz < D) prev = causal_step_v<V>(s[(size_t)zz * cols], prev);
             cp[k] = prev;
         }
     } else {
         // warm-up K planes before the chunk, then the first K planes of the chunk
         const int zs = zc0 - K;  // > 0
-        prev = __fmul_rn(kWarm, s[(size_t)zs * cols]);
+        prev = O::mulc(kWarm, s[(size_t)zs * cols]);
 #pragma unroll
-        for (int k = 1; k < K; k++) prev = causal_step(s[(size_t)(zs + k) * cols], prev);
+        for (int k = 1; k < K; k++) prev = causal_step_v<V>(s[(size_t)(zs + k) * cols], prev);
         zw = zc0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int zz = zw + k;
-            if (zz < D) prev = causal_step(s[(size_t)zz * cols], prev);
+            if (zz < D) prev = causal_step_v<V>(s[(size_t)zz * cols], prev);
             cp[k] = prev;
         }
     }
@@ -330,17 +368,17 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
     // (2 x ZB loads outstanding per thread).  Steps whose whole window lies inside the volume and the chunk take a
     // guard-free path with one IMAD.WIDE per address (32-bit plane stride).
     const unsigned stride = (unsigned)cols;  // host: cols < 2^31
-    const float *sp = s + (size_t)(zw + K) * cols;  // plane zw + K of this column
-    float *dp = d + (size_t)zw * cols;              // plane zw
-    float raw[ZB];
+    const V *sp = s + (size_t)(zw + K) * cols;  // plane zw + K of this column
+    V *dp = d + (size_t)zw * cols;              // plane zw
+    V raw[ZB];
 #pragma unroll
-    for (int k = 0; k < ZB; k++) raw[k] = zw + K + k < D ? sp[(size_t)k * stride] : 0.0f;
+    for (int k = 0; k < ZB; k++) raw[k] = zw + K + k < D ? sp[(size_t)k * stride] : O::zero();
     for (; zw < zc1; zw += ZB) {
         sp += (size_t)ZB * stride;
         if (zw + K + ZB <= D && zw + ZB <= zc1) {  // uniform
 #pragma unroll
             for (int k = 0; k < ZB; k++) {
-                prev = causal_step(raw[k], prev);
+                prev = causal_step_v<V>(raw[k], prev);
                 cp[K + k] = prev;
             }
             if (zw + K + 2 * ZB <= D) {
@@ -348,12 +386,12 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
                 for (int k = 0; k < ZB; k++) raw[k] = sp[(size_t)k * stride];
             } else if (zw + ZB < zc1) {
 #pragma unroll
-                for (int k = 0; k < ZB; k++) raw[k] = zw + ZB + K + k < D ? sp[(size_t)k * stride] : 0.0f;
+                for (int k = 0; k < ZB; k++) raw[k] = zw + ZB + K + k < D ? sp[(size_t)k * stride] : O::zero();
             }
-            float c = __fmul_rn(kAnti, cp[K + ZB - 1]);
+            V c = O::mulc(kAnti, cp[K + ZB - 1]);
 #pragma unroll
             for (int k = K + ZB - 2; k >= 0; k--) {
-                c = anticausal_step(c, cp[k]);
+                c = anticausal_step_v<V>(c, cp[k]);
                 if (k < ZB) dp[(size_t)k * stride] = c;
             }
         } else {
@@ -361,21 +399,21 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const float *src
 #pragma unroll
             for (int k = 0; k < ZB; k++) {
                 const int zz = zw + K + k;
-                if (zz < D) prev = causal_step(raw[k], prev);
+                if (zz < D) prev = causal_step_v<V>(raw[k], prev);
                 cp[K + k] = prev;
             }
             if (zw + ZB < zc1) {
 #pragma unroll
-                for (int k = 0; k < ZB; k++) raw[k] = zw + ZB + K + k < D ? sp[(size_t)k * stride] : 0.0f;
+                for (int k = 0; k < ZB; k++) raw[k] = zw + ZB + K + k < D ? sp[(size_t)k * stride] : O::zero();
             }
             // anticausal from the last available plane of the window back to zw
             const int last = min(zw + K + ZB, D) - 1;  // plane index where the recursion (re)starts
-            float c = 0.0f;
+            V c = O::zero();
 #pragma unroll
             for (int k = K + ZB - 1; k >= 0; k--) {
                 const int zz = zw + k;
-                if (zz == last) c = __fmul_rn(kAnti, cp[k]);
-                else if (zz < last) c = anticausal_step(c, cp[k]);
+                if (zz == last) c = O::mulc(kAnti, cp[k]);
+                else if (zz < last) c = anticausal_step_v<V>(c, cp[k]);
                 if (k < ZB && zz < zc1) dp[(size_t)k * stride] = c;
             }
         }
@@ -438,7 +476,11 @@ int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, 
     // planes the kernel may read: everything up to K past the range (a pipelined caller has not produced the
     // rest of d_src yet); the anticausal restart at that artificial end is the usual |z|^12-accurate stand-in
     const int d_avail = z1 + K < d0 ? z1 + K : d0;
-    const size_t bx = (cols + Z_THREADS - 1) / Z_THREADS;
+    // two columns per thread (packed pairs) when the planes allow 8-byte accesses
+    static const bool no_pack = getenv("VT_Z_SCALAR") != nullptr;  // A/B knob
+    const bool pack = !no_pack && cols % 2 == 0 && ((uintptr_t)d_src % 8) == 0 && ((uintptr_t)d_dst % 8) == 0;
+    const size_t vcols = pack ? cols / 2 : cols;
+    const size_t bx = (vcols + Z_THREADS - 1) / Z_THREADS;
     if (bx > 0x7fffffffull || cols > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
     const int nz = z1 - z0;
     if (d_src == d_dst) {
@@ -446,7 +488,7 @@ int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, 
         chunks = 1;
     } else if (chunks <= 0) {
         // aim at >= ~300 000 threads, chunks of at least 64 planes (each pays 2*K planes of warm-up / look-ahead)
-        chunks = (int)((300000 + cols - 1) / cols);
+        chunks = (int)((300000 + vcols - 1) / vcols);
         const int max_chunks = nz / 64 > 0 ? nz / 64 : 1;
         if (chunks > max_chunks) chunks = max_chunks;
         if (const char *e = getenv("VT_Z_CHUNKS")) chunks = atoi(e) > 0 ? atoi(e) : chunks;  // tuning knob
@@ -456,7 +498,12 @@ int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, 
     if (chunks > 65535) return VT_ERR_UNSUPPORTED;
     {
         VtProf prof(VT_K_PREFILTER_Z, st);
-        prefilter_z_kernel<<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>(d_src, d_dst, d_avail, cols, z_chunk, z0, z1);
+        if (pack)
+            prefilter_z_kernel<vt_f2><<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>((const vt_f2 *)d_src, (vt_f2 *)d_dst,
+                                                                                     d_avail, vcols, z_chunk, z0, z1);
+        else
+            prefilter_z_kernel<float><<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>(d_src, d_dst, d_avail, cols, z_chunk,
+                                                                                     z0, z1);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
