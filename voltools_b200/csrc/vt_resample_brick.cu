@@ -144,7 +144,8 @@ __device__ __forceinline__ float cubic_simple_brick(const Brick &b, float x, flo
     return r;
 }
 
-template <int INTERP, int RULE, bool OOB_ZERO>
+// MODE: 0 = out-of-bounds voxels are skipped, 1 = written as zero, 2 = rotate-and-project (voxels are summed along axis 0)
+template <int INTERP, int RULE, int MODE>
 __global__ void __launch_bounds__(NT, 3)
     vt_brick_kernel(const __grid_constant__ VtResampleParams P, const __grid_constant__ VtBrickStaging G)
 {
@@ -198,7 +199,8 @@ __global__ void __launch_bounds__(NT, 3)
     __syncthreads();  // the barrier is initialised before anyone polls it
     vt_mbar_wait(bar, 0);
     if (!live) return;
-    const bool project = (P.flags & VT_INTERNAL_PROJECT) != 0;  // sum along axis 0 instead of storing
+    constexpr bool project = MODE == 2;  // sum along axis 0 instead of storing
+    constexpr bool OOB_ZERO = MODE == 1;
     float acc = 0.0f;
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
@@ -331,16 +333,19 @@ int launch2(const VtResampleParams &P, cudaStream_t st)
     const size_t smem = 128 + (size_t)G.bw * G.bh * G.bd * 4;
     static bool attr_set = false;
     if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      128 + MAX_BRICK_BYTES));
-        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     128 + MAX_BRICK_BYTES));
+        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      128 + MAX_BRICK_BYTES));
         attr_set = true;
     }
     {
         VtProf prof(VT_K_BRICK_LINEAR + INTERP, st);
-        if (P.flags & VT_OOB_ZERO) vt_brick_kernel<INTERP, RULE, true><<<grid, NT, smem, st>>>(P, G);
-        else vt_brick_kernel<INTERP, RULE, false><<<grid, NT, smem, st>>>(P, G);
+        if (P.flags & VT_INTERNAL_PROJECT) vt_brick_kernel<INTERP, RULE, 2><<<grid, NT, smem, st>>>(P, G);
+        else if (P.flags & VT_OOB_ZERO) vt_brick_kernel<INTERP, RULE, 1><<<grid, NT, smem, st>>>(P, G);
+        else vt_brick_kernel<INTERP, RULE, 0><<<grid, NT, smem, st>>>(P, G);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());

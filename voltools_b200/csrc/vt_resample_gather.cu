@@ -144,7 +144,8 @@ __device__ __forceinline__ float cubic_simple(const SrcView &s, float x, float y
     return result;
 }
 
-template <int INTERP, int RULE, bool OOB_ZERO>
+// MODE: 0 = out-of-bounds voxels are skipped, 1 = written as zero, 2 = rotate-and-project (voxels are summed along axis 0)
+template <int INTERP, int RULE, int MODE>
 __global__ void __launch_bounds__(TX *TY) vt_gather_kernel(const __grid_constant__ VtResampleParams P)
 {
     const int nz = P.z_end - P.z_begin;
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(TX *TY) vt_gather_kernel(const __grid_constant
     const float fa1 = (float)a1, fa2 = (float)a2;
     const int zlo = P.z_begin + zt * TZ;
     const int zhi = min(zlo + TZ, P.z_end);
-    const bool project = (P.flags & VT_INTERNAL_PROJECT) != 0;  // sum along axis 0 instead of storing
+    constexpr bool project = MODE == 2;  // sum along axis 0 instead of storing
+    constexpr bool OOB_ZERO = MODE == 1;
     float acc = 0.0f;
     for (int a0 = zlo; a0 < zhi; a0++) {
         const float fa0 = (float)a0;
@@ -194,8 +196,9 @@ int launch2(const VtResampleParams &P, cudaStream_t st)
     if (grid.y > 65535u || grid.z > 65535u) return VT_ERR_UNSUPPORTED;
     {
         VtProf prof(VT_K_GATHER_LINEAR + INTERP, st);
-        if (P.flags & VT_OOB_ZERO) vt_gather_kernel<INTERP, RULE, true><<<grid, block, 0, st>>>(P);
-        else vt_gather_kernel<INTERP, RULE, false><<<grid, block, 0, st>>>(P);
+        if (P.flags & VT_INTERNAL_PROJECT) vt_gather_kernel<INTERP, RULE, 2><<<grid, block, 0, st>>>(P);
+        else if (P.flags & VT_OOB_ZERO) vt_gather_kernel<INTERP, RULE, 1><<<grid, block, 0, st>>>(P);
+        else vt_gather_kernel<INTERP, RULE, 0><<<grid, block, 0, st>>>(P);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());

@@ -20,6 +20,7 @@
 // cubicTex3DSimple (voltools/kernels/helper_interpolation.h:3-68) for this class of matrices.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -520,16 +521,37 @@ bool slice_ok(const VtResampleParams &P, int interp)
     return true;
 }
 
-// Shared-memory row pitch: the warp's 32 columns (2 tile rows x 16) read the same tap of their own footprint
-// position; lanes land on bank (y*pitch + x) mod 32.  The host picks the pitch (cp.async variant: per matrix; TMA
-// variant: the box width) with the fewest bank conflicts over a few sample warps.
-// bank conflicts of one warp's first tap for a given shared-memory pitch (see choose_pitch)
-constexpr int PITCH_SAMPLES = 6;
-int pitch_cost(const VtMat &M, int pitch, int layout)
+// Shared-memory row pitch and warp shape.  A warp's 32 columns read the same tap of their own footprint position; lanes
+// land on bank (y*pitch + x) mod 32.  The host simulates the first tap of a few warps (every other tap shifts all lanes
+// by the same amount) and feeds the average number of wavefronts per load into a cost model fitted to measurements at
+// 512^3 over (angle, pitch, shape) (tools/slice_grid_probe.py, profiles/r01k_slice_grid.log), in SM cycles per voxel:
+//      cubic_simple   0.30 + 0.45 * wavefronts          (shared-memory bound: 16 loads per voxel and plane)
+//      cubic_tex      max(1.13, that)                   (1.13 = its instruction-issue floor)
+//      linear         max(0.40, 0.19 + 0.0045 * pitch + 0.06 * wavefronts)   (L2 -> SM traffic grows with the box width)
+//   + 0.02 (4 x 8) / 0.12 (8 x 4): a warp's stores cover 4 or 8 rows instead of 2.
+constexpr int PITCH_SAMPLES = 8;
+float pitch_conflicts(const VtMat &M, int pitch, int layout)
 {
+    // small memo: a sweep comes back with the same matrices launch after launch
+    struct Entry {
+        float k[6];
+        int pitch, layout;
+        float value;
+    };
+    static thread_local Entry memo[256];
+    const float key[6] = {M.r[1][1], M.r[1][2], M.r[1][3], M.r[2][1], M.r[2][2], M.r[2][3]};
+    unsigned h = 2166136261u;
+    for (int i = 0; i < 6; i++) {
+        unsigned u;
+        memcpy(&u, &key[i], 4);
+        h = (h ^ u) * 16777619u;
+    }
+    h = (h ^ (unsigned)(pitch * 4 + layout)) * 16777619u;
+    Entry &e = memo[(h >> 8) & 255];
+    if (e.pitch == pitch && e.layout == layout && memcmp(e.k, key, sizeof key) == 0 && e.value > 0.0f) return e.value;
     int cost = 0;
     for (int sample = 0; sample < PITCH_SAMPLES; sample++) {
-        // tiles spread over the image, different warps of the CTA
+        // tiles spread over the image (different sub-texel phases), a different warp of the CTA in each
         const int a1_0 = 16 * (1 + 3 * sample), a2_0 = 16 * (2 + 5 * sample);
         unsigned char count[32] = {0};
         int first_addr[32];
@@ -548,7 +570,20 @@ int pitch_cost(const VtMat &M, int pitch, int layout)
         }
         cost += worst;
     }
-    return cost;
+    memcpy(e.k, key, sizeof key);
+    e.pitch = pitch;
+    e.layout = layout;
+    e.value = (float)cost / (float)PITCH_SAMPLES;
+    return e.value;
+}
+template <int INTERP>
+float pitch_cost(const VtMat &M, int pitch, int layout)
+{
+    const float wf = pitch_conflicts(M, pitch, layout);
+    const float pen = layout == 0 ? 0.0f : (layout == 1 ? 0.02f : 0.12f);
+    if (INTERP == VT_LINEAR) return fmaxf(0.40f, 0.19f + 0.0045f * (float)pitch + 0.06f * wf) + pen;
+    const float lds = 0.30f + 0.45f * wf;
+    return (INTERP == VT_CUBIC_TEX ? fmaxf(1.13f, lds) : lds) + pen;
 }
 
 // TMA staging is possible when the source rows/planes are 16-byte aligned
@@ -609,26 +644,22 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         const int need_h = min(BMAX, (int)floorf(ext_y + 0.1f) + 6), need_w = min(BMAX, (int)floorf(ext_x + 0.1f) + 6);
         // + 3: the box start is rounded down to a multiple of 4 texels (16-byte aligned start address)
         // the box width is the shared-memory pitch of every matrix of the launch; each matrix then takes its best shape
-        // Cost of a width, in SM cycles per output voxel and plane: shared-memory wavefronts of the taps (one per clock)
-        // + the staged footprint through the L2 -> SM path (~64 B/clk; the linear kernel sits at 74 % of L2 throughput,
-        // so a wider box must buy more than it costs there).
-        constexpr int TAPS = INTERP == VT_LINEAR ? 4 : 16;
         int best_w = (need_w + 3 + 3) / 4 * 4;
         float best_cost = 1e30f;
         unsigned char shape[VT_MAX_BATCH];
-        for (int w = (need_w + 3 + 3) / 4 * 4; w <= need_w + 3 + 12 && w <= PITCH_MAX; w += 4) {
-            float total = (float)P.n_mats * (float)(w * need_h) * (4.0f / 64.0f / (float)NT);
+        for (int w = (need_w + 3 + 3) / 4 * 4; w <= PITCH_MAX; w += 4) {
+            float total = 0.0f;
             unsigned char sh[VT_MAX_BATCH];
             for (int k = 0; k < P.n_mats; k++) {
-                int bc = 1 << 30;
+                float bc = 1e30f;
                 for (int layout = 0; layout < N_LAYOUTS; layout++) {
-                    const int c = pitch_cost(P.mats[k], w, layout);
+                    const float c = pitch_cost<INTERP>(P.mats[k], w, layout);
                     if (c < bc) {
                         bc = c;
                         sh[k] = (unsigned char)layout;
                     }
                 }
-                total += (float)(TAPS * bc) / (float)(PITCH_SAMPLES * 32);
+                total += bc;
             }
             if (total < best_cost) {
                 best_cost = total;
@@ -636,9 +667,14 @@ int launch2(VtResampleParams &P, cudaStream_t st)
                 memcpy(shape, sh, sizeof sh);
             }
         }
-        const char *force = getenv("VT_SLICE_LAYOUT");  // tuning knob
+        const char *force = getenv("VT_SLICE_LAYOUT");  // tuning knobs
         for (int k = 0; k < P.n_mats; k++)
             P.aux[k] = (unsigned char)((force ? atoi(force) % N_LAYOUTS : shape[k]) << 6);
+        if (const char *e = getenv("VT_SLICE_W"))
+            if (atoi(e) >= (need_w + 3 + 3) / 4 * 4 && atoi(e) <= PITCH_MAX && atoi(e) % 4 == 0) best_w = atoi(e);
+        if (getenv("VT_SLICE_DEBUG"))
+            fprintf(stderr, "slice interp %d: need %d x %d, box_w %d, shape[0] %d, cost %.3f\n", INTERP, need_w, need_h, best_w,
+                    (int)(P.aux[0] >> 6), best_cost);
         G.box_w = best_w;
         G.box_h = need_h;
         G.plane_elems = G.box_w * G.box_h;  // a box of depth PPS lands as PPS densely packed planes
@@ -650,10 +686,13 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         if (rc) return rc;
     } else {
         for (int k = 0; k < P.n_mats; k++) {
-            int best = 33, best_layout = 0, best_cost = 1 << 30;
+            int best = 33, best_layout = 0;
+            float best_cost = 1e30f;
             for (int pitch = PITCH_MIN; pitch <= PITCH_MAX; pitch++)
                 for (int layout = 0; layout < N_LAYOUTS; layout++) {
-                    const int c = pitch_cost(P.mats[k], pitch, layout);
+                    // (per-element cp.async staging: the pitch does not change the staged traffic; the fit is for TMA
+                    // but the ordering by wavefronts is what matters here)
+                    const float c = pitch_cost<INTERP>(P.mats[k], pitch, layout);
                     if (c < best_cost) {
                         best_cost = c;
                         best = pitch;

@@ -38,7 +38,8 @@ constexpr int VPT = TZ * TY * TX / NT;  // 4
 // along axis 0.  Measured on B200 at 512^3 (tools/perf_probe.py): 8 x 4, 2 x 16 columns per warp and VPT = 2 / 8
 // all land within 4 % of this one (340 Gvox/s linear, 66 Gvox/s cubic_tex: the unit's fetch rate, ~1.2 and ~1.8
 // float32 trilinear fetches per clock per SM, is the limit, not the mapping); one voxel per thread is 25 % slower.
-template <int INTERP, bool OOB_ZERO>
+// MODE: 0 = out-of-bounds voxels are skipped, 1 = written as zero, 2 = rotate-and-project (voxels are summed along axis 0)
+template <int INTERP, int MODE>
 __global__ void __launch_bounds__(NT) vt_tex_kernel(const __grid_constant__ VtResampleParams P, cudaTextureObject_t tex)
 {
     const int tid = threadIdx.x;
@@ -58,7 +59,8 @@ __global__ void __launch_bounds__(NT) vt_tex_kernel(const __grid_constant__ VtRe
     const float fa1 = (float)a1, fa2 = (float)a2;
     float *__restrict__ dst = P.dst + (size_t)mat * P.dst_batch_stride + ((size_t)a1 * P.o2 + a2);
     const size_t oplane = (size_t)P.o1 * P.o2;
-    const bool project = (P.flags & VT_INTERNAL_PROJECT) != 0;  // sum along axis 0 instead of storing
+    constexpr bool project = MODE == 2;  // sum along axis 0 instead of storing
+    constexpr bool OOB_ZERO = MODE == 1;
     float acc = 0.0f;
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
@@ -109,8 +111,9 @@ int launch(const VtResampleParams &P, cudaTextureObject_t tex, cudaStream_t st)
     if (grid.y > 65535u || grid.z > 65535u) return VT_ERR_UNSUPPORTED;
     {
         VtProf prof(INTERP == VT_LINEAR ? VT_K_TEX_LINEAR : VT_K_TEX_CUBIC, st);
-        if (P.flags & VT_OOB_ZERO) vt_tex_kernel<INTERP, true><<<grid, NT, 0, st>>>(P, tex);
-        else vt_tex_kernel<INTERP, false><<<grid, NT, 0, st>>>(P, tex);
+        if (P.flags & VT_INTERNAL_PROJECT) vt_tex_kernel<INTERP, 2><<<grid, NT, 0, st>>>(P, tex);
+        else if (P.flags & VT_OOB_ZERO) vt_tex_kernel<INTERP, 1><<<grid, NT, 0, st>>>(P, tex);
+        else vt_tex_kernel<INTERP, 0><<<grid, NT, 0, st>>>(P, tex);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
