@@ -240,7 +240,6 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
     # stream-ordered on torch's current stream), so one volume's small kernels (250 CTAs do not fill 148 SMs x 2-3
     # resident CTAs) overlap the next volume's.  The timed region starts and ends on the default stream, which the
     # side streams fork from and join back into every step.
-    main_stream = torch.cuda.current_stream(dev)
     side = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else []
 
     def step_on(streams):
@@ -248,6 +247,7 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
             for v, o in zip(vols, outs):
                 vt.transform(v, interpolation=interp, output=o, device=device, **kw)
             return
+        main_stream = torch.cuda.current_stream(dev)  # the capture stream while a CUDA graph is being recorded
         for s in streams:
             s.wait_stream(main_stream)
         for i, (v, o) in enumerate(zip(vols, outs)):
@@ -256,10 +256,37 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
         for s in streams:
             main_stream.wait_stream(s)
 
-    def step():
+    def step_eager():
         step_on(side)
 
     for _ in range(max(3, args.warmup)):
+        step_eager()
+    torch.cuda.synchronize()
+    # A step is 24 kernels of 30-80 us behind 8 Python calls: the host barely keeps ahead of the GPU (and falls behind
+    # with several ranks sharing the host's cores).  The same calls are therefore recorded once into a CUDA graph --
+    # same kernels, same streams, same buffers -- and the timed steps replay it.  --no-graph times the eager calls.
+    graph, launches_per_step = None, None
+    if not args.no_graph:
+        try:
+            l_cap = _native.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step_eager()
+            launches_per_step = _native.launch_count() - l_cap
+            g.replay()
+            torch.cuda.synchronize()
+            graph = g
+        except Exception as e:  # capture not possible here: eager calls
+            print(f'bench: CUDA graph capture failed ({e!r}); timing eager calls', file=sys.stderr)
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step_eager()
+
+    for _ in range(3):
         step()
     torch.cuda.synchronize()
     uuid = str(getattr(torch.cuda.get_device_properties(dev), 'uuid', dev))
@@ -272,7 +299,7 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
         torch.cuda.synchronize()
     l0 = _native.launch_count()
     sec = timed(torch, step, args.steps, 0, barrier)
-    launches = _native.launch_count() - l0
+    launches = launches_per_step * args.steps if graph is not None else _native.launch_count() - l0
     clk = clocks.stop()
     sec = reduce_max(sec)
     vox_step = batch * n ** 3
@@ -281,6 +308,10 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
     if side:
         sec1 = reduce_max(timed(torch, lambda: step_on([]), args.steps, 2, barrier))
         single_stream_value = world * vox_step * args.steps / sec1 / 1e9
+    eager_value = value
+    if graph is not None:
+        sec2 = reduce_max(timed(torch, step_eager, args.steps, 2, barrier))
+        eager_value = world * vox_step * args.steps / sec2 / 1e9
 
     # per-kernel durations over the same K steps (CUDA events inside the library, on the launch stream), with the
     # calls on ONE stream so that each kernel is timed alone
@@ -365,7 +396,8 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
                    'l2': 'inputs larger than L2: 8 distinct volumes per step (500 MB in + 500 MB out per GPU)',
                    'call': "voltools_b200.transform(vol, rotation=(0,45,0), rotation_order='rzxz', "
                            "interpolation='filt_bspline', output=out, device='gpu:X')",
-                   'cuda_streams': max(1, args.streams), 'single_stream_value': single_stream_value},
+                   'cuda_streams': max(1, args.streams), 'cuda_graph': graph is not None,
+                   'eager_value': eager_value, 'single_stream_eager_value': single_stream_value},
         'clocks': {'sm_mhz': clk['sm_mhz'], 'sm_max_mhz': clk['sm_max_mhz'], 'reasons': clk['reasons'],
                    'samples': clk['samples']},
         'e2e': {'value': e2e_value, 'unit': METRIC, 'h2d_bytes_per_step': vox_step * 4, 'd2h_bytes_per_step': vox_step * 4,
@@ -534,6 +566,7 @@ def main():
     ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes', 'sweep', 'zslab', 'project'])
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time eager calls instead of replaying a captured CUDA graph')
     ap.add_argument('--streams', type=int, default=2, help="CUDA streams the step's independent volumes are issued on")
     ap.add_argument('--batch', type=int, default=None, help='volumes per step (default 8; smaller only for profiling)')
     args = ap.parse_args()
