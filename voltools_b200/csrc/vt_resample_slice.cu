@@ -100,14 +100,6 @@ __host__ __device__ __forceinline__ float inplane_coord(const float *row, float 
 template <int INTERP>
 struct Taps;
 
-// Tap offsets are kept in BYTES relative to the start of a staged plane, and a stage's planes are addressed as
-// (uniform base) + (per-thread byte offset) + immediate: the loads then need no per-stage address arithmetic
-// (LDS [R + UR + imm]); with element offsets every address cost an LEA (and the second plane a MOV + LEA more).
-__device__ __forceinline__ float tap(const char *plane, int byte_off) { return *(const float *)(plane + byte_off); }
-// keeps a finished byte offset in its register: without it the compiler carries offset/4 instead and rescales it
-// (LEA) at every use
-__device__ __forceinline__ void pin(int &v) { asm volatile("" : "+r"(v)); }
-
 // ---- linear: one plane, 4 taps with the texture unit's integer weights (c = 0 -> S = 256) ----------------
 template <>
 struct Taps<VT_LINEAR> {
@@ -115,7 +107,7 @@ struct Taps<VT_LINEAR> {
     static constexpr int PLANES_BEFORE = 0, PLANES_AFTER = 0;
     static constexpr int PPS = 4, NSTAGE = 3;
     float w[4];
-    int r0, r1;  // byte offsets of the two tap rows within a staged plane
+    int r0, r1;  // element offsets of the two tap rows within a stage
     template <int RULE>
     __device__ __forceinline__ void init(float p1, float p2, int ylo, int xlo, int pitch)
     {
@@ -137,22 +129,20 @@ struct Taps<VT_LINEAR> {
             w[2] = (1.0f - ax) * ay;
             w[3] = ax * ay;
         }
-        r0 = 4 * ((by - ylo) * pitch + (bx - xlo));
-        r1 = r0 + 4 * pitch;
-        pin(r0);
-        pin(r1);
+        r0 = (by - ylo) * pitch + (bx - xlo);
+        r1 = r0 + pitch;
     }
-    // per-plane sums of the stage's four planes (plane p starts at s + p*pb bytes); planes are paired in FFMA2s
-    __device__ __forceinline__ void planes(const char *s, int pb, float (&out)[PPS]) const
+    // per-plane sums of the stage's four planes (plane p starts at s + p*pe); planes are paired in FFMA2s
+    __device__ __forceinline__ void planes(const float *s, int pe, float (&out)[PPS]) const
     {
-        const char *s1 = s + pb, *s2 = s1 + pb, *s3 = s2 + pb;
+        const float *s1 = s + pe, *s2 = s1 + pe, *s3 = s2 + pe;
         vt_f2 a01 = 0ull, a23 = 0ull;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int o = (k < 2 ? r0 : r1) + 4 * (k & 1);
+            const int o = (k < 2 ? r0 : r1) + (k & 1);
             const vt_f2 ww = vt_pk(w[k], w[k]);
-            a01 = vt_fma2(vt_pk(tap(s, o), tap(s1, o)), ww, a01);
-            a23 = vt_fma2(vt_pk(tap(s2, o), tap(s3, o)), ww, a23);
+            a01 = vt_fma2(vt_pk(s[o], s1[o]), ww, a01);
+            a23 = vt_fma2(vt_pk(s2[o], s3[o]), ww, a23);
         }
         vt_unpk(a01, out[0], out[1]);
         vt_unpk(a23, out[2], out[3]);
@@ -181,25 +171,23 @@ struct Taps<VT_CUBIC_SIMPLE> {
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++) w[j * 4 + i] = __fmul_rn(wx[i], wy[j]);
-        row[0] = 4 * (((int)fy0 - 1 - ylo) * pitch + ((int)fx0 - 1 - xlo));  // bytes
+        row[0] = ((int)fy0 - 1 - ylo) * pitch + ((int)fx0 - 1 - xlo);
 #pragma unroll
-        for (int j = 1; j < 4; j++) row[j] = row[j - 1] + 4 * pitch;
-#pragma unroll
-        for (int j = 0; j < 4; j++) pin(row[j]);
+        for (int j = 1; j < 4; j++) row[j] = row[j - 1] + pitch;
         wz0 = vt_bspline(-1.0f);  // fraction along axis 0 is exactly 0
         wz1 = vt_bspline(0.0f);
         wz2 = vt_bspline(1.0f);
     }
     // in-plane sums of the stage's two planes, one FFMA2 per tap: {plane q, plane q+1} x {w, w}
-    __device__ __forceinline__ void planes(const char *s, int pb, float (&out)[PPS]) const
+    __device__ __forceinline__ void planes(const float *s, int pe, float (&out)[PPS]) const
     {
-        const char *s1 = s + pb;
+        const float *s1 = s + pe;
         vt_f2 acc = 0ull;
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                acc = vt_fma2(vt_pk(tap(s, row[j] + 4 * i), tap(s1, row[j] + 4 * i)), vt_pk(w[j * 4 + i], w[j * 4 + i]), acc);
+                acc = vt_fma2(vt_pk(s[row[j] + i], s1[row[j] + i]), vt_pk(w[j * 4 + i], w[j * 4 + i]), acc);
         vt_unpk(acc, out[0], out[1]);
     }
 };
@@ -214,7 +202,7 @@ struct Taps<VT_CUBIC_TEX> {
     static constexpr int PLANES_BEFORE = 1, PLANES_AFTER = 1;
     static constexpr int PPS = 2, NSTAGE = 4;
     float wa[16], wb[16], wc[16];
-    int adr[8];  // byte offsets of taps (row j, x pair k): adr[j*2+k], the pair is (adr, adr+4)
+    int adr[8];  // element offsets of taps (row j, x pair k): adr[j*2+k], the pair is (adr, adr+1)
     template <int RULE>
     __device__ __forceinline__ void init(float p1, float p2, int ylo, int xlo, int pitch)
     {
@@ -285,24 +273,22 @@ struct Taps<VT_CUBIC_TEX> {
         for (int j = 0; j < 2; j++)
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                adr[(2 * j) * 2 + k] = 4 * ((by[j] - ylo) * pitch + (bx[k] - xlo));
-                adr[(2 * j + 1) * 2 + k] = adr[(2 * j) * 2 + k] + 4 * pitch;
+                adr[(2 * j) * 2 + k] = (by[j] - ylo) * pitch + (bx[k] - xlo);
+                adr[(2 * j + 1) * 2 + k] = adr[(2 * j) * 2 + k] + pitch;
             }
-#pragma unroll
-        for (int j = 0; j < 8; j++) pin(adr[j]);
     }
     // A-, B- and C-weighted sums of the stage's two planes: per tap {wa, wb} x {t, t} for each plane (the scalar
     // texel is FFMA2's broadcast operand) and {t0, t1} x {wc, wc}: 3 FFMA2 instead of 6 FFMA
-    __device__ __forceinline__ void planes3(const char *s, int pb, float (&qa)[PPS], float (&qb)[PPS], float (&qc)[PPS]) const
+    __device__ __forceinline__ void planes3(const float *s, int pe, float (&qa)[PPS], float (&qb)[PPS], float (&qc)[PPS]) const
     {
-        const char *s1 = s + pb;
+        const float *s1 = s + pe;
         vt_f2 ab0 = 0ull, ab1 = 0ull, c01 = 0ull;
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int o = adr[j * 2 + (i >> 1)] + 4 * (i & 1);
-                const float t0 = tap(s, o), t1 = tap(s1, o);
+                const int o = adr[j * 2 + (i >> 1)] + (i & 1);
+                const float t0 = s[o], t1 = s1[o];
                 const vt_f2 wab = vt_pk(wa[j * 4 + i], wb[j * 4 + i]);
                 ab0 = vt_fma2(wab, vt_pk(t0, t0), ab0);
                 ab1 = vt_fma2(wab, vt_pk(t1, t1), ab1);
@@ -463,17 +449,16 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
         else cp_async_wait<NSTAGE - 2>();
         __syncthreads();  // stage `cur` has landed for every thread; everyone is done with the previous stage
         issue(q + (NSTAGE - 1) * PPS, srcf, fill);  // refills the stage the previous planes lived in
-        const char *s = (const char *)ring + cur * stage_bytes;
-        const int pb = 4 * pe;
+        const float *s = (const float *)(ring + cur * stage_bytes);
         float r[PPS];
 #pragma unroll
         for (int p = 0; p < PPS; p++) r[p] = 0.0f;
         if (inplane) {
             if constexpr (INTERP == VT_LINEAR) {
-                taps.planes(s, pb, r);
+                taps.planes(s, pe, r);
             } else if constexpr (INTERP == VT_CUBIC_SIMPLE) {
                 float pq[PPS];
-                taps.planes(s, pb, pq);
+                taps.planes(s, pe, pq);
 #pragma unroll
                 for (int p = 0; p < PPS; p++) {
                     // the reference accumulates kz = -1, 0, 1 in that order (helper_interpolation.h:51)
@@ -483,7 +468,7 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
                 }
             } else {
                 float qa[PPS], qb[PPS], qc[PPS];
-                taps.planes3(s, pb, qa, qb, qc);
+                taps.planes3(s, pe, qa, qb, qc);
 #pragma unroll
                 for (int p = 0; p < PPS; p++) {
                     r[p] = (s3 + s1) + qc[p];  // s3 = A-sum of plane q-2, s1 = B-sum of plane q-1
@@ -845,21 +830,19 @@ __global__ void __launch_bounds__(NT)
     if (!(p2 < 0 || p1 < 0 || p2 >= (float)P.s2 || p1 >= (float)P.s1)) {
         T taps;
         taps.template init<RULE>(p1, p2, -PS_PAD, -PS_PAD, pitch);
-        const char *sb = (const char *)sums;
-        const int pb = 4 * pe;
         if constexpr (INTERP == VT_LINEAR) {
             float o[T::PPS];
-            taps.planes(sb, pb, o);
+            taps.planes(sums, pe, o);
             r = o[0];
         } else if constexpr (INTERP == VT_CUBIC_SIMPLE) {
             float ab[T::PPS], bc[T::PPS];
-            taps.planes(sb, pb, ab);
-            taps.planes(sb + pb, pb, bc);
+            taps.planes(sums, pe, ab);
+            taps.planes(sums + pe, pe, bc);
             r = fmaf(taps.wz2, bc[1], fmaf(taps.wz1, ab[1], __fmul_rn(taps.wz0, ab[0])));
         } else {
             float qa[T::PPS], qb[T::PPS], qc[T::PPS], ra[T::PPS], rb[T::PPS], rc[T::PPS];
-            taps.planes3(sb, pb, qa, qb, qc);
-            taps.planes3(sb + pb, pb, ra, rb, rc);
+            taps.planes3(sums, pe, qa, qb, qc);
+            taps.planes3(sums + pe, pe, ra, rb, rc);
             r = (qa[0] + qb[1]) + rc[1];
         }
     }
