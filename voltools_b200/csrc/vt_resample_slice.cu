@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
     using T = Taps<INTERP>;
     constexpr int PPS = T::PPS, NSTAGE = T::NSTAGE;
     static_assert(NSTAGE <= MAX_NSTAGE, "mbarrier block holds MAX_NSTAGE barriers");
+    static_assert(NSTAGE == 3 || NSTAGE == 4, "the ring loop is unrolled for 3 or 4 stages");
     const int tid = threadIdx.x;
     const int ntx = (P.o2 + TS - 1) / TS;
     const int tile_y = blockIdx.x / ntx, tile_x = blockIdx.x - tile_y * ntx;
@@ -330,8 +331,14 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
     const VtMat &M = P.mats[mat];
     const int pitch = TMA ? G.box_w : (int)(P.aux[mat] & 63);
     const int layout = (int)(P.aux[mat] >> 6);
-    const unsigned stage_bytes = G.stage_bytes;
-    const int pe = G.plane_elems;
+    // Cubic modes: planes and ring stages sit at COMPILE-TIME strides (STAGE floats per plane) and the ring loop is
+    // unrolled over the stages, so every tap load is LDS [per-thread register + immediate]: no address arithmetic per
+    // stage (with run-time strides each stage cost ~24 LEA / MOV instructions next to its 48 FFMA2 + 32 LDS, and
+    // cubic_tex sits on its issue rate).  linear keeps the densely packed box (4 planes per stage: a fixed stride would
+    // cost a fourth resident CTA) and only gets the unrolled ring.
+    constexpr bool FIXED = INTERP != VT_LINEAR;
+    const unsigned stage_bytes = FIXED ? (unsigned)(PPS * STAGE * 4) : G.stage_bytes;
+    const int pe = FIXED ? STAGE : G.plane_elems;
     const int t0 = (int)M.r[0][3];
     const int zc0 = P.z_begin + blockIdx.y * z_chunk;
     const int zc1 = min(zc0 + z_chunk, P.z_end);
@@ -417,7 +424,13 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
             if (tid == 0 && q <= q_last) {
                 const unsigned bar = bars_s + 8u * st;
                 vt_mbar_expect_tx(bar, (unsigned)(G.box_w * G.box_h * PPS) * 4u);
-                vt_tma_load_3d(ring_s + st * stage_bytes, &G.tmap, bar, xlo, ylo, q);  // planes past the source: zeros
+                if constexpr (FIXED) {  // one box of depth 1 per plane, at the fixed plane stride
+#pragma unroll
+                    for (int p = 0; p < PPS; p++)
+                        vt_tma_load_3d(ring_s + st * stage_bytes + 4u * (unsigned)(p * STAGE), &G.tmap, bar, xlo, ylo, q + p);
+                } else {
+                    vt_tma_load_3d(ring_s + st * stage_bytes, &G.tmap, bar, xlo, ylo, q);  // planes past the source: zeros
+                }
             }
         } else {
 #pragma unroll
@@ -442,15 +455,18 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
     T taps;
     if (inplane) taps.template init<RULE>(p1, p2, ylo, xlo, pitch);
     float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // sliding window of per-plane sums
-    unsigned cur = 0, fill = NSTAGE - 1;     // ring stage being consumed / refilled
-    unsigned phase = 0;                      // mbarrier parity of stage `cur`
+    unsigned phase = 0;                      // mbarrier parity of the ring's current round
     const char *srcf = srcq + (size_t)((NSTAGE - 1) * PPS) * plane_bytes;  // address of plane q + (NSTAGE-1)*PPS
-    for (int q = q_first; q <= q_last; q += PPS) {
-        if constexpr (TMA) vt_mbar_wait(bars_s + 8u * cur, phase);
+
+    // one ring stage: planes q .. q+PPS-1 live in stage CUR (compile time); refills the stage consumed before it
+    auto stage_step = [&](auto cur_c, int q) {
+        constexpr unsigned CUR = decltype(cur_c)::value;
+        constexpr unsigned FILL = (CUR + NSTAGE - 1) % NSTAGE;
+        if constexpr (TMA) vt_mbar_wait(bars_s + 8u * CUR, phase);
         else cp_async_wait<NSTAGE - 2>();
-        __syncthreads();  // stage `cur` has landed for every thread; everyone is done with the previous stage
-        issue(q + (NSTAGE - 1) * PPS, srcf, fill);  // refills the stage the previous planes lived in
-        const float *s = (const float *)(ring + cur * stage_bytes);
+        __syncthreads();  // stage CUR has landed for every thread; everyone is done with the previous stage
+        issue(q + (NSTAGE - 1) * PPS, srcf, FILL);
+        const float *s = (const float *)(ring + CUR * stage_bytes);
         float r[PPS];
 #pragma unroll
         for (int p = 0; p < PPS; p++) r[p] = 0.0f;
@@ -494,8 +510,19 @@ __global__ void __launch_bounds__(NT, INTERP == VT_LINEAR ? 4 : 3)
             dstz += oplane;
         }
         srcf += (size_t)PPS * plane_bytes;
-        if (++cur == NSTAGE) { cur = 0; phase ^= 1u; }
-        if (++fill == NSTAGE) fill = 0;
+    };
+    for (int q = q_first;;) {
+        stage_step(std::integral_constant<unsigned, 0>{}, q);
+        if ((q += PPS) > q_last) break;
+        stage_step(std::integral_constant<unsigned, 1>{}, q);
+        if ((q += PPS) > q_last) break;
+        stage_step(std::integral_constant<unsigned, 2>{}, q);
+        if ((q += PPS) > q_last) break;
+        if constexpr (NSTAGE == 4) {
+            stage_step(std::integral_constant<unsigned, 3>{}, q);
+            if ((q += PPS) > q_last) break;
+        }
+        phase ^= 1u;
     }
 }
 
@@ -687,11 +714,12 @@ int launch2(VtResampleParams &P, cudaStream_t st)
                     (int)(P.aux[0] >> 6), best_cost);
         G.box_w = best_w;
         G.box_h = need_h;
-        G.plane_elems = G.box_w * G.box_h;  // a box of depth PPS lands as PPS densely packed planes
+        constexpr bool FIXED = INTERP != VT_LINEAR;  // see the kernel: cubic planes sit at the fixed stride STAGE
+        G.plane_elems = FIXED ? STAGE : G.box_w * G.box_h;  // linear: a box of depth PPS lands as PPS densely packed planes
         G.stage_bytes = ((unsigned)(G.plane_elems * PPS * 4) + 127u) & ~127u;
         const unsigned long long gdim[3] = {(unsigned long long)P.s2, (unsigned long long)P.s1, (unsigned long long)P.s0};
         const unsigned long long gstr[2] = {(unsigned long long)P.src_row * 4, (unsigned long long)P.src_plane * 4};
-        const unsigned box[3] = {(unsigned)G.box_w, (unsigned)G.box_h, (unsigned)PPS};
+        const unsigned box[3] = {(unsigned)G.box_w, (unsigned)G.box_h, FIXED ? 1u : (unsigned)PPS};
         const int rc = vt_encode_tmap_3d(&G.tmap, P.src, gdim, gstr, box);
         if (rc) return rc;
     } else {
