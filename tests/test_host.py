@@ -128,3 +128,39 @@ def test_product_does_not_touch_the_oracle():
             text = p.read_text()
             assert 'import oracle' not in text and 'from oracle' not in text and 'vt_oracle' not in text, p
             assert 'import scipy' not in text and 'from scipy' not in text, f'{p}: CPU fallback dependency'
+
+
+def test_project_abi_argument_checks_without_a_gpu():
+    """vt_project_* validate their arguments before touching CUDA; the workspace size is pure host arithmetic."""
+    lib = ctypes.CDLL(str(ROOT / 'voltools_b200' / 'libvoltools_b200.so'))
+    lib.vt_project_workspace_bytes.restype = ctypes.c_size_t
+    lib.vt_project_workspace_bytes.argtypes = [ctypes.c_int] * 3
+    assert lib.vt_project_workspace_bytes(0, 4, 4) == 0
+    small, big = lib.vt_project_workspace_bytes(16, 32, 32), lib.vt_project_workspace_bytes(512, 512, 512)
+    # 4 zero-bordered planes + 3 partial-sum planes per z-chunk
+    assert small >= 4 * (32 + 4) * (32 + 4) * 4 + 3 * 32 * 32 * 4
+    assert big > small and big < 64 << 20
+    f32p, vp, i, ll = ctypes.POINTER(ctypes.c_float), ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+    lib.vt_project_strided_f32.argtypes = [vp, i, i, i, ll, ll, vp, i, i, i, ll, f32p, i, i, ctypes.c_uint, i, i, vp,
+                                           ctypes.c_size_t, i, vp]
+    m = np.identity(4, dtype=np.float32)
+    mp = m.ctypes.data_as(f32p)
+    args = lambda **kw: [kw.get('src', 8), 4, 4, 4, 4, 16, kw.get('dst', 8), 4, 4, 4, kw.get('stride', 16), kw.get('m', mp),  # noqa: E731
+                         kw.get('k', 1), kw.get('interp', 0), 0, 0, 4, None, 0, -1, None]
+    assert lib.vt_project_strided_f32(*args(m=None)) == 1        # VT_ERR_INVALID_ARG: no matrices
+    assert lib.vt_project_strided_f32(*args(k=-1)) == 1
+    assert lib.vt_project_strided_f32(*args(interp=7)) == 1
+    assert lib.vt_project_strided_f32(*args(stride=15)) == 1     # images would overlap
+    assert lib.vt_project_strided_f32(*args(k=0)) == 0           # nothing to do
+    assert lib.vt_project_strided_f32(*args(src=None)) == 1
+
+
+def test_project_python_api_surface():
+    import voltools_b200 as vt
+    for name in ('project', 'affine_project', 'project_many'):
+        assert callable(getattr(vt.StaticVolume, name))
+    assert callable(vt.project)
+    with pytest.raises(ValueError):
+        vt.project(np.zeros((4, 4, 4), np.float32), interpolation='nearest')
+    with pytest.raises(ValueError):
+        vt.project(np.zeros((4, 4, 4), np.float32), device='cpu')

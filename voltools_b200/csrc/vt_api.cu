@@ -408,11 +408,9 @@ int vt_project_strided_f32(const float *d_src, int s0, int s1, int s2, long long
         } else {
             // general matrices (or no workspace): the resampling kernels add into the zeroed image
             if (family == 3) family = vt_brick_supported(P, interp) ? 2 : 1;
-            if (o0 > 0 && z_end > z_begin) {
-                // one memset per image keeps a padded proj_batch_stride intact
-                for (int k = 0; k < count; k++)
-                    VT_CUDA(cudaMemsetAsync(P.dst + (size_t)k * proj_batch_stride, 0, (size_t)o1 * o2 * sizeof(float), st));
-            }
+            // one memset per image keeps a padded proj_batch_stride intact (an empty z range leaves the zeros)
+            for (int k = 0; k < count; k++)
+                VT_CUDA(cudaMemsetAsync(P.dst + (size_t)k * proj_batch_stride, 0, (size_t)o1 * o2 * sizeof(float), st));
             P.flags = flags | VT_INTERNAL_PROJECT;
             rc = family == 2 ? vt_launch_brick(P, interp, st) : vt_launch_gather(P, interp, st);
         }
