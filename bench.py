@@ -15,6 +15,7 @@ Workloads (BASELINE.json `configs`, inputs per SURVEY.md section 8d):
   sweep   configs[2]: StaticVolume 256^3 filt_bspline, 180-angle sweep; rank 0 prefilters, one NCCL broadcast of
           the coefficient volume, the angles are split across ranks (strong scaling).
   modes   all five interpolation modes at 512^3 (rot45 and full affine) -> reported under "modes" (1 GPU).
+  cpu_baselines  reference CPU path and scipy.ndimage.affine_transform at 100^3 .. 512^3 on this host (no GPU work).
   project rotate-and-project at 512^3: StaticVolume.project_many vs transform + sum(axis=0) (1 GPU).
 
 `value` is device-resident throughput (inputs already in HBM, CUDA events); `e2e` is the same batch through the
@@ -163,6 +164,38 @@ def cpu_baseline_leg(cfg):
         out['extra'] = extra
     except Exception as e:  # informational only
         out['extra'] = {'error': repr(e)}
+    return out
+
+
+def run_cpu_baselines(args):
+    """SURVEY 8(d) CPU baselines on this host: the unmodified reference's CPU path (voltools.transform(device='cpu'))
+    and scipy.ndimage.affine_transform (order 1 / 3, tests/benchmark.py:60) at 100^3, 250^3, 256^3 and 512^3, rot45
+    matrix, one core each (SciPy ndimage is single-threaded).  1024^3 is extrapolated (x8 voxels of the 512^3 time)."""
+    from scipy import ndimage
+    from voltools_b200.utils import transform_matrix
+    ref_vt = _ref_voltools()
+    out = {'cores_used': 1, 'host_cores': os.cpu_count(), 'rows': {}}
+    for n in (100, 250, 256, 512):
+        v = np.random.default_rng(0).random((n, n, n), dtype=np.float32)
+        c = np.divide(np.subtract(v.shape, 1), 2, dtype=np.float32)
+        m = transform_matrix(center=c, **ROT45)
+        row = {}
+        for label, fn in (('scipy_order1', lambda: ndimage.affine_transform(v, m, order=1)),
+                          ('scipy_order3', lambda: ndimage.affine_transform(v, m, order=3)),
+                          ('reference_cpu_linear', (lambda: ref_vt.transform(v, interpolation='linear', device='cpu', **ROT45))
+                           if ref_vt else None),
+                          ('reference_cpu_filt_bspline',
+                           (lambda: ref_vt.transform(v, interpolation='filt_bspline', device='cpu', **ROT45))
+                           if ref_vt else None)):
+            if fn is None:
+                continue
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            row[label] = {'s': dt, 'gvox_s': n ** 3 / dt / 1e9}
+        out['rows'][f'{n}^3'] = row
+    out['rows']['1024^3 (extrapolated: 8 x the 512^3 time)'] = {
+        k: {'s': 8 * r['s'], 'gvox_s': r['gvox_s']} for k, r in out['rows']['512^3'].items()}
     return out
 
 
@@ -563,7 +596,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes', 'sweep', 'zslab', 'project'])
+    ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes', 'sweep', 'zslab', 'project', 'cpu_baselines'])
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager calls instead of replaying a captured CUDA graph')
@@ -576,6 +609,10 @@ def main():
         cfg['name'] = cfg['name'].replace('batch of 8', f'batch of {args.batch}')
     if args.impl == 'reference':
         reference_arm(args, cfg)
+        return
+    if args.workload == 'cpu_baselines':
+        print(json.dumps({'metric': METRIC, 'workload': 'CPU baselines (SURVEY 8d), rot45, one core',
+                          'cpu_baselines': run_cpu_baselines(args)}))
         return
     import torch
     import voltools_b200 as vt
