@@ -578,3 +578,26 @@ def test_largest_config_1024(vt):
                     N.affine(u.data_ptr(), shape, base(got), shape, mat, interp, N.OOB_ZERO | fam, z_range=zr)
                 assert float((got - ref).abs().max()) <= 1e-6, (interp, fam)
     tex.close()
+
+
+def test_second_device_in_one_process(vt):
+    """device='gpu:1' after 'gpu:0' in the same process: per-device kernel attributes (dynamic shared memory > 48 KB for
+    the brick and slice kernels), contexts and the caller's current device being left alone."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs in one process')
+    shape = (40, 48, 56)
+    vol = np.random.default_rng(21).random(shape, dtype=np.float32)
+    mats = _matrices(vt, shape)
+    for mode in ('linear', 'filt_bspline', 'bspline_simple'):
+        r = _range(vol, mode)
+        for name in ('rot45', 'full_affine', 'downscale'):
+            want = oracle.affine(vol, mats[name], mode)
+            for dev in ('gpu:0', 'gpu:1'):
+                got = vt.affine(vol, mats[name], interpolation=mode, device=dev)
+                assert _err(got, want, r) <= TOL[mode], (mode, name, dev)
+                assert torch.cuda.current_device() == 0
+        sv = vt.StaticVolume(vol, interpolation=mode, device='gpu:1')
+        out = sv.affine_many([mats['rot45'], mats['full_affine']])
+        assert out.device.index == 1
+        assert _err(out[1].cpu().numpy(), oracle.affine(vol, mats['full_affine'], mode), r) <= TOL[mode]

@@ -17,6 +17,8 @@
 // float32 rounding differs by ~1e-7 of the range.
 #include <cuda.h>
 
+#include <atomic>
+
 #include "vt_common.cuh"
 
 namespace {
@@ -331,15 +333,19 @@ int launch2(const VtResampleParams &P, cudaStream_t st)
     dim3 grid((P.o2 + TX - 1) / TX, (P.o1 + TY - 1) / TY, nzt * P.n_mats);
     if (grid.y > 65535u || grid.z > 65535u) return VT_ERR_UNSUPPORTED;
     const size_t smem = 128 + (size_t)G.bw * G.bh * G.bd * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device and per function: one flag per device (a process may drive several GPUs)
+    static std::atomic<bool> attr_set_dev[64];
+    int attr_dev = 0;
+    VT_CUDA(cudaGetDevice(&attr_dev));
+    std::atomic<bool> &attr_set = attr_set_dev[attr_dev & 63];
+    if (!attr_set.load(std::memory_order_acquire)) {
         VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      128 + MAX_BRICK_BYTES));
         VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      128 + MAX_BRICK_BYTES));
         VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      128 + MAX_BRICK_BYTES));
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     {
         VtProf prof(VT_K_BRICK_LINEAR + INTERP, st);

@@ -20,6 +20,8 @@
 // cubicTex3DSimple (voltools/kernels/helper_interpolation.h:3-68) for this class of matrices.
 #include <cuda.h>
 
+#include <atomic>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -743,14 +745,18 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         G.stage_bytes = PPS * STAGE * 4;
     }
     const size_t smem = 128 + (size_t)NSTAGE * G.stage_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device and per function: one flag per device (a process may drive several GPUs)
+    static std::atomic<bool> attr_set_dev[64];
+    int attr_dev = 0;
+    VT_CUDA(cudaGetDevice(&attr_dev));
+    std::atomic<bool> &attr_set = attr_set_dev[attr_dev & 63];
+    if (!attr_set.load(std::memory_order_acquire)) {
         const int mx = 128 + NSTAGE * PPS * STAGE * 4;
         VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         VT_CUDA(cudaFuncSetAttribute(vt_slice_kernel<INTERP, RULE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     {
         VtProf prof(VT_K_SLICE_LINEAR + INTERP, st);
