@@ -98,6 +98,14 @@ class OracleEngine:
         v = buffer.numpy()[:, :, :width]
         return torch.from_numpy(np.stack([oracle.affine(v, m, self._mode(interpolation)) for m in matrices]))
 
+    def project_many(self, buffer, width, interpolation, matrices, z_range=None):
+        import torch
+        v = buffer.numpy()[:, :, :width]
+        z0, z1 = (0, v.shape[0]) if z_range is None else z_range
+        return torch.from_numpy(np.stack([
+            oracle.affine(v, m, self._mode(interpolation), z_range=(z0, z1))[z0:z1].astype(np.float64).sum(axis=0)
+            .astype(np.float32) for m in matrices]))
+
     def resample_slab(self, buffer, width, interpolation, matrix, z0, z1):
         import torch
         v = buffer.numpy()[:, :, :width]
@@ -132,6 +140,11 @@ def _worker(rank, world, init_file, outdir):
         full = multigpu.gather_slabs(slab, dst=0)
         np.savez(os.path.join(outdir, f'slab_{rank}.npz'), slab=slab.numpy(), z=np.array([z0, z1]),
                  full=full.numpy() if full is not None else np.zeros(0))
+        # rotate-and-project: a tilt series split across the ranks, and one projection summed from z-slabs (all-reduce)
+        tilts = [transform_matrix(rotation=(a, 0, 0), rotation_order='sxyz', center=c) for a in (-60, -20, 15, 50, 72)]
+        proj, pidx = multigpu.project_sweep(vol if rank == 0 else None, tilts, 'filt_bspline', src=0, engine=eng)
+        whole = multigpu.zslab_project(vol if rank == 0 else None, m, 'bspline_simple', src=0, engine=eng)
+        np.savez(os.path.join(outdir, f'proj_{rank}.npz'), proj=proj.numpy(), idx=np.array(pidx), whole=whole.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -172,3 +185,14 @@ def test_sweep_and_zslab_two_ranks_gloo():
         assert tuple(z0['z']) == (0, 7) and tuple(z1['z']) == (7, 13)
         assert np.array_equal(z0['slab'], want[0:7]) and np.array_equal(z1['slab'], want[7:13])
         assert np.array_equal(z0['full'], want)
+        tilts = [transform_matrix(rotation=(a, 0, 0), rotation_order='sxyz', center=c) for a in (-60, -20, 15, 50, 72)]
+        seen = []
+        for r in range(world):
+            z = np.load(os.path.join(d, f'proj_{r}.npz'))
+            for p, i in zip(z['proj'], z['idx']):
+                ref = oracle.affine(vol, tilts[int(i)], 'filt_bspline').astype(np.float64).sum(axis=0)
+                assert np.allclose(p, ref, rtol=0, atol=1e-5 * shape[0])
+                seen.append(int(i))
+            # the all-reduced projection is complete and identical on every rank
+            assert np.allclose(z['whole'], want.astype(np.float64).sum(axis=0), rtol=0, atol=1e-5 * shape[0])
+        assert sorted(seen) == list(range(len(tilts)))

@@ -33,6 +33,14 @@ for mode in ('filt_bspline', 'linear', 'bspline_simple'):
     whole = multigpu.gather_slabs(slab)
     if rank == 0:
         assert float((whole - full).abs().max()) <= tol
+    # rotate-and-project: a tilt series split across the ranks; one projection summed from z-slabs by all-reduce
+    tilts = [vt.utils.transform_matrix(rotation=(a, 0, 0), rotation_order='sxyz', center=c) for a in range(-60, 60, 15)]
+    proj, pidx = multigpu.project_sweep(vol if rank == 0 else None, tilts, mode)
+    scale = (float(sv.coefficients.max() - sv.coefficients.min())) * shape[0]
+    ref_p = sv.project_many([tilts[i] for i in pidx])
+    assert float((proj - ref_p).abs().max()) <= 2e-6 * scale, (mode, rank, 'project_sweep')
+    whole_p = multigpu.zslab_project(vol if rank == 0 else None, m, mode)
+    assert float((whole_p - full.double().sum(dim=0).float()).abs().max()) <= 2e-6 * scale, (mode, rank, 'zslab_project')
 dist.barrier()
 if rank == 0:
     print(f'multi-GPU check OK on {world} ranks')

@@ -142,6 +142,12 @@ class CudaEngine:
                            z_range=(z0, z1), device=self.dev,
                            stream=self.torch.cuda.current_stream(self.dev).cuda_stream, src_strides=sv._strides)
 
+    def project_many(self, buffer, width, interpolation, matrices, z_range=None):
+        """(K, d1, width) projections along axis 0 of the transformed volume (planes z_range of it), fused."""
+        from .volume import StaticVolume
+        sv = StaticVolume.from_coefficients(buffer, interpolation, width)
+        return sv.project_many(matrices, z_range=z_range)
+
     def resample_slab(self, buffer, width, interpolation, matrix, z0, z1):
         from . import _native
         from .volume import StaticVolume
@@ -270,6 +276,43 @@ def zslab_affine(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline'
     z0, z1 = split_slabs(int(buffer.shape[0]), world, rank)
     m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(4, 4)
     return engine.resample_slab(buffer, width, interpolation, m, z0, z1), (z0, z1)
+
+
+def project_sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = 'filt_bspline', src: int = 0, group=None,
+                  engine=None, shape=None, chunks=None):
+    """Tilt series (examples/projections.py: `transform(rotation=...).sum(axis=0)` per angle), the matrices split across
+    the ranks of `group` like `sweep`; the transformed volumes are never written (vt_project_strided_f32).
+    Returns (projections, indices): `projections[i]` (d1, d2) belongs to `matrices[indices[i]]`, resident on this rank."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if engine is None:
+        import torch
+        engine = CudaEngine(torch.cuda.current_device())
+    mats = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
+    mine = split_strided(len(mats), world, rank)
+    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape, None, chunks)
+    if not len(mine):
+        return engine.empty((0, int(buffer.shape[1]), width)), []
+    return engine.project_many(buffer, width, interpolation, mats[mine.start::world]), list(mine)
+
+
+def zslab_project(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline', src: int = 0, group=None, engine=None,
+                  shape=None):
+    """ONE projection of one (large) volume under any matrix: rank r sums the output planes of its z-slab
+    (`split_slabs`) with the fused kernels, then one all-reduce (NCCL, over NVLink) adds the partial images -- the only
+    exchange step of the path besides the coefficient broadcast, d1 x d2 floats.  Returns the full (d1, d2) projection
+    on every rank."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if engine is None:
+        import torch
+        engine = CudaEngine(torch.cuda.current_device())
+    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape)
+    z0, z1 = split_slabs(int(buffer.shape[0]), world, rank)
+    m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(1, 4, 4)
+    part = engine.project_many(buffer, width, interpolation, m, z_range=(z0, z1))[0].contiguous()
+    dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    return part
 
 
 def gather_slabs(slab, group=None, dst: int = 0):
