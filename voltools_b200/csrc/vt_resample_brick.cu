@@ -268,6 +268,30 @@ void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
 {
     const VtMat &M = P.mats[0];
     constexpr int NS = 2;
+    // The search below costs ~100 us of host time.  Small launches cannot win that back (tools/latency_probe.py: a 16^3
+    // filt_bspline transform under a general matrix took 198 us per call, 88 us under a slice-family one), and a
+    // resident volume keeps getting the same matrices: skip it below 8 M output voxels, memoise it above.
+    if ((long long)(P.z_end - P.z_begin) * P.o1 * P.o2 * P.n_mats < (8LL << 20)) return;
+    struct Memo {
+        VtMat m;
+        int key[7];
+        int bw, bh, layout;
+        bool valid;
+    };
+    static thread_local Memo memo[8];
+    static thread_local unsigned memo_next = 0;
+    const int key[7] = {P.o1, P.o2, P.z_begin, P.z_end, G.bw, G.bh, G.bd};
+    for (const Memo &e : memo)
+        if (e.valid && memcmp(&e.m, &M, sizeof M) == 0 && memcmp(e.key, key, sizeof key) == 0) {
+            G.bw = e.bw;
+            G.bh = e.bh;
+            G.layout = e.layout;
+            return;
+        }
+    Memo &slot = memo[memo_next++ & 7];
+    slot.m = M;
+    memcpy(slot.key, key, sizeof key);
+    slot.valid = false;
     static thread_local int iz[2][NS][NT], iy[2][NS][NT], ix[2][NS][NT];
     for (int layout = 0; layout < 2; layout++)
         for (int smp = 0; smp < NS; smp++) {
@@ -314,6 +338,10 @@ void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
                 }
             }
         }
+    slot.bw = G.bw;
+    slot.bh = G.bh;
+    slot.layout = G.layout;
+    slot.valid = true;
 }
 
 template <int INTERP, int RULE>
