@@ -281,14 +281,12 @@ template <typename V>
 struct ZOps;
 template <>
 struct ZOps<float> {
-    static constexpr int W = 1;
     static __device__ __forceinline__ float zero() { return 0.0f; }
     static __device__ __forceinline__ float mulc(float c, float x) { return __fmul_rn(c, x); }
     static __device__ __forceinline__ float fmac(float c, float x, float y) { return __fmaf_rn(c, x, y); }
 };
 template <>
 struct ZOps<vt_f2> {
-    static constexpr int W = 2;
     static __device__ __forceinline__ vt_f2 zero() { return 0ull; }
     static __device__ __forceinline__ vt_f2 mulc(float c, vt_f2 x)
     {
