@@ -100,6 +100,13 @@ __host__ __device__ __forceinline__ float inplane_coord(const float *row, float 
 #endif
 }
 
+// planes per ring stage of the cubic kernels (even; the ring then has 4 stages of 2 planes or 3 stages of 4).
+// Measured: 4 planes per stage (half the barriers, more loads in flight, but 76 / 80+spill registers) is 6-10 % SLOWER
+// than 2 (cubic_tex 250^3: 0.087 vs 0.082 ms; 256^3 12-angle sums 1.113 vs 1.001 ms).
+#ifndef VT_CUBIC_PPS
+#define VT_CUBIC_PPS 2
+#endif
+
 template <int INTERP>
 struct Taps;
 
@@ -157,7 +164,7 @@ template <>
 struct Taps<VT_CUBIC_SIMPLE> {
     static constexpr int LO = -1, HI = 2;
     static constexpr int PLANES_BEFORE = 1, PLANES_AFTER = 1;
-    static constexpr int PPS = 2, NSTAGE = 4;
+    static constexpr int PPS = VT_CUBIC_PPS, NSTAGE = VT_CUBIC_PPS == 2 ? 4 : 3;
     float w[16];
     int row[4];
     float wz0, wz1, wz2;
@@ -184,14 +191,20 @@ struct Taps<VT_CUBIC_SIMPLE> {
     // in-plane sums of the stage's two planes, one FFMA2 per tap: {plane q, plane q+1} x {w, w}
     __device__ __forceinline__ void planes(const float *s, int pe, float (&out)[PPS]) const
     {
-        const float *s1 = s + pe;
-        vt_f2 acc = 0ull;
+        vt_f2 acc[PPS / 2];
+#pragma unroll
+        for (int h = 0; h < PPS / 2; h++) acc[h] = 0ull;
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                acc = vt_fma2(vt_pk(s[row[j] + i], s1[row[j] + i]), vt_pk(w[j * 4 + i], w[j * 4 + i]), acc);
-        vt_unpk(acc, out[0], out[1]);
+            for (int i = 0; i < 4; i++) {
+                const vt_f2 ww = vt_pk(w[j * 4 + i], w[j * 4 + i]);
+#pragma unroll
+                for (int h = 0; h < PPS / 2; h++)
+                    acc[h] = vt_fma2(vt_pk(s[(2 * h) * pe + row[j] + i], s[(2 * h + 1) * pe + row[j] + i]), ww, acc[h]);
+            }
+#pragma unroll
+        for (int h = 0; h < PPS / 2; h++) vt_unpk(acc[h], out[2 * h], out[2 * h + 1]);
     }
 };
 
@@ -203,7 +216,7 @@ template <>
 struct Taps<VT_CUBIC_TEX> {
     static constexpr int LO = -1, HI = 2;
     static constexpr int PLANES_BEFORE = 1, PLANES_AFTER = 1;
-    static constexpr int PPS = 2, NSTAGE = 4;
+    static constexpr int PPS = VT_CUBIC_PPS, NSTAGE = VT_CUBIC_PPS == 2 ? 4 : 3;
     float wa[16], wb[16], wc[16];
     int adr[8];  // element offsets of taps (row j, x pair k): adr[j*2+k], the pair is (adr, adr+1)
     template <int RULE>
@@ -284,22 +297,30 @@ struct Taps<VT_CUBIC_TEX> {
     // texel is FFMA2's broadcast operand) and {t0, t1} x {wc, wc}: 3 FFMA2 instead of 6 FFMA
     __device__ __forceinline__ void planes3(const float *s, int pe, float (&qa)[PPS], float (&qb)[PPS], float (&qc)[PPS]) const
     {
-        const float *s1 = s + pe;
-        vt_f2 ab0 = 0ull, ab1 = 0ull, c01 = 0ull;
+        vt_f2 ab[PPS], c[PPS / 2];
+#pragma unroll
+        for (int p = 0; p < PPS; p++) ab[p] = 0ull;
+#pragma unroll
+        for (int h = 0; h < PPS / 2; h++) c[h] = 0ull;
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int o = adr[j * 2 + (i >> 1)] + (i & 1);
-                const float t0 = s[o], t1 = s1[o];
                 const vt_f2 wab = vt_pk(wa[j * 4 + i], wb[j * 4 + i]);
-                ab0 = vt_fma2(wab, vt_pk(t0, t0), ab0);
-                ab1 = vt_fma2(wab, vt_pk(t1, t1), ab1);
-                c01 = vt_fma2(vt_pk(t0, t1), vt_pk(wc[j * 4 + i], wc[j * 4 + i]), c01);
+                const vt_f2 wcc = vt_pk(wc[j * 4 + i], wc[j * 4 + i]);
+#pragma unroll
+                for (int h = 0; h < PPS / 2; h++) {
+                    const float t0 = s[(2 * h) * pe + o], t1 = s[(2 * h + 1) * pe + o];
+                    ab[2 * h] = vt_fma2(wab, vt_pk(t0, t0), ab[2 * h]);
+                    ab[2 * h + 1] = vt_fma2(wab, vt_pk(t1, t1), ab[2 * h + 1]);
+                    c[h] = vt_fma2(vt_pk(t0, t1), wcc, c[h]);
+                }
             }
-        vt_unpk(ab0, qa[0], qb[0]);
-        vt_unpk(ab1, qa[1], qb[1]);
-        vt_unpk(c01, qc[0], qc[1]);
+#pragma unroll
+        for (int p = 0; p < PPS; p++) vt_unpk(ab[p], qa[p], qb[p]);
+#pragma unroll
+        for (int h = 0; h < PPS / 2; h++) vt_unpk(c[h], qc[2 * h], qc[2 * h + 1]);
     }
 };
 
@@ -880,14 +901,26 @@ __global__ void __launch_bounds__(NT)
             r = o[0];
         } else if constexpr (INTERP == VT_CUBIC_SIMPLE) {
             float ab[T::PPS], bc[T::PPS];
-            taps.planes(sums, pe, ab);
-            taps.planes(sums + pe, pe, bc);
-            r = fmaf(taps.wz2, bc[1], fmaf(taps.wz1, ab[1], __fmul_rn(taps.wz0, ab[0])));
+            taps.planes(sums, pe, ab);  // in-plane sums of the A, B (and, with 4 planes per stage, C) plane sums
+            float sc;
+            if constexpr (T::PPS >= 3) {
+                sc = ab[2];
+            } else {
+                taps.planes(sums + pe, pe, bc);
+                sc = bc[1];
+            }
+            r = fmaf(taps.wz2, sc, fmaf(taps.wz1, ab[1], __fmul_rn(taps.wz0, ab[0])));
         } else {
             float qa[T::PPS], qb[T::PPS], qc[T::PPS], ra[T::PPS], rb[T::PPS], rc[T::PPS];
             taps.planes3(sums, pe, qa, qb, qc);
-            taps.planes3(sums + pe, pe, ra, rb, rc);
-            r = (qa[0] + qb[1]) + rc[1];
+            float cc;
+            if constexpr (T::PPS >= 3) {
+                cc = qc[2];
+            } else {
+                taps.planes3(sums + pe, pe, ra, rb, rc);
+                cc = rc[1];
+            }
+            r = (qa[0] + qb[1]) + cc;
         }
     }
     P.dst[(size_t)mat * P.dst_batch_stride + (size_t)a1 * P.o2 + a2] = r;
