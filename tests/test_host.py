@@ -164,3 +164,15 @@ def test_project_python_api_surface():
         vt.project(np.zeros((4, 4, 4), np.float32), interpolation='nearest')
     with pytest.raises(ValueError):
         vt.project(np.zeros((4, 4, 4), np.float32), device='cpu')
+
+
+def test_build_script_loads_without_the_package():
+    """__graft_entry__.build() must work on a clean checkout: the build script is loaded by path, because importing the
+    package needs the shared library the build creates."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('vt_csrc_build_test', ROOT / 'voltools_b200' / 'csrc' / 'build.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert callable(mod.build) and mod.SO.name == 'libvoltools_b200.so'
+    entry = (ROOT / '__graft_entry__.py').read_text()
+    assert 'spec_from_file_location' in entry and 'from voltools_b200.csrc import build' not in entry
