@@ -30,5 +30,11 @@ for it in range(2):
             N.affine(src.data_ptr(), shape, dst.data_ptr(), shape, aff, interp, N.OOB_ZERO | N.KERNEL_GATHER, stream=st)
         if 'brick' in what:
             N.affine(src.data_ptr(), shape, dst.data_ptr(), shape, aff, interp, N.OOB_ZERO | N.KERNEL_BRICK, stream=st)
+if 'project' in what:
+    sv = vt.StaticVolume(src, interpolation='filt_bspline', device='gpu:0')
+    tilt = vt.utils.transform_matrix(rotation=(30, 0, 0), rotation_order='sxyz', center=c)
+    for it in range(2):
+        sv.project_many([tilt])
+        sv.project_many([aff])
 torch.cuda.synchronize()
 print('ok', N.launch_count())

@@ -835,20 +835,29 @@ __global__ void __launch_bounds__(PS_NT)
     const int q0 = lo + c * z_chunk, q1 = min(q0 + z_chunk, hi);
     const float *p = src + (size_t)q0 * src_plane + (size_t)y * src_row + x;
     float sa = 0.0f, sb = 0.0f, sc = 0.0f;
+    float common = 0.0f;  // planes inside all three ranges (everything but two planes at either end): one add each
     int q = q0;
     for (; q + PS_UNROLL <= q1; q += PS_UNROLL) {
         float v[PS_UNROLL];
 #pragma unroll
         for (int u = 0; u < PS_UNROLL; u++) v[u] = __ldg(p + (size_t)u * src_plane);
+        if (q >= R.b0 + 1 && q + PS_UNROLL <= R.b1 - 1) {  // uniform
 #pragma unroll
-        for (int u = 0; u < PS_UNROLL; u++) {
-            const int qq = q + u;
-            if (qq >= R.b0 - 1 && qq < R.b1 - 1) sa += v[u];
-            if (qq >= R.b0 && qq < R.b1) sb += v[u];
-            if (qq >= R.b0 + 1 && qq < R.b1 + 1) sc += v[u];
+            for (int u = 0; u < PS_UNROLL; u++) common += v[u];
+        } else {
+#pragma unroll
+            for (int u = 0; u < PS_UNROLL; u++) {
+                const int qq = q + u;
+                if (qq >= R.b0 - 1 && qq < R.b1 - 1) sa += v[u];
+                if (qq >= R.b0 && qq < R.b1) sb += v[u];
+                if (qq >= R.b0 + 1 && qq < R.b1 + 1) sc += v[u];
+            }
         }
         p += (size_t)PS_UNROLL * src_plane;
     }
+    sa += common;
+    sb += common;
+    sc += common;
     for (; q < q1; q++) {
         const float v = __ldg(p);
         if (q >= R.b0 - 1 && q < R.b1 - 1) sa += v;
