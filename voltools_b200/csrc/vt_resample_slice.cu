@@ -9,20 +9,26 @@
 // that (the general kernels cannot):
 //   * a CTA owns a 16x16 tile of (a1, a2) columns and marches along axis 0;
 //   * the in-plane footprint of the tile (its rotated bounding box + filter support) is the same rectangle in
-//     every input plane; it is staged plane by plane into a shared-memory ring with cp.async (zero-filled
-//     outside the source = the texture's border mode), using per-thread offsets computed once;
+//     every input plane; it is staged into a shared-memory ring of 3-4 stages of 2-4 planes each, by TMA box loads
+//     (cp.async.bulk.tensor: texels outside the source arrive as zeros = the texture's border mode) when the source
+//     rows are 16-byte aligned, else by per-element cp.async with per-thread offsets computed once;
 //   * weights are computed once per column with the reference's exact float32 recipe and kept in registers;
-//   * per plane a thread does 4 (linear) or 16 (cubic) shared-memory loads; the three axis-0 taps of the cubic
-//     modes come from a register sliding window over the per-plane sums.
+//   * per plane a thread does 4 (linear) or 16 (cubic) shared-memory loads, two planes per FFMA2; the three axis-0
+//     taps of the cubic modes come from a register sliding window over the per-plane sums;
+//   * the ring loop is unrolled over its stages and the cubic modes keep planes at compile-time strides, so a tap
+//     load is LDS [register + immediate];
+//   * how a warp's lanes tile the CTA's columns (2x16 / 4x8 / 8x4) and the row pitch are chosen per matrix by the
+//     host from a bank simulation (lane_pos, pitch_cost), the length of a march from the plane size (L2 reuse
+//     between neighbouring tiles).
+// The same per-column weight code serves the fused rotate-and-project path at the end of this file.
 // Results: same arithmetic as the gather family up to float32 summation order (<= ~1e-7 of the range).
 //
 // Replaces the reference's `transform` kernel (voltools/transforms.py:253-282) + linearTex3D / cubicTex3D /
 // cubicTex3DSimple (voltools/kernels/helper_interpolation.h:3-68) for this class of matrices.
 #include <cuda.h>
 
-#include <atomic>
-
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
