@@ -184,6 +184,17 @@ int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d
                    int n_mats, int interp, unsigned flags, int *family);
 
 /*
+ * Host-only introspection (no device is touched): what the slice family would decide for this launch on a GPU with
+ * `sms` multiprocessors -- z-chunks per column tile and their length, TMA or cp.async staging, the TMA box, and per
+ * matrix the warp shape (0 = 2x16, 1 = 4x8, 2 = 8x4 lanes over the CTA's 16x16 columns) and shared-memory pitch.
+ * VT_ERR_UNSUPPORTED if the matrices are not of the slice family.  `d_src` is only inspected for its alignment.
+ * Used by the CPU-side tests to pin the tuned heuristics.
+ */
+int vt_slice_plan(const void *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride, int o0,
+                  int o1, int o2, const float *h_mats, int n_mats, int interp, unsigned flags, int sms, int *chunks,
+                  int *z_chunk, int *tma, int *box_w, int *box_h, int *shapes, int *pitches);
+
+/*
  * Host-buffer path: numpy in -> numpy out, as transforms.affine() with output=None
  * (voltools/transforms.py:180-223: H2D, [prefilter], kernel, D2H).  Blocking.  The context owns pinned
  * staging and device buffers that grow to the largest volume seen, and pipelines the copies with the

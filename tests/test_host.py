@@ -176,3 +176,36 @@ def test_build_script_loads_without_the_package():
     assert callable(mod.build) and mod.SO.name == 'libvoltools_b200.so'
     entry = (ROOT / '__graft_entry__.py').read_text()
     assert 'spec_from_file_location' in entry and 'from voltools_b200.csrc import build' not in entry
+
+
+def test_slice_planner_decisions_without_a_gpu():
+    """vt_slice_plan is host-only: pins the tuned launch heuristics of the slice family."""
+    import voltools_b200 as vt
+    from voltools_b200 import _native as N
+
+    def rot(n, angle):
+        c = np.divide(np.subtract((n, n, n), 1), 2, dtype=np.float32)
+        return vt.utils.transform_matrix(rotation=(0, angle, 0), rotation_order='rzxz', center=c)
+
+    # a general rotation is not of the slice family
+    assert N.slice_plan((64, 64, 64), vt.utils.transform_matrix(rotation=(10, 20, 30), center=(31.5,) * 3), N.LINEAR) is None
+    # long marches over 4 MB planes lose the L2 reuse between tiles: the linear kernel's marches are capped at 512 MB
+    big = N.slice_plan((1024, 1024, 1024), rot(1024, 45), N.LINEAR)
+    assert big['tma'] and big['chunks'] >= 8 and big['z_chunk'] * 4 * 1024 * 1024 <= 512 << 20
+    assert N.slice_plan((1024, 1024, 1024), rot(1024, 45), N.CUBIC_TEX)['chunks'] <= 4   # on-chip bound: fewer start-ups
+    assert N.slice_plan((512, 512, 512), rot(512, 45), N.LINEAR)['z_chunk'] <= 128
+    # 0 and 90 degrees: 2 x 16 warps would put both rows on the same banks; a 4 x 8 / 8 x 4 shape is conflict free
+    for angle in (0, 90):
+        for interp in (N.CUBIC_TEX, N.CUBIC_SIMPLE):
+            assert N.slice_plan((512, 512, 512), rot(512, angle), interp)['shapes'][0] in (1, 2), (angle, interp)
+    # 45 degrees: no shape helps, the box is the 36-wide one (32 conflicts 3-way), 27 rows
+    for n in (250, 256, 512):
+        p = N.slice_plan((n, n, n), rot(n, 45), N.CUBIC_TEX)
+        assert (p['box_w'], p['box_h'], p['shapes'][0]) == (36, 27, 0), (n, p)
+    # a batch: one box width for the launch, a shape per matrix; planning is deterministic (memoised tables)
+    mats = [rot(256, a) for a in range(0, 180, 6)]
+    p1, p2 = N.slice_plan((256,) * 3, mats, N.CUBIC_SIMPLE), N.slice_plan((256,) * 3, mats, N.CUBIC_SIMPLE)
+    assert p1 == p2 and len(p1['shapes']) == 30 and len(set(p1['pitches'])) == 1 and len(set(p1['shapes'])) > 1
+    # rows that are not multiples of 16 bytes: per-element cp.async staging, a pitch per matrix in 32..40
+    odd = N.slice_plan((40, 50, 61), rot(50, 30), N.LINEAR, src_strides=(61, 50 * 61))
+    assert not odd['tma'] and 32 <= odd['pitches'][0] <= 40

@@ -66,6 +66,8 @@ def lib():
                                              ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _vp, ctypes.c_size_t,
                                              _i, _vp]
         L.vt_project_tex_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i, ctypes.c_uint, _i, _i, _vp]
+        L.vt_slice_plan.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i, _f32p, _i, _i,
+                                    ctypes.c_uint, _i] + [ctypes.POINTER(_i)] * 7
         L.vt_host_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
         L.vt_host_ctx_destroy.argtypes = [_vp]
         L.vt_host_affine_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f32p, _i, _i, ctypes.c_uint]
@@ -181,6 +183,23 @@ def project(src_ptr, src_shape, proj_ptr, dst_shape, matrices, interp, flags=0, 
     check(lib().vt_project_strided_f32(src_ptr, *map(int, src_shape), int(src_strides[0]), int(src_strides[1]), proj_ptr,
                                        *map(int, dst_shape), batch_stride, mp, len(m), interp, flags, z0, z1,
                                        workspace_ptr, workspace_bytes, device, stream))
+
+
+def slice_plan(shape, matrices, interp, flags=0, sms=148, src_strides=None, src_ptr=None):
+    """Host-only: the slice family's launch decisions (vt_slice_plan) as a dict, or None if the matrices are not of the
+    slice family."""
+    m, mp = _mats(matrices)
+    if src_strides is None:
+        src_strides = (padded_row(shape[2]), int(shape[1]) * padded_row(shape[2]))
+    out = [_i(0) for _ in range(5)]
+    shapes, pitches = (_i * len(m))(), (_i * len(m))()
+    rc = lib().vt_slice_plan(src_ptr, *map(int, shape), int(src_strides[0]), int(src_strides[1]), *map(int, shape), mp,
+                             len(m), interp, flags, sms, *[ctypes.byref(o) for o in out], shapes, pitches)
+    if rc == 2:
+        return None
+    check(rc)
+    return {'chunks': out[0].value, 'z_chunk': out[1].value, 'tma': bool(out[2].value), 'box_w': out[3].value,
+            'box_h': out[4].value, 'shapes': list(shapes), 'pitches': list(pitches)}
 
 
 def affine_plan(src_ptr, src_shape, dst_shape, matrices, interp, flags=0):

@@ -16,6 +16,8 @@ int vt_launch_brick(const VtResampleParams &P, int interp, cudaStream_t st);    
 int vt_brick_supported(const VtResampleParams &P, int interp);                  // vt_resample_brick.cu
 int vt_launch_slice(VtResampleParams &P, int interp, cudaStream_t st);          // vt_resample_slice.cu
 int vt_slice_supported(const VtResampleParams &P, int interp);                  // vt_resample_slice.cu
+int vt_slice_plan_impl(const VtResampleParams &P, int interp, int sms, int *chunks, int *z_chunk, int *tma, int *box_w,
+                       int *box_h, int *shapes, int *pitches);                                    // vt_resample_slice.cu
 size_t vt_slice_project_workspace_bytes(int s0, int s1, int s2);                                   // vt_resample_slice.cu
 int vt_launch_slice_project(VtResampleParams &P, int interp, float *d_workspace, cudaStream_t st);  // vt_resample_slice.cu
 int vt_prefilter_seq(float *d_vol, int d0, int d1, int d2, cudaStream_t st);    // vt_prefilter.cu
@@ -331,6 +333,22 @@ int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d
     if (f < 0) return VT_ERR_UNSUPPORTED;
     *family = f;
     return VT_OK;
+}
+
+int vt_slice_plan(const void *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride, int o0,
+                  int o1, int o2, const float *h_mats, int n_mats, int interp, unsigned flags, int sms, int *chunks,
+                  int *z_chunk, int *tma, int *box_w, int *box_h, int *shapes, int *pitches)
+{
+    if (!h_mats || n_mats < 1 || n_mats > VT_MAX_BATCH || !chunks || !z_chunk || !tma || !box_w || !box_h || sms < 1)
+        return VT_ERR_INVALID_ARG;
+    VtResampleParams P;
+    float dummy;
+    int rc = fill_params(P, d_src ? (const float *)d_src : &dummy, s0, s1, s2, src_row_stride, src_plane_stride, &dummy, o0,
+                         o1, o2, 0, flags, 0, o0);
+    if (rc) return rc;
+    if (!d_src) P.src = nullptr;  // alignment of a null pointer: aligned
+    copy_mats(P, h_mats, 0, n_mats);
+    return vt_slice_plan_impl(P, interp, sms, chunks, z_chunk, tma, box_w, box_h, shapes, pitches);
 }
 
 int vt_affine_strided_f32(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,

@@ -585,17 +585,22 @@ bool slice_ok(const VtResampleParams &P, int interp)
 //      cubic_simple   0.30 + 0.45 * wavefronts          (shared-memory bound: 16 loads per voxel and plane)
 //      cubic_tex      max(1.13, that)                   (1.13 = its instruction-issue floor)
 //      linear         max(0.40, 0.19 + 0.0045 * pitch + 0.06 * wavefronts)   (L2 -> SM traffic grows with the box width)
-//   + 0.02 (4 x 8) / 0.12 (8 x 4): a warp's stores cover 4 or 8 rows instead of 2.
-constexpr int PITCH_SAMPLES = 8;
-float pitch_conflicts(const VtMat &M, int pitch, int layout)
+//   + 0.02 (4 x 8) / 0.12 (8 x 4) measured: a warp's stores cover 4 or 8 rows instead of 2.
+constexpr int PITCH_SAMPLES = 16;
+constexpr int PITCH_LO = 24, PITCH_HI = PITCH_MAX;  // pitches the tables cover (bit p - PITCH_LO of the masks)
+
+// Average wavefronts per load of a matrix for every (pitch, warp shape) asked for.  The footprint origins of the sample
+// warps do not depend on the pitch, so they are computed once (the float coordinate recipe is the expensive part) and
+// each pitch is then integer bank counting; results are memoised per matrix (a sweep comes back with the same matrices
+// launch after launch, and a launch of 32 new matrices must stay well below the ~2 ms its kernels take).
+struct ConflictTable {
+    float key[6];
+    unsigned valid;  // pitches already filled
+    float wf[PITCH_HI - PITCH_LO + 1][N_LAYOUTS];
+};
+const ConflictTable &conflict_table(const VtMat &M, unsigned need)
 {
-    // small memo: a sweep comes back with the same matrices launch after launch
-    struct Entry {
-        float k[6];
-        int pitch, layout;
-        float value;
-    };
-    static thread_local Entry memo[256];
+    static thread_local ConflictTable memo[512];
     const float key[6] = {M.r[1][1], M.r[1][2], M.r[1][3], M.r[2][1], M.r[2][2], M.r[2][3]};
     unsigned h = 2166136261u;
     for (int i = 0; i < 6; i++) {
@@ -603,41 +608,65 @@ float pitch_conflicts(const VtMat &M, int pitch, int layout)
         memcpy(&u, &key[i], 4);
         h = (h ^ u) * 16777619u;
     }
-    h = (h ^ (unsigned)(pitch * 4 + layout)) * 16777619u;
-    Entry &e = memo[(h >> 8) & 255];
-    if (e.pitch == pitch && e.layout == layout && memcmp(e.k, key, sizeof key) == 0 && e.value > 0.0f) return e.value;
-    int cost = 0;
-    for (int sample = 0; sample < PITCH_SAMPLES; sample++) {
-        // tiles spread over the image (different sub-texel phases), a different warp of the CTA in each
-        const int a1_0 = 16 * (1 + 3 * sample), a2_0 = 16 * (2 + 5 * sample);
-        unsigned char count[32] = {0};
-        int first_addr[32];
-        int worst = 0;
-        for (int lane = 0; lane < 32; lane++) {
-            int ty, tx;
-            lane_pos(32 * ((3 * sample) & 7) + lane, layout, ty, tx);
-            const int a1 = a1_0 + ty, a2 = a2_0 + tx;
-            const int y = (int)floorf(inplane_coord(M.r[1], (float)a1, (float)a2) - 0.5f);
-            const int x = (int)floorf(inplane_coord(M.r[2], (float)a1, (float)a2) - 0.5f);
-            const int addr = y * pitch + x + (1 << 20);
-            const int bank = addr & 31;
-            if (count[bank] && first_addr[bank] == addr) continue;  // same word: broadcast
-            if (!count[bank]) first_addr[bank] = addr;
-            if (++count[bank] > worst) worst = count[bank];
-        }
-        cost += worst;
+    ConflictTable &e = memo[(h >> 7) & 511];
+    if (memcmp(e.key, key, sizeof key) != 0) {
+        memcpy(e.key, key, sizeof key);
+        e.valid = 0;
     }
-    memcpy(e.k, key, sizeof key);
-    e.pitch = pitch;
-    e.layout = layout;
-    e.value = (float)cost / (float)PITCH_SAMPLES;
-    return e.value;
+    const unsigned todo = need & ~e.valid;
+    if (!todo) return e;
+    short oy[N_LAYOUTS][PITCH_SAMPLES][32], ox[N_LAYOUTS][PITCH_SAMPLES][32];
+    for (int layout = 0; layout < N_LAYOUTS; layout++)
+        for (int sample = 0; sample < PITCH_SAMPLES; sample++) {
+            // tiles spread over the image (different sub-texel phases), a different warp of the CTA in each
+            // (irregular positions: an arithmetic progression of tiles resonates with the lattice at some angles)
+            static const unsigned char T1[16] = {1, 14, 5, 27, 9, 2, 19, 30, 11, 23, 4, 16, 7, 21, 13, 26};
+            static const unsigned char T2[16] = {3, 8, 29, 12, 1, 22, 17, 6, 25, 10, 31, 15, 20, 2, 28, 18};
+            const int a1_0 = 16 * T1[sample & 15], a2_0 = 16 * T2[sample & 15];
+            const float y0 = floorf(inplane_coord(M.r[1], (float)a1_0, (float)a2_0) - 0.5f);
+            const float x0 = floorf(inplane_coord(M.r[2], (float)a1_0, (float)a2_0) - 0.5f);
+            for (int lane = 0; lane < 32; lane++) {
+                int ty, tx;
+                lane_pos(32 * ((5 * sample + (sample >> 3)) & 7) + lane, layout, ty, tx);
+                const int a1 = a1_0 + ty, a2 = a2_0 + tx;
+                // relative to the tile's first column: small numbers whatever the translation is
+                oy[layout][sample][lane] = (short)(floorf(inplane_coord(M.r[1], (float)a1, (float)a2) - 0.5f) - y0);
+                ox[layout][sample][lane] = (short)(floorf(inplane_coord(M.r[2], (float)a1, (float)a2) - 0.5f) - x0);
+            }
+        }
+    for (int pitch = PITCH_LO; pitch <= PITCH_HI; pitch++) {
+        if (!(todo >> (pitch - PITCH_LO) & 1u)) continue;
+        for (int layout = 0; layout < N_LAYOUTS; layout++) {
+            int cost = 0;
+            for (int sample = 0; sample < PITCH_SAMPLES; sample++) {
+                unsigned char count[32] = {0};
+                int first_addr[32];
+                int worst = 0;
+                for (int lane = 0; lane < 32; lane++) {
+                    const int addr = oy[layout][sample][lane] * pitch + ox[layout][sample][lane] + (1 << 20);
+                    const int bank = addr & 31;
+                    if (count[bank] && first_addr[bank] == addr) continue;  // same word: broadcast
+                    if (!count[bank]) first_addr[bank] = addr;
+                    if (++count[bank] > worst) worst = count[bank];
+                }
+                cost += worst;
+            }
+            e.wf[pitch - PITCH_LO][layout] = (float)cost / (float)PITCH_SAMPLES;
+        }
+    }
+    e.valid |= todo;
+    return e;
+}
+float pitch_conflicts(const VtMat &M, int pitch, int layout)
+{
+    return conflict_table(M, 1u << (pitch - PITCH_LO)).wf[pitch - PITCH_LO][layout];
 }
 template <int INTERP>
 float pitch_cost(const VtMat &M, int pitch, int layout)
 {
     const float wf = pitch_conflicts(M, pitch, layout);
-    const float pen = layout == 0 ? 0.0f : (layout == 1 ? 0.02f : 0.12f);
+    // (a little more than measured -- 0.02 / 0.12 -- so that sampling noise in `wf` does not flip a tie away from 2 x 16)
+    const float pen = layout == 0 ? 0.0f : (layout == 1 ? 0.05f : 0.15f);
     if (INTERP == VT_LINEAR) return fmaxf(0.40f, 0.19f + 0.0045f * (float)pitch + 0.06f * wf) + pen;
     const float lds = 0.30f + 0.45f * wf;
     return (INTERP == VT_CUBIC_TEX ? fmaxf(1.13f, lds) : lds) + pen;
@@ -649,10 +678,20 @@ bool tma_ok(const VtResampleParams &P)
     return (P.src_row % 4) == 0 && (P.src_plane % 4) == 0 && ((uintptr_t)P.src % 16) == 0;
 }
 
-template <int INTERP, int RULE>
-int launch2(VtResampleParams &P, cudaStream_t st)
+// Everything the host decides about a launch, without touching the device (also exported for inspection and for the
+// CPU-side tests: vt_slice_plan).
+struct SlicePlan {
+    int chunks, z_chunk;  // z-chunks per column tile and their length in output planes
+    bool tma;             // TMA box staging (16-byte aligned source rows) or per-element cp.async
+    int box_w, box_h;     // TMA box = shared-memory pitch x rows (TMA variant)
+    float cost;           // modelled SM cycles per voxel and plane, summed over the matrices (TMA variant)
+    unsigned char aux[VT_MAX_BATCH];  // per matrix: warp shape << 6 | pitch (pitch only in the cp.async variant)
+};
+
+template <int INTERP>
+int plan_slice(const VtResampleParams &P, int sms, SlicePlan &L)
 {
-    constexpr int PPS = Taps<INTERP>::PPS, NSTAGE = Taps<INTERP>::NSTAGE;
+    constexpr int PPS = Taps<INTERP>::PPS;
     const int nz = P.z_end - P.z_begin;
     const int tiles = ((P.o1 + TS - 1) / TS) * ((P.o2 + TS - 1) / TS);
     // z-chunks: a CTA marches z_chunk + WARM planes and pays a fixed start-up (weights, descriptor fetch, first
@@ -662,11 +701,9 @@ int launch2(VtResampleParams &P, cudaStream_t st)
     constexpr int WARM = Taps<INTERP>::PLANES_BEFORE + Taps<INTERP>::PLANES_AFTER;
     constexpr int RESIDENT = INTERP == VT_LINEAR ? 4 : 3;  // __launch_bounds__ of the kernel
     constexpr int STARTUP = 8;
-    int sms = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long slots = (long long)sms * RESIDENT, per_chunk = (long long)tiles * P.n_mats;
     int chunks = 1, z_chunk = nz;
-    long long best_cost = -1;
+    long long best_chunk_cost = -1;
     // Long marches over large planes lose the L2 reuse between neighbouring tiles (their footprints overlap ~3.4x): CTAs
     // drift apart along z, and once the drift times the plane size exceeds the L2 the overlap is fetched from HBM again.
     // Measured at 1024^3 linear, 45 degrees (4 MB planes): 1 chunk of 1024 planes 3.49 ms, 2: 3.08, 4: 2.25, 8: 1.73,
@@ -683,8 +720,8 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         const int cc = (nz + zc - 1) / zc;
         const long long waves = (per_chunk * cc + slots - 1) / slots;
         const long long cost = waves * (zc + WARM + STARTUP);
-        if (best_cost < 0 || cost < best_cost) {
-            best_cost = cost;
+        if (best_chunk_cost < 0 || cost < best_chunk_cost) {
+            best_chunk_cost = cost;
             chunks = cc;
             z_chunk = zc;
         }
@@ -695,12 +732,13 @@ int launch2(VtResampleParams &P, cudaStream_t st)
             chunks = (nz + z_chunk - 1) / z_chunk;
         }
     }
-    dim3 grid(tiles, chunks, P.n_mats);
     if (chunks > 65535 || P.n_mats > 65535) return VT_ERR_UNSUPPORTED;
-    const bool tma = tma_ok(P) && !(P.flags & VT_STAGE_CP_ASYNC);
-    VtSliceStaging G;
-    memset(&G, 0, sizeof G);
-    if (tma) {
+    L.chunks = chunks;
+    L.z_chunk = z_chunk;
+    L.tma = tma_ok(P) && !(P.flags & VT_STAGE_CP_ASYNC);
+    L.box_w = L.box_h = 0;
+    L.cost = 0.0f;
+    if (L.tma) {
         // box: the largest footprint of the batch (+5 texels of filter support / rounding), rows padded to 16 B
         float ext_y = 0.0f, ext_x = 0.0f;
         for (int k = 0; k < P.n_mats; k++) {
@@ -713,6 +751,9 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         int best_w = (need_w + 3 + 3) / 4 * 4;
         float best_cost = 1e30f;
         unsigned char shape[VT_MAX_BATCH];
+        unsigned mask = 0;
+        for (int w = best_w; w <= PITCH_MAX; w += 4) mask |= 1u << (w - PITCH_LO);
+        for (int k = 0; k < P.n_mats; k++) conflict_table(P.mats[k], mask);  // all widths of a matrix in one pass
         for (int w = (need_w + 3 + 3) / 4 * 4; w <= PITCH_MAX; w += 4) {
             float total = 0.0f;
             unsigned char sh[VT_MAX_BATCH];
@@ -735,24 +776,20 @@ int launch2(VtResampleParams &P, cudaStream_t st)
         }
         const char *force = getenv("VT_SLICE_LAYOUT");  // tuning knobs
         for (int k = 0; k < P.n_mats; k++)
-            P.aux[k] = (unsigned char)((force ? atoi(force) % N_LAYOUTS : shape[k]) << 6);
+            L.aux[k] = (unsigned char)((force ? atoi(force) % N_LAYOUTS : shape[k]) << 6);
         if (const char *e = getenv("VT_SLICE_W"))
             if (atoi(e) >= (need_w + 3 + 3) / 4 * 4 && atoi(e) <= PITCH_MAX && atoi(e) % 4 == 0) best_w = atoi(e);
         if (getenv("VT_SLICE_DEBUG"))
             fprintf(stderr, "slice interp %d: need %d x %d, box_w %d, shape[0] %d, cost %.3f\n", INTERP, need_w, need_h, best_w,
-                    (int)(P.aux[0] >> 6), best_cost);
-        G.box_w = best_w;
-        G.box_h = need_h;
-        constexpr bool FIXED = INTERP != VT_LINEAR;  // see the kernel: cubic planes sit at the fixed stride STAGE
-        G.plane_elems = FIXED ? STAGE : G.box_w * G.box_h;  // linear: a box of depth PPS lands as PPS densely packed planes
-        G.stage_bytes = ((unsigned)(G.plane_elems * PPS * 4) + 127u) & ~127u;
-        const unsigned long long gdim[3] = {(unsigned long long)P.s2, (unsigned long long)P.s1, (unsigned long long)P.s0};
-        const unsigned long long gstr[2] = {(unsigned long long)P.src_row * 4, (unsigned long long)P.src_plane * 4};
-        const unsigned box[3] = {(unsigned)G.box_w, (unsigned)G.box_h, FIXED ? 1u : (unsigned)PPS};
-        const int rc = vt_encode_tmap_3d(&G.tmap, P.src, gdim, gstr, box);
-        if (rc) return rc;
+                    (int)(L.aux[0] >> 6), best_cost);
+        L.box_w = best_w;
+        L.box_h = need_h;
+        L.cost = best_cost;
     } else {
+        unsigned mask = 0;
+        for (int pitch = PITCH_MIN; pitch <= PITCH_MAX; pitch++) mask |= 1u << (pitch - PITCH_LO);
         for (int k = 0; k < P.n_mats; k++) {
+            conflict_table(P.mats[k], mask);
             int best = 33, best_layout = 0;
             float best_cost = 1e30f;
             for (int pitch = PITCH_MIN; pitch <= PITCH_MAX; pitch++)
@@ -766,8 +803,40 @@ int launch2(VtResampleParams &P, cudaStream_t st)
                         best_layout = layout;
                     }
                 }
-            P.aux[k] = (unsigned char)(best | (best_layout << 6));
+            L.aux[k] = (unsigned char)(best | (best_layout << 6));
         }
+    }
+    return VT_OK;
+}
+
+template <int INTERP, int RULE>
+int launch2(VtResampleParams &P, cudaStream_t st)
+{
+    constexpr int PPS = Taps<INTERP>::PPS, NSTAGE = Taps<INTERP>::NSTAGE;
+    const int tiles = ((P.o1 + TS - 1) / TS) * ((P.o2 + TS - 1) / TS);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    SlicePlan L;
+    int rc = plan_slice<INTERP>(P, sms, L);
+    if (rc) return rc;
+    const int z_chunk = L.z_chunk;
+    const bool tma = L.tma;
+    memcpy(P.aux, L.aux, sizeof L.aux);
+    dim3 grid(tiles, L.chunks, P.n_mats);
+    VtSliceStaging G;
+    memset(&G, 0, sizeof G);
+    if (tma) {
+        G.box_w = L.box_w;
+        G.box_h = L.box_h;
+        constexpr bool FIXED = INTERP != VT_LINEAR;  // see the kernel: cubic planes sit at the fixed stride STAGE
+        G.plane_elems = FIXED ? STAGE : G.box_w * G.box_h;  // linear: a box of depth PPS lands as PPS densely packed planes
+        G.stage_bytes = ((unsigned)(G.plane_elems * PPS * 4) + 127u) & ~127u;
+        const unsigned long long gdim[3] = {(unsigned long long)P.s2, (unsigned long long)P.s1, (unsigned long long)P.s0};
+        const unsigned long long gstr[2] = {(unsigned long long)P.src_row * 4, (unsigned long long)P.src_plane * 4};
+        const unsigned box[3] = {(unsigned)G.box_w, (unsigned)G.box_h, FIXED ? 1u : (unsigned)PPS};
+        rc = vt_encode_tmap_3d(&G.tmap, P.src, gdim, gstr, box);
+        if (rc) return rc;
+    } else {
         G.plane_elems = STAGE;
         G.stage_bytes = PPS * STAGE * 4;
     }
@@ -1020,6 +1089,32 @@ int project1(VtResampleParams &P, float *ws, cudaStream_t st)
 }  // namespace
 
 int vt_slice_supported(const VtResampleParams &P, int interp) { return slice_ok(P, interp) ? 1 : 0; }
+
+// host-only: what vt_launch_slice would decide for these parameters on a GPU with `sms` multiprocessors
+int vt_slice_plan_impl(const VtResampleParams &P, int interp, int sms, int *chunks, int *z_chunk, int *tma, int *box_w,
+                       int *box_h, int *shapes, int *pitches)
+{
+    if (!slice_ok(P, interp)) return VT_ERR_UNSUPPORTED;
+    SlicePlan L;
+    int rc;
+    switch (interp) {
+        case VT_LINEAR: rc = plan_slice<VT_LINEAR>(P, sms, L); break;
+        case VT_CUBIC_TEX: rc = plan_slice<VT_CUBIC_TEX>(P, sms, L); break;
+        case VT_CUBIC_SIMPLE: rc = plan_slice<VT_CUBIC_SIMPLE>(P, sms, L); break;
+        default: return VT_ERR_INVALID_ARG;
+    }
+    if (rc) return rc;
+    *chunks = L.chunks;
+    *z_chunk = L.z_chunk;
+    *tma = L.tma ? 1 : 0;
+    *box_w = L.box_w;
+    *box_h = L.box_h;
+    for (int k = 0; k < P.n_mats; k++) {
+        if (shapes) shapes[k] = L.aux[k] >> 6;
+        if (pitches) pitches[k] = L.tma ? L.box_w : (L.aux[k] & 63);
+    }
+    return VT_OK;
+}
 
 int vt_launch_slice(VtResampleParams &P, int interp, cudaStream_t st)
 {
