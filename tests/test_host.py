@@ -206,6 +206,12 @@ def test_slice_planner_decisions_without_a_gpu():
     mats = [rot(256, a) for a in range(0, 180, 6)]
     p1, p2 = N.slice_plan((256,) * 3, mats, N.CUBIC_SIMPLE), N.slice_plan((256,) * 3, mats, N.CUBIC_SIMPLE)
     assert p1 == p2 and len(p1['shapes']) == 30 and len(set(p1['pitches'])) == 1 and len(set(p1['shapes'])) > 1
+    # strong in-plane magnification: narrow footprints, boxes down to 12 texels wide (the tables cover 12..40)
+    c64 = np.divide(np.subtract((64,) * 3, 1), 2, dtype=np.float32)
+    for sc, wmax in ((0.1, 12), (0.3, 16)):
+        zoom = vt.utils.transform_matrix(rotation=(0, 20, 0), rotation_order='rzxz', scale=(1.0, sc, sc), center=c64)
+        pz = N.slice_plan((64,) * 3, zoom, N.CUBIC_SIMPLE)
+        assert pz['box_w'] % 4 == 0 and 12 <= pz['box_w'] <= 40 and pz['box_w'] >= wmax and pz['shapes'][0] in (0, 1, 2)
     # rows that are not multiples of 16 bytes: per-element cp.async staging, a pitch per matrix in 32..40
     odd = N.slice_plan((40, 50, 61), rot(50, 30), N.LINEAR, src_strides=(61, 50 * 61))
     assert not odd['tma'] and 32 <= odd['pitches'][0] <= 40

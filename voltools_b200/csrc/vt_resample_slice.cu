@@ -587,7 +587,9 @@ bool slice_ok(const VtResampleParams &P, int interp)
 //      linear         max(0.40, 0.19 + 0.0045 * pitch + 0.06 * wavefronts)   (L2 -> SM traffic grows with the box width)
 //   + 0.02 (4 x 8) / 0.12 (8 x 4) measured: a warp's stores cover 4 or 8 rows instead of 2.
 constexpr int PITCH_SAMPLES = 16;
-constexpr int PITCH_LO = 24, PITCH_HI = PITCH_MAX;  // pitches the tables cover (bit p - PITCH_LO of the masks)
+constexpr int PITCH_LO = 12, PITCH_HI = PITCH_MAX;  // pitches the tables cover (bit p - PITCH_LO of the masks): the
+                                                    // narrowest TMA box (strong magnification) is 12 texels wide
+static_assert(PITCH_HI - PITCH_LO < 32, "one mask bit per pitch");
 
 // Average wavefronts per load of a matrix for every (pitch, warp shape) asked for.  The footprint origins of the sample
 // warps do not depend on the pitch, so they are computed once (the float coordinate recipe is the expensive part) and
