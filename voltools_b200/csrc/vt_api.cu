@@ -421,7 +421,7 @@ int vt_project_strided_f32(const float *d_src, int s0, int s1, int s2, long long
         P.flags = flags;
         int family = choose_family(P, interp, flags);
         if (family < 0) return VT_ERR_UNSUPPORTED;
-        if (family == 3 && have_ws) {
+        if (family == 3 && have_ws && s1 <= 65535 && o1 <= 65535 * 16) {  // (grid limits of the plane-sum / 2-D kernels)
             rc = vt_launch_slice_project(P, interp, (float *)d_workspace, st);
         } else {
             // general matrices (or no workspace): the resampling kernels add into the zeroed image
