@@ -70,7 +70,7 @@ __device__ __forceinline__ float causal_init(const float *e, int n, int step)
 // ---------------------------------------------------------------------------------------------------
 constexpr int RB = 16;   // rows per step
 constexpr int SEG = 16;  // X chunk: samples per thread in the X pass
-constexpr int NBUF = 3;  // staging tiles of the XY kernel
+constexpr int NBUF = 4;  // staging tiles of the XY kernel: Y pass | X pass | in flight | being refilled
 constexpr int HX = 16;   // X halo of interior strips (>= K; a multiple of SEG keeps the Y pass's warps chunk-aligned)
 // powers of the pole: kPow[j] = z^j
 __device__ constexpr float kPow[17] = {1.0000000000e+00f,  -2.6794922352e-01f, 7.1796786384e-02f,  -1.9237893163e-02f,
@@ -187,10 +187,17 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
         sp += (size_t)RB * W;
     };
 
-    // NBUF - 1 steps of rows are in flight ahead of the one being filtered: with 1-2 CTAs per SM a single step
-    // (16 KB) does not cover the HBM latency
+    // The X pass runs ONE STEP AHEAD of the Y pass (software pipeline): in an iteration every thread filters its
+    // (row, chunk) of tile k+1 along x and then sweeps its column of tile k along y, so a step needs one block-wide
+    // barrier instead of two and the two passes of different warps overlap (the kernel was waiting on its barriers, not
+    // on issue slots: packing the Y pass in FFMA2 changed nothing).  Tiles: k (Y) | k+1 (X) | k+2 (in flight) | k+3
+    // (being refilled): two steps of rows are in flight ahead of the X pass -- with 1-2 CTAs per SM a single step
+    // (16 KB) does not cover the HBM latency.
 #pragma unroll
     for (int i = 0; i < NBUF - 1; i++) stage(ra + i * RB, i);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NBUF - 2) : "memory");
+    __syncthreads();  // tile 0 has landed
+    if (rb - ra > 0) x_pass<L>(smem + xrow * P + xc * SEG, xc, cf, xa == 0);
     float cp[K + RB];  // causal Y values of rows [r0 - K, r0 + RB)
 #pragma unroll
     for (int k = 0; k < K + RB; k++) cp[k] = 0.0f;
@@ -199,11 +206,11 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
 
     for (int r0 = ra;; r0 += RB, buf = buf + 1 == NBUF ? 0 : buf + 1) {
         const int nrows = min(RB, rb - r0);  // <= 0 once the rows are exhausted (flush steps)
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(NBUF - 2) : "memory");
-        __syncthreads();  // tile[buf] has landed; the previous step's column sweep is done with its tile
+        const int nb = buf + 1 == NBUF ? 0 : buf + 1;  // tile of the next step
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(NBUF - 3) : "memory");
+        __syncthreads();  // tile[nb] has landed; tile[buf] is X-filtered; the previous step's column sweep is done
         stage(r0 + (NBUF - 1) * RB, buf == 0 ? NBUF - 1 : buf - 1);  // refills the previous step's tile
-        if (nrows > 0) x_pass<L>(smem + (buf * RB + xrow) * P + xc * SEG, xc, cf, xa == 0);
-        __syncthreads();
+        if (rb - (r0 + RB) > 0) x_pass<L>(smem + (nb * RB + xrow) * P + xc * SEG, xc, cf, xa == 0);
         // ---- Y: one thread per column, rows r0 .. r0+nrows-1 enter the window ----
         const int w0 = r0 - K;  // row of cp[0]
         if (has_col) {
