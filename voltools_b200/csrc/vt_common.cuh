@@ -150,6 +150,10 @@ __device__ __forceinline__ void vt_mbar_expect_tx(unsigned bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void vt_mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool vt_mbar_try_wait(unsigned bar, unsigned parity)
 {
     unsigned ok;
