@@ -12,6 +12,9 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.jso
 cat gpurun_out/bench_ref.json
 python bench.py --workload modes --steps 3 --warmup 2 > gpurun_out/modes.json 2> gpurun_out/modes.err; echo "modes rc=$?"
 cat gpurun_out/modes.json
+python bench.py --workload project --steps 5 --warmup 2 > gpurun_out/project.json 2> gpurun_out/project.err; echo "project rc=$?"
+python tools/prefilter_probe.py 250 256 512 > gpurun_out/prefilter_probe.log 2>&1; echo "prefilter probe rc=$?"
+python tools/sweep_probe.py 256 > gpurun_out/sweep_probe.log 2>&1; echo "sweep probe rc=$?"
 CMD="python bench.py --steps 1 --warmup 1 --batch 2 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
