@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 4
+#define VT_ABI_VERSION 5
 
 /* status codes: 0 ok; 1..99 library errors; 1000+e = cudaError_t e; 2000+e = CUresult e */
 #define VT_OK 0
@@ -154,6 +154,37 @@ int vt_tex_destroy(vt_tex *tex);
  * vt_affine_f32 (VT_WEIGHTS_EXACT and VT_CUBIC_SIMPLE are not available here) */
 int vt_affine_tex_f32(const vt_tex *tex, float *d_dst, int o0, int o1, int o2, long long dst_batch_stride,
                       const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin, int z_end, void *stream);
+
+/*
+ * Slice4 family: the `transform` kernel launch (voltools/transforms.py:212, volume.py:78) for matrices that leave one
+ * axis m alone -- M[m] = e_m + integer shift, M[r][m] = 0 otherwise: every rotation about axis m through the centre --
+ * on a sampled volume stored in the "Z4" layout of that axis,
+ *        L[g][y][x][j] = V[index 4g+j along axis m][y][x],   j = 0..3,  zero past the end of axis m,
+ * (y, x) = the two other axes in ascending order; vt_z4_bytes() bytes, 16-byte aligned.  The layout takes the place of
+ * the reference's CUDA array (voltools/transforms.py:184-199): one TMA box delivers four consecutive planes per texel
+ * and every tap is a 16-byte shared-memory load serving four output planes.
+ *   vt_pack_z4_f32       plain (possibly row-padded) volume -> Z4 layout of `axis` (one 8 B/voxel pass; the reference
+ *                        pays the same pass for its array copy, transforms.py:197-199)
+ *   vt_prefilter_z4_f32  vt_prefilter_f32 (variant 0) whose Z sweep writes the Z4 layout of axis 0 directly; the
+ *                        caller-owned workspace holds d0*d1*d2 floats
+ *   vt_z4_axis_of        *axis = the lowest axis every matrix of the batch leaves alone in the required way, or -1
+ *   vt_affine_z4_f32     arguments as vt_affine_f32; VT_ERR_UNSUPPORTED if a matrix does not leave `axis` alone.
+ *                        Results are bit-identical to vt_affine_f32's slice kernels.
+ *   vt_z4_plan           host-only introspection (no device is touched): chunks along the march axis, TMA box, and per
+ *                        matrix the quarter-warp shape (0..3 = 1x8, 2x4, 4x2, 8x1 columns per 8 lanes), the
+ *                        shared-memory pitch in texels and the simulated wavefronts per quarter-warp load
+ */
+size_t vt_z4_bytes(int s0, int s1, int s2, int axis);
+int vt_pack_z4_f32(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,
+                   float *d_dst4, int axis, int device, void *stream);
+int vt_prefilter_z4_f32(const float *d_src, float *d_dst4, int d0, int d1, int d2, void *d_workspace, size_t workspace_bytes,
+                        int device, void *stream);
+int vt_z4_axis_of(int s0, int s1, int s2, int o0, int o1, int o2, const float *h_mats, int n_mats, int interp, int *axis);
+int vt_affine_z4_f32(const float *d_src4, int axis, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
+                     long long dst_batch_stride, const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin,
+                     int z_end, int device, void *stream);
+int vt_z4_plan(int axis, int s0, int s1, int s2, int o0, int o1, int o2, const float *h_mats, int n_mats, int interp, int sms,
+               int *chunks, int *m_chunk, int *box_w, int *box_h, int *shapes, int *pitches, float *wavefronts);
 
 /*
  * Rotate-and-project: the transformed volume summed over axis 0, without ever writing the volume -- what

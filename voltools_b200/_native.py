@@ -71,12 +71,20 @@ def lib():
         L.vt_host_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
         L.vt_host_ctx_destroy.argtypes = [_vp]
         L.vt_host_affine_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f32p, _i, _i, ctypes.c_uint]
+        L.vt_z4_bytes.restype = ctypes.c_size_t
+        L.vt_z4_bytes.argtypes = [_i, _i, _i, _i]
+        L.vt_pack_z4_f32.argtypes = [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i, _vp]
+        L.vt_prefilter_z4_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, ctypes.c_size_t, _i, _vp]
+        L.vt_z4_axis_of.argtypes = [_i, _i, _i, _i, _i, _i, _f32p, _i, _i, ctypes.POINTER(_i)]
+        L.vt_affine_z4_f32.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, ctypes.c_longlong, _f32p, _i, _i,
+                                       ctypes.c_uint, _i, _i, _i, _vp]
+        L.vt_z4_plan.argtypes = [_i, _i, _i, _i, _i, _i, _i, _f32p, _i, _i, _i] + [ctypes.POINTER(_i)] * 6 + [_f32p]
         L.vt_launch_count.restype = ctypes.c_longlong
         L.vt_profile_enable.argtypes = [_i]
         L.vt_profile_kernel_name.restype = ctypes.c_char_p
         L.vt_profile_kernel_name.argtypes = [_i]
         L.vt_profile_read.argtypes = [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
-        if L.vt_abi_version() != 4:
+        if L.vt_abi_version() != 5:
             raise RuntimeError('libvoltools_b200.so ABI version mismatch')
         _lib = L
     return _lib
@@ -134,7 +142,11 @@ def prefilter(src_ptr, shape, device=-1, stream=0, variant=0, dst_ptr=None, dst_
         dst_strides = (int(shape[2]), int(shape[1]) * int(shape[2]))
     row, plane = int(dst_strides[0]), int(dst_strides[1])
     ws, ws_ptr, ws_bytes = None, None, 0
-    if workspace and variant == 0 and dst != src_ptr and int(shape[0]) >= 128:
+    if workspace is not True and workspace is not False and workspace is not None:  # a caller-owned scratch tensor
+        ws, ws_ptr, ws_bytes = workspace, workspace.data_ptr(), workspace.numel() * workspace.element_size()
+        if ws_bytes < lib().vt_prefilter_workspace_bytes(shape[0], shape[1], shape[2], row, plane):
+            ws_ptr, ws_bytes = None, 0
+    elif workspace and variant == 0 and dst != src_ptr and int(shape[0]) >= 128:
         import torch
         ws_bytes = lib().vt_prefilter_workspace_bytes(shape[0], shape[1], shape[2], row, plane)
         dev = torch.cuda.current_device() if device < 0 else device
@@ -165,6 +177,79 @@ def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, ba
     check(lib().vt_affine_strided_f32(src_ptr, *map(int, src_shape), int(src_strides[0]), int(src_strides[1]), dst_ptr,
                                       *map(int, dst_shape), batch_stride, mp, len(m), interp, flags, z0, z1, device,
                                       stream))
+
+
+# ---- slice4 family: Z4 layout (vt_resample_z4.cu) -----------------------------------------------------------
+import os as _os
+
+
+def z4_wanted(interp, resident):
+    """Policy: does a slice-family launch of `interp` go to the slice4 kernels?  A resident volume always (the Z4
+    copy is packed once); a one-shot call when the pack pass (8 B/voxel) is paid back by the faster kernel: the cubic
+    modes (measured).  VT_Z4=0/1 forces it off/on (A/B measurements)."""
+    force = _os.environ.get('VT_Z4')
+    if force is not None:
+        return force != '0'
+    return True if resident else interp != LINEAR
+
+
+def z4_bytes(shape, axis):
+    return lib().vt_z4_bytes(*map(int, shape), int(axis))
+
+
+def pack_z4(src_ptr, shape, dst4_ptr, axis, device=-1, stream=0, src_strides=None):
+    """Plain volume (src_strides = (row, plane) in elements, default dense) -> Z4 layout of `axis`."""
+    if src_strides is None:
+        src_strides = (int(shape[2]), int(shape[1]) * int(shape[2]))
+    check(lib().vt_pack_z4_f32(src_ptr, *map(int, shape), int(src_strides[0]), int(src_strides[1]), dst4_ptr, int(axis),
+                               device, stream))
+
+
+def prefilter_z4(src_ptr, shape, dst4_ptr, ws_ptr, ws_bytes, device=-1, stream=0):
+    """Samples -> coefficients in the Z4 layout of axis 0 (windowed prefilter; workspace of prod(shape) floats)."""
+    check(lib().vt_prefilter_z4_f32(src_ptr, dst4_ptr, *map(int, shape), ws_ptr, ws_bytes, device, stream))
+
+
+def z4_axis(src_shape, dst_shape, matrices, interp):
+    """The axis (0..2) every matrix leaves alone in the way the slice4 kernels need, or -1."""
+    m, mp = _mats(matrices)
+    ax = _i(-1)
+    check(lib().vt_z4_axis_of(*map(int, src_shape), *map(int, dst_shape), mp, len(m), interp, ctypes.byref(ax)))
+    return ax.value
+
+
+def affine_z4(src4_ptr, axis, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, batch_stride=None, z_range=None,
+              device=-1, stream=0):
+    m, mp = _mats(matrices)
+    if batch_stride is None:
+        batch_stride = int(dst_shape[0]) * int(dst_shape[1]) * int(dst_shape[2])
+    z0, z1 = (0, dst_shape[0]) if z_range is None else z_range
+    check(lib().vt_affine_z4_f32(src4_ptr, int(axis), *map(int, src_shape), dst_ptr, *map(int, dst_shape), batch_stride,
+                                 mp, len(m), interp, flags, z0, z1, device, stream))
+
+
+def z4_plan(shape, matrices, interp, axis, sms=148):
+    """Host-only: the slice4 family's launch decisions (vt_z4_plan) as a dict, or None if unsupported."""
+    m, mp = _mats(matrices)
+    out = [_i(0) for _ in range(4)]
+    shapes, pitches, wf = (_i * len(m))(), (_i * len(m))(), (ctypes.c_float * len(m))()
+    rc = lib().vt_z4_plan(int(axis), *map(int, shape), *map(int, shape), mp, len(m), interp, sms,
+                          *[ctypes.byref(o) for o in out], shapes, pitches, wf)
+    if rc == 2:
+        return None
+    check(rc)
+    return {'chunks': out[0].value, 'm_chunk': out[1].value, 'box_w': out[2].value, 'box_h': out[3].value,
+            'shapes': list(shapes), 'pitches': list(pitches), 'wavefronts': [float(v) for v in wf]}
+
+
+def download(t, stream=0):
+    """Device tensor -> numpy through a pinned staging buffer (a pageable destination makes cudaMemcpy stage through
+    the driver's small bounce buffer at a fraction of the link rate): the `.get()` of transforms.py:223."""
+    import torch
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
 
 
 def project_workspace_bytes(src_shape):

@@ -28,6 +28,17 @@ int vt_prefilter_xy_range(const float *d_src, float *d_dst, int d0, int d1, int 
 int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, int z0, int z1, int chunks,
                          cudaStream_t st);  // vt_prefilter_win.cu
 
+int vt_prefilter_z_range_z4(const float *d_src, float *d_dst4, int d0, size_t cols, int z0, int z1, int chunks,
+                            cudaStream_t st);  // vt_prefilter_win.cu
+int vt_z4_axis(const VtResampleParams &P, int interp);                                                     // vt_resample_z4.cu
+size_t vt_z4_floats(int s0, int s1, int s2, int axis);                                                     // vt_resample_z4.cu
+int vt_pack_z4_impl(const float *d_src, int s0, int s1, int s2, long long row, long long plane, float *d_dst4, int axis,
+                    cudaStream_t st);                                                                      // vt_resample_z4.cu
+int vt_z4_plan_impl(const VtResampleParams &P, int axis, int interp, int sms, int *chunks, int *m_chunk, int *box_w,
+                    int *box_h, int *shapes, int *pitches, float *wavefronts);                             // vt_resample_z4.cu
+int vt_launch_z4(const VtResampleParams &P, const float *d_src4, int axis, int interp, cudaStream_t st);   // vt_resample_z4.cu
+bool vt_z4_axis_accepts(const VtResampleParams &P, int axis);                                              // vt_resample_z4.cu
+
 struct vt_tex;
 int vt_launch_tex(const VtResampleParams &P, const vt_tex *t, int interp, cudaStream_t st);            // vt_resample_tex.cu
 int vt_tex_create_impl(int s0, int s1, int s2, int device, vt_tex **out);                              // vt_resample_tex.cu
@@ -61,7 +72,8 @@ long long g_prof_n[VT_K_COUNT];
 const char *const g_prof_names[VT_K_COUNT] = {
     "prefilter_x", "prefilter_y", "prefilter_z", "prefilter_fused", "gather_linear", "gather_cubic_tex",
     "gather_cubic_simple", "brick_linear", "brick_cubic_tex", "brick_cubic_simple", "slice_linear",
-    "slice_cubic_tex", "slice_cubic_simple", "tex_linear", "tex_cubic", "plane_sum", "project_2d"};
+    "slice_cubic_tex", "slice_cubic_simple", "tex_linear", "tex_cubic", "plane_sum", "project_2d", "z4_linear",
+    "z4_cubic_tex", "z4_cubic_simple", "pack_z4"};
 
 void prof_drain_locked()
 {
@@ -384,6 +396,98 @@ int vt_affine_f32(const float *d_src, int s0, int s1, int s2, float *d_dst, int 
 {
     return vt_affine_strided_f32(d_src, s0, s1, s2, s2, (long long)s1 * s2, d_dst, o0, o1, o2, dst_batch_stride, h_mats,
                                  n_mats, interp, flags, z_begin, z_end, device, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// slice4 family: the Z4 layout (vt_resample_z4.cu)
+// ---------------------------------------------------------------------------------------------------
+size_t vt_z4_bytes(int s0, int s1, int s2, int axis)
+{
+    if (s0 < 1 || s1 < 1 || s2 < 1 || axis < 0 || axis > 2) return 0;
+    return vt_z4_floats(s0, s1, s2, axis) * sizeof(float);
+}
+
+int vt_pack_z4_f32(const float *d_src, int s0, int s1, int s2, long long src_row_stride, long long src_plane_stride,
+                   float *d_dst4, int axis, int device, void *stream)
+{
+    if (!d_src || !d_dst4 || s0 < 1 || s1 < 1 || s2 < 1 || axis < 0 || axis > 2) return VT_ERR_INVALID_ARG;
+    if (src_row_stride < s2 || src_plane_stride < src_row_stride * s1 || ((uintptr_t)d_dst4 % 16) != 0) return VT_ERR_INVALID_ARG;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    return vt_pack_z4_impl(d_src, s0, s1, s2, src_row_stride, src_plane_stride, d_dst4, axis, (cudaStream_t)stream);
+}
+
+int vt_prefilter_z4_f32(const float *d_src, float *d_dst4, int d0, int d1, int d2, void *d_workspace, size_t workspace_bytes,
+                        int device, void *stream)
+{
+    if (!d_src || !d_dst4 || !d_workspace || d0 < 1 || d1 < 1 || d2 < 1) return VT_ERR_INVALID_ARG;
+    if (workspace_bytes < (size_t)d0 * d1 * d2 * sizeof(float) || ((uintptr_t)d_dst4 % 16) != 0) return VT_ERR_INVALID_ARG;
+    if (d_workspace == (void *)d_src || d_workspace == (void *)d_dst4 || d_src == d_dst4) return VT_ERR_INVALID_ARG;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long plane = (long long)d1 * d2;
+    int rc = vt_prefilter_xy_range(d_src, (float *)d_workspace, d0, d1, d2, d2, plane, 0, d0, st);
+    if (rc) return rc;
+    return vt_prefilter_z_range_z4((const float *)d_workspace, d_dst4, d0, (size_t)plane, 0, d0, 0, st);
+}
+
+int vt_z4_axis_of(int s0, int s1, int s2, int o0, int o1, int o2, const float *h_mats, int n_mats, int interp, int *axis)
+{
+    if (!axis || !h_mats || n_mats < 1) return VT_ERR_INVALID_ARG;
+    VtResampleParams P;
+    float dummy;
+    int rc = fill_params(P, &dummy, s0, s1, s2, s2, (long long)s1 * s2, &dummy, o0, o1, o2, 0, 0, 0, o0);
+    if (rc) return rc;
+    (void)interp;
+    unsigned mask = 7u;  // axes every chunk of VT_MAX_BATCH matrices accepts
+    for (int first = 0; first < n_mats && mask; first += VT_MAX_BATCH) {
+        copy_mats(P, h_mats, first, (n_mats - first) < VT_MAX_BATCH ? (n_mats - first) : VT_MAX_BATCH);
+        for (int a = 0; a < 3; a++)
+            if ((mask >> a & 1u) && !vt_z4_axis_accepts(P, a)) mask &= ~(1u << a);
+    }
+    *axis = (mask & 1u) ? 0 : ((mask & 2u) ? 1 : ((mask & 4u) ? 2 : -1));
+    return VT_OK;
+}
+
+int vt_affine_z4_f32(const float *d_src4, int axis, int s0, int s1, int s2, float *d_dst, int o0, int o1, int o2,
+                     long long dst_batch_stride, const float *h_mats, int n_mats, int interp, unsigned flags, int z_begin,
+                     int z_end, int device, void *stream)
+{
+    if (!h_mats || n_mats < 0 || !d_src4 || axis < 0 || axis > 2) return VT_ERR_INVALID_ARG;
+    if (interp != VT_LINEAR && interp != VT_CUBIC_TEX && interp != VT_CUBIC_SIMPLE) return VT_ERR_INVALID_ARG;
+    if (n_mats == 0) return VT_OK;
+    VtResampleParams P;
+    int rc = fill_params(P, d_src4, s0, s1, s2, s2, (long long)s1 * s2, d_dst, o0, o1, o2, dst_batch_stride, flags, z_begin,
+                         z_end);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    for (int first = 0; first < n_mats; first += VT_MAX_BATCH) {
+        const int count = (n_mats - first) < VT_MAX_BATCH ? (n_mats - first) : VT_MAX_BATCH;
+        copy_mats(P, h_mats, first, count);
+        P.dst = d_dst + (size_t)first * dst_batch_stride;
+        // the batch must leave `axis` alone (any of the axes it leaves alone will do)
+        if (!vt_z4_axis_accepts(P, axis)) return VT_ERR_UNSUPPORTED;
+        rc = vt_launch_z4(P, d_src4, axis, interp, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return VT_OK;
+}
+
+int vt_z4_plan(int axis, int s0, int s1, int s2, int o0, int o1, int o2, const float *h_mats, int n_mats, int interp, int sms,
+               int *chunks, int *m_chunk, int *box_w, int *box_h, int *shapes, int *pitches, float *wavefronts)
+{
+    if (!h_mats || n_mats < 1 || n_mats > VT_MAX_BATCH || !chunks || !m_chunk || !box_w || !box_h || sms < 1 || axis < 0 ||
+        axis > 2)
+        return VT_ERR_INVALID_ARG;
+    VtResampleParams P;
+    float dummy;
+    int rc = fill_params(P, &dummy, s0, s1, s2, s2, (long long)s1 * s2, &dummy, o0, o1, o2, 0, 0, 0, o0);
+    if (rc) return rc;
+    copy_mats(P, h_mats, 0, n_mats);
+    if (!vt_z4_axis_accepts(P, axis)) return VT_ERR_UNSUPPORTED;
+    return vt_z4_plan_impl(P, axis, interp, sms, chunks, m_chunk, box_w, box_h, shapes, pitches, wavefronts);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -67,6 +67,10 @@ enum VtKernelId {
     VT_K_TEX_CUBIC,
     VT_K_PLANE_SUM,
     VT_K_PROJECT_2D,
+    VT_K_Z4_LINEAR,
+    VT_K_Z4_CUBIC_TEX,
+    VT_K_Z4_CUBIC_SIMPLE,
+    VT_K_PACK_Z4,
     VT_K_COUNT
 };
 struct VtProf {

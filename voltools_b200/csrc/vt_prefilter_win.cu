@@ -314,12 +314,35 @@ __device__ __forceinline__ V anticausal_step_v(V next, V c)
     return ZOps<V>::fmac(kPole, next, ZOps<V>::mulc(kNegPole, c));
 }
 
-// src may equal dst (in place): no __restrict__ here.  `cols` = columns per plane in units of V.
+// Z4 output (vt_resample_z4.cu): dst4[g][column] = float4 of planes 4g .. 4g+3 of that column (zeros past the last plane)
 template <typename V>
+__device__ __forceinline__ void store_z4(float4 *d4, size_t group, size_t fcols, size_t col, const V (&o)[4]);
+template <>
+__device__ __forceinline__ void store_z4<float>(float4 *d4, size_t group, size_t fcols, size_t col, const float (&o)[4])
+{
+    d4[group * fcols + col] = make_float4(o[0], o[1], o[2], o[3]);
+}
+template <>
+__device__ __forceinline__ void store_z4<vt_f2>(float4 *d4, size_t group, size_t fcols, size_t col, const vt_f2 (&o)[4])
+{
+    float a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) vt_unpk(o[k], a[k], b[k]);
+    float4 *q = d4 + group * fcols + 2 * col;  // the pair's two columns are adjacent: 32 contiguous bytes
+    q[0] = make_float4(a[0], a[1], a[2], a[3]);
+    q[1] = make_float4(b[0], b[1], b[2], b[3]);
+}
+
+// src may equal dst (in place): no __restrict__ here.  `cols` = columns per plane in units of V.
+// Z4OUT: dst is the Z4 layout of axis 0 (out of place only; z_begin and z_chunk are multiples of 4).
+template <typename V, bool Z4OUT>
 __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const V *src, V *dst, int D, size_t cols, int z_chunk,
                                                                 int z_begin, int z_end)
 {
     using O = ZOps<V>;
+    constexpr size_t VW = sizeof(V) / sizeof(float);
+    float4 *d4 = (float4 *)dst;
+    const size_t fcols = cols * VW;  // float columns per plane
     const size_t col = (size_t)blockIdx.x * Z_THREADS + threadIdx.x;
     if (col >= cols) return;
     const int zc0 = z_begin + blockIdx.y * z_chunk;  // this CTA emits planes [zc0, zc1)
@@ -394,10 +417,22 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const V *src, V 
                 for (int k = 0; k < ZB; k++) raw[k] = zw + ZB + K + k < D ? sp[(size_t)k * stride] : O::zero();
             }
             V c = O::mulc(kAnti, cp[K + ZB - 1]);
+            if constexpr (Z4OUT) {
+                V o[4];
 #pragma unroll
-            for (int k = K + ZB - 2; k >= 0; k--) {
-                c = anticausal_step_v<V>(c, cp[k]);
-                if (k < ZB) dp[(size_t)k * stride] = c;
+                for (int k = K + ZB - 2; k >= 0; k--) {
+                    c = anticausal_step_v<V>(c, cp[k]);
+                    if (k < ZB) {
+                        o[k & 3] = c;
+                        if ((k & 3) == 0) store_z4<V>(d4, (size_t)((zw + k) >> 2), fcols, col, o);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = K + ZB - 2; k >= 0; k--) {
+                    c = anticausal_step_v<V>(c, cp[k]);
+                    if (k < ZB) dp[(size_t)k * stride] = c;
+                }
             }
         } else {
             // causal values of the next ZB planes (look-ahead region moves forward)
@@ -414,12 +449,20 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const V *src, V 
             // anticausal from the last available plane of the window back to zw
             const int last = min(zw + K + ZB, D) - 1;  // plane index where the recursion (re)starts
             V c = O::zero();
+            V o[4];
 #pragma unroll
             for (int k = K + ZB - 1; k >= 0; k--) {
                 const int zz = zw + k;
                 if (zz == last) c = O::mulc(kAnti, cp[k]);
                 else if (zz < last) c = anticausal_step_v<V>(c, cp[k]);
-                if (k < ZB && zz < zc1) dp[(size_t)k * stride] = c;
+                if constexpr (Z4OUT) {
+                    if (k < ZB) {
+                        o[k & 3] = zz < zc1 ? c : O::zero();  // planes past the end of the volume: zeros
+                        if ((k & 3) == 0 && zz < zc1) store_z4<V>(d4, (size_t)(zz >> 2), fcols, col, o);
+                    }
+                } else {
+                    if (k < ZB && zz < zc1) dp[(size_t)k * stride] = c;
+                }
             }
         }
         dp += (size_t)ZB * stride;
@@ -475,7 +518,23 @@ int vt_prefilter_xy_range(const float *d_src, float *d_dst, int d0, int d1, int 
 // Z pass producing planes [z0, z1) of d_dst from the XY-filtered volume d_src (depth d0, `cols` columns per plane).
 // It reads planes [z0 - K, z1 + K) of d_src and nothing else (from plane 0 when z0 <= K).  d_src == d_dst (in place) is only valid for the whole range in one
 // chunk; out of place the range is cut into `chunks` z-chunks (0 = choose).
+static int z_range_impl(const float *d_src, float *d_dst, int d0, size_t cols, int z0, int z1, int chunks, bool z4out,
+                        cudaStream_t st);
 int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, int z0, int z1, int chunks, cudaStream_t st)
+{
+    return z_range_impl(d_src, d_dst, d0, cols, z0, z1, chunks, false, st);
+}
+// the same sweep writing the Z4 layout of axis 0 (vt_resample_z4.cu): d_dst4 holds ceil(d0/4) groups of `cols` float4
+// (cols = the dense plane d1*d2 here: the XY-filtered source must be dense too).  z0 is a multiple of 4 and z1 a
+// multiple of 4 or d0; out of place only.
+int vt_prefilter_z_range_z4(const float *d_src, float *d_dst4, int d0, size_t cols, int z0, int z1, int chunks,
+                            cudaStream_t st)
+{
+    if ((z0 & 3) || ((z1 & 3) && z1 != d0) || d_src == d_dst4) return VT_ERR_INVALID_ARG;
+    return z_range_impl(d_src, d_dst4, d0, cols, z0, z1, chunks, true, st);
+}
+static int z_range_impl(const float *d_src, float *d_dst, int d0, size_t cols, int z0, int z1, int chunks, bool z4out,
+                        cudaStream_t st)
 {
     if (z1 <= z0) return VT_OK;
     // planes the kernel may read: everything up to K past the range (a pipelined caller has not produced the
@@ -483,7 +542,7 @@ int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, 
     const int d_avail = z1 + K < d0 ? z1 + K : d0;
     // two columns per thread (packed pairs) when the planes allow 8-byte accesses
     static const bool no_pack = getenv("VT_Z_SCALAR") != nullptr;  // A/B knob
-    const bool pack = !no_pack && cols % 2 == 0 && ((uintptr_t)d_src % 8) == 0 && ((uintptr_t)d_dst % 8) == 0;
+    const bool pack = !no_pack && cols % 2 == 0 && ((uintptr_t)d_src % 8) == 0 && ((uintptr_t)d_dst % (z4out ? 16 : 8)) == 0;
     const size_t vcols = pack ? cols / 2 : cols;
     const size_t bx = (vcols + Z_THREADS - 1) / Z_THREADS;
     if (bx > 0x7fffffffull || cols > 0x7fffffffull) return VT_ERR_UNSUPPORTED;
@@ -503,12 +562,17 @@ int vt_prefilter_z_range(const float *d_src, float *d_dst, int d0, size_t cols, 
     if (chunks > 65535) return VT_ERR_UNSUPPORTED;
     {
         VtProf prof(VT_K_PREFILTER_Z, st);
-        if (pack)
-            prefilter_z_kernel<vt_f2><<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>((const vt_f2 *)d_src, (vt_f2 *)d_dst,
-                                                                                     d_avail, vcols, z_chunk, z0, z1);
+        const dim3 grid((unsigned)bx, chunks);
+        if (pack && z4out)
+            prefilter_z_kernel<vt_f2, true><<<grid, Z_THREADS, 0, st>>>((const vt_f2 *)d_src, (vt_f2 *)d_dst, d_avail, vcols,
+                                                                        z_chunk, z0, z1);
+        else if (pack)
+            prefilter_z_kernel<vt_f2, false><<<grid, Z_THREADS, 0, st>>>((const vt_f2 *)d_src, (vt_f2 *)d_dst, d_avail, vcols,
+                                                                         z_chunk, z0, z1);
+        else if (z4out)
+            prefilter_z_kernel<float, true><<<grid, Z_THREADS, 0, st>>>(d_src, d_dst, d_avail, cols, z_chunk, z0, z1);
         else
-            prefilter_z_kernel<float><<<dim3((unsigned)bx, chunks), Z_THREADS, 0, st>>>(d_src, d_dst, d_avail, cols, z_chunk,
-                                                                                     z0, z1);
+            prefilter_z_kernel<float, false><<<grid, Z_THREADS, 0, st>>>(d_src, d_dst, d_avail, cols, z_chunk, z0, z1);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());

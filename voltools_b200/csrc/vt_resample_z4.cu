@@ -1,0 +1,874 @@
+// vt_resample_z4.cu -- "slice4" kernel family: transforms that leave ONE axis alone, on a coefficient volume whose
+// untouched axis is interleaved by four.
+//
+// When the matrix maps output axis m straight onto input axis m with an integer offset
+//        M[m] = e_m + (0,0,0,t),  t integer,  M[r][m] = 0 for r != m
+// (every rotation about axis m through the centre of the volume: BASELINE configs[0..2] and the README sweep for
+// m = 0; `rotation=(25,0,0)` 'rzxz' of examples/transformation.py for m = 2), the in-plane position of an output
+// column and therefore every in-plane interpolation weight is the same along the whole march over axis m, and the
+// fraction along axis m is exactly 0.  vt_resample_slice.cu exploits that for m = 0 on the plain layout and ends up
+// bound by shared-memory wavefronts: 16 scalar LDS per voxel and plane, ~2 wavefronts each at 45 degrees because a
+// warp's 32 texels cannot be spread over 32 banks under a rotation.  This family changes the LAYOUT instead:
+//
+//   "Z4" layout of axis m:   L[g][y][x][j] = V[index 4g+j along axis m][y][x]      (j = 0..3, zero past the end)
+//
+// (y, x) being the other two axes in ascending order.  One TMA box then delivers, per texel of a tile's in-plane
+// footprint, FOUR consecutive planes in 16 contiguous bytes, and a tap becomes one LDS.128 that serves four output
+// planes:
+//   * 4 instead of 16 LDS per voxel and plane, and the four planes of a load pair up naturally in FFMA2;
+//   * bank conflicts are evaluated per QUARTER warp (8 lanes x 16 bytes = one 128-byte wavefront), so 8 texels
+//     have to fall into 8 distinct 16-byte bank groups instead of 32 texels into 32 banks: the host picks, per
+//     matrix, how 8 lanes tile the columns (1x8, 2x4, 4x2, 8x1) and the row pitch mod 8 (one of eight tensor maps
+//     whose box widths differ by one texel) from a simulation -- 1.0-1.5 wavefronts per quarter (mean 1.19 over a
+//     180-angle sweep) instead of 1.66-1.97;
+//   * rows of 16-byte texels are always 16-byte aligned: no row padding, no rounding of the box start.
+// The same kernel marches along axis 0, 1 or 2: only the output strides and the roles of the two in-plane indices in
+// the reference's float32 coordinate recipe change (`prod_on_fast`).
+//
+// The layout is produced by vt_pack_z4 (any axis, from the plain layout) or directly by the prefilter's Z pass
+// (axis 0).  Results are bit-identical to vt_resample_slice.cu (same weights, same summation order).
+//
+// Replaces the reference's `transform` kernel (voltools/transforms.py:253-282) + linearTex3D / cubicTex3D /
+// cubicTex3DSimple (voltools/kernels/helper_interpolation.h:3-68) for this class of matrices.
+#include <cuda.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
+#include "vt_common.cuh"
+
+namespace {
+
+constexpr int TS = 16;        // tile edge
+constexpr int NT = TS * TS;   // threads per CTA, one column each
+constexpr int BH_MAX = 32;    // max footprint rows (texels)
+constexpr int BW_MAX = 40;    // max box width (texels): footprint <= 33 + 7 pitch classes
+constexpr int STAGE_BYTES = BH_MAX * BW_MAX * 16;  // one ring stage: a footprint of four planes (20 KB)
+constexpr int NSTAGE = 3;
+constexpr int NPITCH = 8;     // tensor maps per launch: box widths bw0 .. bw0+7 (pitch mod 8 is what matters)
+constexpr int N_SHAPES = 4;   // quarter-warp shapes 1x8, 2x4, 4x2, 8x1 (rows x columns of the tile)
+
+struct Z4Mat {
+    float ys, yf, yc;  // source y (slower in-plane axis) = f(slow index, fast index): coefficients, constant
+    float xs, xf, xc;  // source x (contiguous in-plane axis)
+    int tm;            // integer shift along the march axis
+    unsigned char shape, pitch_idx, pad0, pad1;
+};
+
+struct Z4Params {
+    float *dst;
+    long long dst_batch_stride;
+    long long os_slow, os_fast, os_m;  // output element strides of the tile's slow / fast axes and of the march axis
+    int o_fast;                        // extent of the fast tile axis
+    int slow_b, slow_e;                // range of the slow tile axis to produce
+    int m_b, m_e;                      // range of the march axis to produce
+    int s_y, s_x, s_m;                 // source extents: in-plane rows, in-plane columns, march axis
+    int n_mats;
+    int prod_on_fast;                  // which in-plane index the recipe multiplies first (see z4_coord)
+    int bw0, bh;                       // box width of map 0 (map k: bw0 + k) and box height, texels
+    int tiles_fast;
+    Z4Mat mats[VT_MAX_BATCH];
+};
+
+struct Z4Maps {
+    CUtensorMap map[NPITCH];
+};
+
+// The reference's coordinate recipe (voltools/transforms.py:264-274 as compiled: t = a1*M1; t = fma(a0,M0,t);
+// t = fma(a2,M2,t); t = M3 + t; p = t + 0.5) for a source row whose coefficient of the march index is zero: that term
+// is an exact no-op, and what is left is one product and one fma over the two in-plane indices.  Which index is
+// multiplied first depends on the axis numbers: march 0 -> a1*M1 then fma(a2); march 1 -> a0*M0 (fma(a0,M0,a1*0)
+// rounds a0*M0 once, like the product) then fma(a2); march 2 -> a1*M1 then fma(a0).  With (slow, fast) = (a1,a2),
+// (a0,a2), (a0,a1) that is "product on slow" for march 0 / 1 and "product on fast" for march 2.
+__host__ __device__ __forceinline__ float z4_coord(float cs, float cf, float cc, float as, float af, int prod_on_fast)
+{
+#ifdef __CUDA_ARCH__
+    const float t = prod_on_fast ? __fmaf_rn(as, cs, __fmul_rn(af, cf)) : __fmaf_rn(af, cf, __fmul_rn(as, cs));
+    return __fadd_rn(__fadd_rn(cc, t), 0.5f);
+#else
+    const float t = prod_on_fast ? fmaf(as, cs, af * cf) : fmaf(af, cf, as * cs);
+    return (cc + t) + 0.5f;
+#endif
+}
+
+// thread -> column of the 16 x 16 tile: 8 consecutive lanes (a quarter warp = one LDS.128 wavefront) form a
+// (1<<s) x (8>>s) patch; patches are laid out row-major, so that a warp's four patches cover 2x16, 2x16, 4x8, 8x4
+__host__ __device__ __forceinline__ void z4_lane_pos(int tid, int s, int &ty, int &tx)
+{
+    const int q = tid >> 3, l = tid & 7;
+    const int band = q >> (s + 1), qcol = q & ((2 << s) - 1);
+    ty = (band << s) + (l >> (3 - s));
+    tx = qcol * (8 >> s) + (l & ((8 >> s) - 1));
+}
+
+__device__ __forceinline__ void lds128(unsigned addr, vt_f2 &lo, vt_f2 &hi)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+}
+
+template <int INTERP>
+struct Taps4;
+
+// ---- linear: 4 taps with the texture unit's integer weights (fraction along the march axis 0 -> S = 256) ----
+template <>
+struct Taps4<VT_LINEAR> {
+    static constexpr int LO = 0, HI = 2;  // footprint margins relative to floor(p - 0.5)
+    static constexpr int BEFORE = 0, AFTER = 0;
+    float w[4];
+    unsigned r0, r1;  // byte offsets of the two tap rows inside a stage
+    template <int RULE>
+    __device__ __forceinline__ void init(float py, float px, int ylo, int xlo, int pitch)
+    {
+        int by, bx;
+        if (RULE == 0) {
+            int a, b;
+            vt_tex_fix_hw(px, bx, a);
+            vt_tex_fix_hw(py, by, b);
+            int wi[4];
+            vt_tex_hw_side(a, b, 256, wi);
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = vt_u2f(wi[k]) * (1.0f / 256.0f);
+        } else {
+            float ax, ay;
+            vt_tex_fix<2>(px, bx, ax);
+            vt_tex_fix<2>(py, by, ay);
+            w[0] = (1.0f - ax) * (1.0f - ay);
+            w[1] = ax * (1.0f - ay);
+            w[2] = (1.0f - ax) * ay;
+            w[3] = ax * ay;
+        }
+        r0 = 16u * (unsigned)((by - ylo) * pitch + (bx - xlo));
+        r1 = r0 + 16u * (unsigned)pitch;
+    }
+    template <unsigned SOFF>
+    __device__ __forceinline__ void planes(unsigned ring, float (&out)[4]) const
+    {
+        vt_f2 a01 = 0ull, a23 = 0ull;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            vt_f2 lo, hi;
+            lds128(ring + (k < 2 ? r0 : r1) + (SOFF + 16u * (k & 1)), lo, hi);
+            const vt_f2 ww = vt_pk(w[k], w[k]);
+            a01 = vt_fma2(lo, ww, a01);
+            a23 = vt_fma2(hi, ww, a23);
+        }
+        vt_unpk(a01, out[0], out[1]);
+        vt_unpk(a23, out[2], out[3]);
+    }
+};
+
+// ---- cubic_simple: 16 in-plane taps, float32 B-spline weights; march-axis weights B(-1), B(0), B(1) ----------
+template <>
+struct Taps4<VT_CUBIC_SIMPLE> {
+    static constexpr int LO = -1, HI = 2;
+    static constexpr int BEFORE = 1, AFTER = 1;
+    float w[16];
+    unsigned row[4];
+    float wz0, wz1, wz2;
+    template <int RULE>
+    __device__ __forceinline__ void init(float py, float px, int ylo, int xlo, int pitch)
+    {
+        const float cgx = __fadd_rn(px, -0.5f), cgy = __fadd_rn(py, -0.5f);
+        const float fx0 = floorf(cgx), fy0 = floorf(cgy);
+        const float fx = __fsub_rn(cgx, fx0), fy = __fsub_rn(cgy, fy0);
+        float wx[4], wy[4];
+        vt_bspline4(fx, wx);
+        vt_bspline4(fy, wy);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[j * 4 + i] = __fmul_rn(wx[i], wy[j]);
+        row[0] = 16u * (unsigned)(((int)fy0 - 1 - ylo) * pitch + ((int)fx0 - 1 - xlo));
+#pragma unroll
+        for (int j = 1; j < 4; j++) row[j] = row[j - 1] + 16u * (unsigned)pitch;
+        wz0 = vt_bspline(-1.0f);  // the fraction along the march axis is exactly 0
+        wz1 = vt_bspline(0.0f);
+        wz2 = vt_bspline(1.0f);
+    }
+    // in-plane sums of the group's four planes, two FFMA2 per tap
+    template <unsigned SOFF>
+    __device__ __forceinline__ void planes(unsigned ring, float (&out)[4]) const
+    {
+        vt_f2 a01 = 0ull, a23 = 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                vt_f2 lo, hi;
+                lds128(ring + row[j] + (SOFF + 16u * i), lo, hi);
+                const vt_f2 ww = vt_pk(w[j * 4 + i], w[j * 4 + i]);
+                a01 = vt_fma2(lo, ww, a01);
+                a23 = vt_fma2(hi, ww, a23);
+            }
+        vt_unpk(a01, out[0], out[1]);
+        vt_unpk(a23, out[2], out[3]);
+    }
+};
+
+// ---- cubic_tex: Ruijters' 8 trilinear fetches with the texture unit's integer weights -----------------------
+// With fraction 0 along the march axis: h0 = idx + 0.3 -> planes idx-1 (S = 256-c0) and idx (S = c0), combined with
+// g0; h1 = idx + 1.5 -> plane idx+1 (S = 256), combined with g1 (see vt_resample_slice.cu Taps<VT_CUBIC_TEX>).
+// Each of the three planes gets its own set of 16 pre-multiplied tap weights.
+template <>
+struct Taps4<VT_CUBIC_TEX> {
+    static constexpr int LO = -1, HI = 2;
+    static constexpr int BEFORE = 1, AFTER = 1;
+    float wa[16], wb[16], wc[16];
+    unsigned adr[8];  // byte offsets of taps (row j, x pair k): adr[j*2+k], the pair is (adr, adr+16)
+    template <int RULE>
+    __device__ __forceinline__ void init(float py, float px, int ylo, int xlo, int pitch)
+    {
+        float g0x, g1x, h0x, h1x, g0y, g1y, h0y, h1y, g0z, g1z, h0z, h1z;
+        vt_ruijters(px, g0x, g1x, h0x, h1x);
+        vt_ruijters(py, g0y, g1y, h0y, h1y);
+        vt_ruijters(8.5f, g0z, g1z, h0z, h1z);  // any texel centre: the fraction along the march axis is exactly 0
+        const float gx[2] = {g0x, g1x}, gy[2] = {g0y, g1y};
+        const float hx[2] = {h0x, h1x}, hy[2] = {h0y, h1y};
+        const float gz[3] = {g0z, g0z, g1z};
+        int bx[2], by[2];
+        if (RULE == 0) {
+            int bz0, c0, bz1, c1;
+            vt_tex_fix_hw(h0z, bz0, c0);  // (7, 205)
+            vt_tex_fix_hw(h1z, bz1, c1);  // (9, 0)
+            const int S[3] = {256 - c0, c0, 256 - c1};
+            int ax[2], ay[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                vt_tex_fix_hw(hx[k], bx[k], ax[k]);
+                vt_tex_fix_hw(hy[k], by[k], ay[k]);
+            }
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+                float *w = p == 0 ? wa : (p == 1 ? wb : wc);
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        int wi[4];
+                        vt_tex_hw_side(ax[i], ay[j], S[p], wi);
+                        const float g = __fmul_rn(__fmul_rn(gx[i], gy[j]), gz[p]) * (1.0f / 256.0f);
+                        w[(2 * j) * 4 + 2 * i] = g * vt_u2f(wi[0]);
+                        w[(2 * j) * 4 + 2 * i + 1] = g * vt_u2f(wi[1]);
+                        w[(2 * j + 1) * 4 + 2 * i] = g * vt_u2f(wi[2]);
+                        w[(2 * j + 1) * 4 + 2 * i + 1] = g * vt_u2f(wi[3]);
+                    }
+            }
+        } else {
+            int bz0, bz1;
+            float c0, c1;
+            vt_tex_fix<2>(h0z, bz0, c0);
+            vt_tex_fix<2>(h1z, bz1, c1);
+            const float S[3] = {1.0f - c0, c0, 1.0f - c1};
+            float ax[2], ay[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                vt_tex_fix<2>(hx[k], bx[k], ax[k]);
+                vt_tex_fix<2>(hy[k], by[k], ay[k]);
+            }
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+                float *w = p == 0 ? wa : (p == 1 ? wb : wc);
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const float g = gx[i] * gy[j] * gz[p] * S[p];
+                        w[(2 * j) * 4 + 2 * i] = g * (1.0f - ax[i]) * (1.0f - ay[j]);
+                        w[(2 * j) * 4 + 2 * i + 1] = g * ax[i] * (1.0f - ay[j]);
+                        w[(2 * j + 1) * 4 + 2 * i] = g * (1.0f - ax[i]) * ay[j];
+                        w[(2 * j + 1) * 4 + 2 * i + 1] = g * ax[i] * ay[j];
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                adr[(2 * j) * 2 + k] = 16u * (unsigned)((by[j] - ylo) * pitch + (bx[k] - xlo));
+                adr[(2 * j + 1) * 2 + k] = adr[(2 * j) * 2 + k] + 16u * (unsigned)pitch;
+            }
+    }
+    // A-, B- and C-weighted in-plane sums of the group's four planes: per tap {wa, wb} x {t, t} for each plane (the
+    // scalar texel is FFMA2's broadcast operand) and {t0, t1} x {wc, wc}, {t2, t3} x {wc, wc}: 6 FFMA2 per LDS.128
+    template <unsigned SOFF>
+    __device__ __forceinline__ void planes3(unsigned ring, float (&qa)[4], float (&qb)[4], float (&qc)[4]) const
+    {
+        vt_f2 ab[4] = {0ull, 0ull, 0ull, 0ull}, c01 = 0ull, c23 = 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                vt_f2 lo, hi;
+                lds128(ring + adr[j * 2 + (i >> 1)] + (SOFF + 16u * (i & 1)), lo, hi);
+                const vt_f2 wab = vt_pk(wa[j * 4 + i], wb[j * 4 + i]);
+                const vt_f2 wcc = vt_pk(wc[j * 4 + i], wc[j * 4 + i]);
+                float t0, t1, t2, t3;
+                vt_unpk(lo, t0, t1);
+                vt_unpk(hi, t2, t3);
+                ab[0] = vt_fma2(wab, vt_pk(t0, t0), ab[0]);
+                ab[1] = vt_fma2(wab, vt_pk(t1, t1), ab[1]);
+                ab[2] = vt_fma2(wab, vt_pk(t2, t2), ab[2]);
+                ab[3] = vt_fma2(wab, vt_pk(t3, t3), ab[3]);
+                c01 = vt_fma2(lo, wcc, c01);
+                c23 = vt_fma2(hi, wcc, c23);
+            }
+#pragma unroll
+        for (int p = 0; p < 4; p++) vt_unpk(ab[p], qa[p], qb[p]);
+        vt_unpk(c01, qc[0], qc[1]);
+        vt_unpk(c23, qc[2], qc[3]);
+    }
+};
+
+__host__ __device__ __forceinline__ int floordiv4(int v) { return v >> 2; }  // arithmetic shift: floor for negatives
+
+template <int INTERP, int RULE, bool OOB_ZERO>
+__global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
+    vt_z4_kernel(const __grid_constant__ Z4Params P, const __grid_constant__ Z4Maps G, int m_chunk)
+{
+    // [128 B: "full" mbarriers of the ring stages][NSTAGE stages of STAGE_BYTES]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using T = Taps4<INTERP>;
+    const int tid = threadIdx.x;
+    const int tile_y = blockIdx.x / P.tiles_fast, tile_x = blockIdx.x - tile_y * P.tiles_fast;
+    const int mat = blockIdx.z;
+    const Z4Mat &M = P.mats[mat];
+    const int pidx = M.pitch_idx;
+    const int pitch = P.bw0 + pidx;
+    const int tm = M.tm;
+    const int pof = P.prod_on_fast;
+    const int zc0 = P.m_b + blockIdx.y * m_chunk;
+    const int zc1 = min(zc0 + m_chunk, P.m_e);
+    const int as0 = P.slow_b + tile_y * TS, af0 = tile_x * TS;
+    const int as1 = min(as0 + TS, P.slow_e) - 1, af1 = min(af0 + TS, P.o_fast) - 1;
+
+    // footprint of the tile: extremes are at the corners (the float recipe is monotone in either index)
+    float y_min, y_max, x_min, x_max;
+    {
+        const float sa = (float)as0, sb = (float)as1, fa = (float)af0, fb = (float)af1;
+        const float y00 = z4_coord(M.ys, M.yf, M.yc, sa, fa, pof), y01 = z4_coord(M.ys, M.yf, M.yc, sa, fb, pof);
+        const float y10 = z4_coord(M.ys, M.yf, M.yc, sb, fa, pof), y11 = z4_coord(M.ys, M.yf, M.yc, sb, fb, pof);
+        const float x00 = z4_coord(M.xs, M.xf, M.xc, sa, fa, pof), x01 = z4_coord(M.xs, M.xf, M.xc, sa, fb, pof);
+        const float x10 = z4_coord(M.xs, M.xf, M.xc, sb, fa, pof), x11 = z4_coord(M.xs, M.xf, M.xc, sb, fb, pof);
+        y_min = fminf(fminf(y00, y01), fminf(y10, y11));
+        y_max = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11));
+        x_min = fminf(fminf(x00, x01), fminf(x10, x11));
+        x_max = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
+    }
+    // clamp to a couple of texels around the source: everything further out is border (zero) anyway and columns that
+    // far out are out of bounds; keeps the integer conversions safe for wild matrices
+    y_min = fmaxf(y_min, -2.0f); x_min = fmaxf(x_min, -2.0f);
+    y_max = fminf(y_max, (float)P.s_y + 2.0f); x_max = fminf(x_max, (float)P.s_x + 2.0f);
+    const int ylo = (int)floorf(y_min - 0.5f) + T::LO, xlo = (int)floorf(x_min - 0.5f) + T::LO;
+
+    const unsigned bars_s = vt_smem_u32(smem_raw);
+    const unsigned ring_s = bars_s + 128u;
+    if (tid == 0) {
+        vt_tma_prefetch_desc(&G.map[pidx]);
+#pragma unroll
+        for (int i = 0; i < NSTAGE; i++) vt_mbar_init(bars_s + 8u * i, 1);
+        vt_mbar_fence_init();
+    }
+    __syncthreads();
+
+    // this thread's column
+    int ty, tx;
+    z4_lane_pos(tid, M.shape, ty, tx);
+    const int a_s = as0 + ty, a_f = af0 + tx;
+    const bool live = a_s < P.slow_e && a_f < P.o_fast;
+    const float py = z4_coord(M.ys, M.yf, M.yc, (float)a_s, (float)a_f, pof);
+    const float px = z4_coord(M.xs, M.xf, M.xc, (float)a_s, (float)a_f, pof);
+    // transforms.py:276-278 for the two in-plane axes
+    const bool inplane = live && !(px < 0 || py < 0 || px >= (float)P.s_x || py >= (float)P.s_y);
+
+    // input planes needed: q = z + tm + d, d in [-BEFORE, AFTER]; group g holds planes 4g .. 4g+3
+    const int q_first = zc0 + tm - T::BEFORE, q_last = zc1 - 1 + tm + T::AFTER;
+    const int g_last = floordiv4(q_last);
+    int g = floordiv4(q_first);
+    const unsigned tx_bytes = 16u * (unsigned)(pitch * P.bh);
+
+    auto issue = [&](int gg, unsigned st) {
+        if (tid == 0 && gg <= g_last) {
+            const unsigned bar = bars_s + 8u * st;
+            vt_mbar_expect_tx(bar, tx_bytes);
+            // groups / rows / columns outside the source arrive as zeros (= the texture's border mode)
+            vt_tma_load_3d(ring_s + st * (unsigned)STAGE_BYTES, &G.map[pidx], bar, 4 * xlo, ylo, gg);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < NSTAGE - 1; i++) issue(g + i, (unsigned)i);
+    // the column's weights are computed while those first loads are in flight
+    T taps;
+    if (inplane) taps.template init<RULE>(py, px, ylo, xlo, pitch);
+    float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // sliding window of per-plane sums
+    unsigned phase = 0;
+    // output pointer of this column at the output plane that input plane 4g is the LAST tap plane of
+    float *dstp = P.dst + (size_t)mat * P.dst_batch_stride + (long long)a_s * P.os_slow + (long long)a_f * P.os_fast +
+                  (long long)(4 * g - T::AFTER - tm) * P.os_m;
+
+    auto stage_step = [&](auto cur_c, int gg) {
+        constexpr unsigned CUR = decltype(cur_c)::value;
+        constexpr unsigned FILL = (CUR + NSTAGE - 1) % NSTAGE;
+        constexpr unsigned SOFF = CUR * (unsigned)STAGE_BYTES;
+        vt_mbar_wait(bars_s + 8u * CUR, phase);
+        __syncthreads();  // everyone is done with the stage consumed in the previous step: refill it
+        issue(gg + NSTAGE - 1, FILL);
+        float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (inplane) {
+            if constexpr (INTERP == VT_LINEAR) {
+                taps.template planes<SOFF>(ring_s, r);
+            } else if constexpr (INTERP == VT_CUBIC_SIMPLE) {
+                float pq[4];
+                taps.template planes<SOFF>(ring_s, pq);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    // the reference accumulates kz = -1, 0, 1 in that order (helper_interpolation.h:51)
+                    r[p] = fmaf(taps.wz2, pq[p], fmaf(taps.wz1, s1, __fmul_rn(taps.wz0, s2)));
+                    s2 = s1;
+                    s1 = pq[p];
+                }
+            } else {
+                float qa[4], qb[4], qc[4];
+                taps.template planes3<SOFF>(ring_s, qa, qb, qc);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    r[p] = (s3 + s1) + qc[p];  // s3 = A-sum of plane q-2, s1 = B-sum of plane q-1
+                    s3 = s2;
+                    s2 = qa[p];
+                    s1 = qb[p];
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int zi = 4 * gg + p - T::AFTER;  // input plane at the centre of the output voxel
+            const int zo = zi - tm;               // output index along the march axis
+            if (zo >= zc0 && zo < zc1) {          // uniform: past the warm-up planes, inside the chunk
+                const bool ok = inplane && (unsigned)zi < (unsigned)P.s_m;  // 0 <= p_m < s_m with p_m = zi + 0.5
+                if (OOB_ZERO) {
+                    if (live) dstp[(long long)p * P.os_m] = ok ? r[p] : 0.0f;
+                } else if (ok) {
+                    dstp[(long long)p * P.os_m] = r[p];
+                }
+            }
+        }
+        dstp += 4 * P.os_m;
+    };
+    for (;;) {
+        stage_step(std::integral_constant<unsigned, 0>{}, g);
+        if (++g > g_last) break;
+        stage_step(std::integral_constant<unsigned, 1>{}, g);
+        if (++g > g_last) break;
+        stage_step(std::integral_constant<unsigned, 2>{}, g);
+        if (++g > g_last) break;
+        phase ^= 1u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout conversion: plain (padded rows) -> Z4 of axis m
+// ---------------------------------------------------------------------------------------------------
+// one thread per Z4 texel (g, y, x): four loads along axis m (stride sm), one 16-byte store.  Lanes run along x,
+// the contiguous axis of the destination; for m = 0, 1 that is also the contiguous axis of the source.  For m = 2
+// the four loads of a thread are one aligned 16-byte load when the rows allow it.
+__global__ void __launch_bounds__(256)
+    vt_pack_z4_kernel(const float *__restrict__ src, float4 *__restrict__ dst, int dm, int dy, int dx, long long sm,
+                      long long sy, long long sx)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, g = blockIdx.z;
+    if (x >= dx) return;
+    const float *p = src + (long long)(4 * g) * sm + (long long)y * sy + (long long)x * sx;
+    float4 v;
+    v.x = __ldg(p);
+    v.y = 4 * g + 1 < dm ? __ldg(p + sm) : 0.0f;
+    v.z = 4 * g + 2 < dm ? __ldg(p + 2 * sm) : 0.0f;
+    v.w = 4 * g + 3 < dm ? __ldg(p + 3 * sm) : 0.0f;
+    dst[((size_t)g * dy + y) * dx + x] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct AxisRoles {
+    int m, ay, ax;         // march axis, source in-plane axes (rows, columns): ascending
+    int slow, fast;        // output axes of the tile
+    int prod_on_fast;
+};
+AxisRoles roles(int m)
+{
+    switch (m) {
+        case 0: return {0, 1, 2, 1, 2, 0};
+        case 1: return {1, 0, 2, 0, 2, 0};
+        default: return {2, 0, 1, 0, 1, 1};
+    }
+}
+
+bool z4_mat_ok(const VtMat &M, int m, const int sdim[3])
+{
+    const AxisRoles R = roles(m);
+    if (sdim[m] >= 16384) return false;  // h0 = idx + 0.3 along the march axis must keep its 1/256 quantum
+    for (int c = 0; c < 3; c++)
+        if (M.r[m][c] != (c == m ? 1.0f : 0.0f)) return false;
+    if (M.r[R.ay][m] != 0.0f || M.r[R.ax][m] != 0.0f) return false;
+    const float t = M.r[m][3];
+    if (!(fabsf(t) < 16384.0f) || t != floorf(t)) return false;
+    const int rows[2] = {R.ay, R.ax};
+    const int lim[2] = {BH_MAX - 6, BW_MAX - (NPITCH - 1) - 6};  // footprint edge <= floor(ext + 0.1) + 6 texels
+    for (int i = 0; i < 2; i++) {
+        const float ext = (fabsf(M.r[rows[i]][R.slow]) + fabsf(M.r[rows[i]][R.fast])) * (float)(TS - 1);
+        if (!(ext <= (float)lim[i] - 0.1f)) return false;
+        if (!(fabsf(M.r[rows[i]][3]) < 1e6f)) return false;
+    }
+    return true;
+}
+
+// Average wavefronts per quarter-warp LDS.128 of a matrix for every (pitch mod 8, quarter shape): lanes land on
+// 16-byte bank group (y*pitch + x) mod 8 of their footprint origin (every other tap shifts all lanes alike).
+// Four sample tiles; a tile's 256 origins are computed once and regrouped for each shape.  Memoised per matrix.
+struct Z4Conflicts {
+    float key[8];
+    bool valid;
+    float wf[8][N_SHAPES];
+};
+// (the statistics do not need the exact float32 recipe: double arithmetic, no libm fmaf on the host)
+static inline int z4_origin(float cs, float cf, float cc, int as, int af)
+{
+    return (int)floor((double)cc + (double)as * cs + (double)af * cf);  // floor(p - 0.5), p = ... + 0.5
+}
+const Z4Conflicts &z4_conflicts(const Z4Mat &M, int pof)
+{
+    constexpr int MEMO = 2048, WAYS = 4;
+    static thread_local Z4Conflicts memo[MEMO];
+    static thread_local unsigned victim = 0;
+    const float key[8] = {M.ys, M.yf, M.yc, M.xs, M.xf, M.xc, (float)pof, 1.0f};
+    unsigned h = 2166136261u;
+    for (int i = 0; i < 7; i++) {
+        unsigned u;
+        memcpy(&u, &key[i], 4);
+        h = (h ^ u) * 16777619u;
+    }
+    const unsigned slot = (h ^ (h >> 13)) & (MEMO - 1);
+    for (int w = 0; w < WAYS; w++) {
+        const Z4Conflicts &c = memo[(slot + w) & (MEMO - 1)];
+        if (c.valid && memcmp(c.key, key, sizeof key) == 0) return c;
+    }
+    int way = 0;
+    for (int w = 0; w < WAYS; w++)
+        if (!memo[(slot + w) & (MEMO - 1)].valid) { way = w; break; } else way = (int)(victim++ % WAYS);
+    Z4Conflicts &e = memo[(slot + way) & (MEMO - 1)];
+    memcpy(e.key, key, sizeof key);
+    constexpr int NSMP = 3, NQ = 10;
+    static const unsigned char T1[NSMP] = {1, 14, 5}, T2[NSMP] = {3, 8, 29};
+    int cost[8][N_SHAPES] = {};
+    for (int smp = 0; smp < NSMP; smp++) {
+        const int as0 = 16 * T1[smp], af0 = 16 * T2[smp];
+        const int y0 = z4_origin(M.ys, M.yf, M.yc, as0, af0), x0 = z4_origin(M.xs, M.xf, M.xc, as0, af0);
+        int oy[TS][TS], ox[TS][TS];
+        for (int ty = 0; ty < TS; ty++)
+            for (int tx = 0; tx < TS; tx++) {
+                oy[ty][tx] = z4_origin(M.ys, M.yf, M.yc, as0 + ty, af0 + tx) - y0;
+                ox[ty][tx] = z4_origin(M.xs, M.xf, M.xc, as0 + ty, af0 + tx) - x0;
+            }
+        for (int s = 0; s < N_SHAPES; s++)
+            for (int qi = 0; qi < NQ; qi++) {
+                const int q = (5 * qi + 1 + smp) & (NT / 8 - 1);  // a sample of the tile's 32 quarter warps
+                int yy[8], xx[8], n = 0;
+                for (int l = 0; l < 8; l++) {
+                    int ty, tx;
+                    z4_lane_pos(q * 8 + l, s, ty, tx);
+                    const int y = oy[ty][tx], x = ox[ty][tx];
+                    bool dup = false;  // same texel as an earlier lane: broadcast
+                    for (int k = 0; k < n; k++) dup |= (yy[k] == y && xx[k] == x);
+                    if (!dup) {
+                        yy[n] = y;
+                        xx[n] = x;
+                        n++;
+                    }
+                }
+                for (int pm = 0; pm < 8; pm++) {
+                    unsigned cnt = 0;  // eight 4-bit counters, one per 16-byte bank group
+                    for (int l = 0; l < n; l++) cnt += 1u << (4 * ((yy[l] * pm + xx[l]) & 7));
+                    int worst = 0;
+                    for (; cnt; cnt >>= 4) worst = std::max(worst, (int)(cnt & 15u));
+                    cost[pm][s] += worst;
+                }
+            }
+    }
+    for (int pm = 0; pm < 8; pm++)
+        for (int s = 0; s < N_SHAPES; s++) e.wf[pm][s] = (float)cost[pm][s] / (float)(NSMP * NQ);
+    e.valid = true;
+    return e;
+}
+
+struct Z4Plan {
+    int chunks, m_chunk;
+    int bw0, bh;
+    float cost;  // modelled wavefronts per quarter-warp load, averaged over the matrices
+};
+
+template <int INTERP>
+int plan_z4(Z4Params &P, int sms, const float ext_y[], const float ext_x[], Z4Plan &L)
+{
+    using T = Taps4<INTERP>;
+    int need_h = 0, need_w = 0;
+    for (int k = 0; k < P.n_mats; k++) {
+        need_h = std::max(need_h, (int)floorf(ext_y[k] + 0.1f) + 6);
+        need_w = std::max(need_w, (int)floorf(ext_x[k] + 0.1f) + 6);
+    }
+    need_h = std::min(need_h, BH_MAX);
+    need_w = std::min(need_w, BW_MAX - (NPITCH - 1));
+    // never wider / taller than the source plus its border: small volumes keep small boxes
+    L.bw0 = need_w;
+    L.bh = need_h;
+    P.bw0 = L.bw0;
+    P.bh = L.bh;
+    // per matrix: quarter shape and pitch class with the fewest simulated wavefronts.  A wider box costs L2->shared
+    // traffic (1/27 per texel of width), 4x2 / 8x1 patches make a warp's stores cover 4 / 8 rows.
+    const char *force_s = getenv("VT_Z4_SHAPE"), *force_p = getenv("VT_Z4_PITCH");  // tuning knobs
+    float total = 0.0f;
+    for (int k = 0; k < P.n_mats; k++) {
+        const Z4Conflicts &C = z4_conflicts(P.mats[k], P.prod_on_fast);
+        float best = 1e30f;
+        int bs = 0, bp = 0;
+        for (int pi = 0; pi < NPITCH; pi++)
+            for (int s = 0; s < N_SHAPES; s++) {
+                const float pen = 0.012f * (float)pi + (s == 2 ? 0.02f : (s == 3 ? 0.06f : 0.0f));
+                const float c = C.wf[(L.bw0 + pi) & 7][s] + pen;
+                if (c < best) {
+                    best = c;
+                    bs = s;
+                    bp = pi;
+                }
+            }
+        if (force_s) bs = atoi(force_s) & 3;
+        if (force_p) bp = atoi(force_p) & 7;
+        P.mats[k].shape = (unsigned char)bs;
+        P.mats[k].pitch_idx = (unsigned char)bp;
+        total += C.wf[(L.bw0 + bp) & 7][bs];
+    }
+    L.cost = total / (float)P.n_mats;
+    // chunks along the march axis: a CTA marches (m_chunk + WARM)/4 groups and pays a fixed start-up; CTAs run in
+    // waves of (SMs x resident CTAs).  Long marches over large planes lose the L2 reuse between neighbouring tiles
+    // (see vt_resample_slice.cu): cap a march at 2 GB of source planes.
+    const int nm = P.m_e - P.m_b;
+    const int tiles = ((P.slow_e - P.slow_b + TS - 1) / TS) * P.tiles_fast;
+    constexpr int WARM = T::BEFORE + T::AFTER + 3;  // + up to 3 planes of group misalignment
+    constexpr int RESIDENT = INTERP == VT_CUBIC_TEX ? 2 : 3;
+    constexpr int STARTUP = 12;
+    const long long slots = (long long)sms * RESIDENT, per_chunk = (long long)tiles * P.n_mats;
+    const long long plane_bytes = (long long)P.s_y * P.s_x * 4;
+    const long long march_bytes = INTERP == VT_LINEAR ? (512LL << 20) : (2048LL << 20);
+    const int march_cap = (int)std::max(32LL, march_bytes / std::max(plane_bytes, 1LL));
+    int chunks = 1, m_chunk = nm;
+    long long best_cost = -1;
+    for (int c = 1; c <= 256 && (c == 1 || nm / c >= 16); c++) {
+        int zc = ((nm + c - 1) / c + 3) / 4 * 4;  // whole groups
+        if (zc < 4) break;
+        if (zc > march_cap && nm / (c + 1) >= 16) continue;
+        const int cc = (nm + zc - 1) / zc;
+        const long long waves = (per_chunk * cc + slots - 1) / slots;
+        const long long cost = waves * (zc + WARM + STARTUP);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            chunks = cc;
+            m_chunk = zc;
+        }
+    }
+    if (const char *e = getenv("VT_Z4_CHUNKS"))
+        if (atoi(e) > 0) {
+            m_chunk = ((nm + atoi(e) - 1) / atoi(e) + 3) / 4 * 4;
+            chunks = (nm + m_chunk - 1) / m_chunk;
+        }
+    if (chunks > 65535) return VT_ERR_UNSUPPORTED;
+    L.chunks = chunks;
+    L.m_chunk = m_chunk;
+    return VT_OK;
+}
+
+template <int INTERP, int RULE>
+int launch2(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[], const float ext_x[], cudaStream_t st)
+{
+    int sms = 148, dev = 0;
+    VT_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    Z4Plan L;
+    int rc = plan_z4<INTERP>(P, sms, ext_y, ext_x, L);
+    if (rc) return rc;
+    Z4Maps G;
+    memset(&G, 0, sizeof G);
+    const unsigned long long groups = (unsigned long long)((P.s_m + 3) / 4);
+    const unsigned long long gdim[3] = {4ull * (unsigned long long)P.s_x, (unsigned long long)P.s_y, groups};
+    const unsigned long long gstr[2] = {16ull * (unsigned long long)P.s_x, 16ull * (unsigned long long)P.s_x * P.s_y};
+    bool used[NPITCH] = {};
+    for (int k = 0; k < P.n_mats; k++) used[P.mats[k].pitch_idx] = true;
+    for (int pi = 0; pi < NPITCH; pi++) {
+        if (!used[pi]) continue;
+        const unsigned box[3] = {4u * (unsigned)(L.bw0 + pi), (unsigned)L.bh, 1u};
+        rc = vt_encode_tmap_3d(&G.map[pi], d_src4, gdim, gstr, box);
+        if (rc) return rc;
+    }
+    if (getenv("VT_Z4_DEBUG"))
+        fprintf(stderr, "z4 interp %d: box %d x %d, mat0 shape %d pitch +%d, wavefronts %.3f, chunks %d x %d\n", INTERP, L.bw0,
+                L.bh, P.mats[0].shape, P.mats[0].pitch_idx, L.cost, L.chunks, L.m_chunk);
+    const int tiles = ((P.slow_e - P.slow_b + TS - 1) / TS) * P.tiles_fast;
+    dim3 grid(tiles, L.chunks, P.n_mats);
+    const size_t smem = 128 + (size_t)NSTAGE * STAGE_BYTES;
+    // the attribute is per device and per function: one flag per device (a process may drive several GPUs)
+    static std::atomic<bool> attr_set_dev[64];
+    std::atomic<bool> &attr_set = attr_set_dev[dev & 63];
+    if (!attr_set.load(std::memory_order_acquire)) {
+        VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.store(true, std::memory_order_release);
+    }
+    {
+        VtProf prof(VT_K_Z4_LINEAR + INTERP, st);
+        if (oob_zero) vt_z4_kernel<INTERP, RULE, true><<<grid, NT, smem, st>>>(P, G, L.m_chunk);
+        else vt_z4_kernel<INTERP, RULE, false><<<grid, NT, smem, st>>>(P, G, L.m_chunk);
+    }
+    vt_count_launch();
+    VT_CUDA(cudaGetLastError());
+    return VT_OK;
+}
+
+// VtResampleParams (logical source dims, output, z-range, matrices) -> Z4Params for march axis m
+void fill_z4(const VtResampleParams &P, int m, Z4Params &Q, float ext_y[], float ext_x[])
+{
+    const AxisRoles R = roles(m);
+    const int sdim[3] = {P.s0, P.s1, P.s2}, odim[3] = {P.o0, P.o1, P.o2};
+    const long long ostr[3] = {(long long)P.o1 * P.o2, (long long)P.o2, 1};
+    memset(&Q, 0, sizeof Q);
+    Q.dst = P.dst;
+    Q.dst_batch_stride = P.dst_batch_stride;
+    Q.os_slow = ostr[R.slow];
+    Q.os_fast = ostr[R.fast];
+    Q.os_m = ostr[m];
+    Q.o_fast = odim[R.fast];
+    // the C ABI's z-range restricts output axis 0: the march axis for m = 0, the slow tile axis otherwise
+    Q.slow_b = m == 0 ? 0 : P.z_begin;
+    Q.slow_e = m == 0 ? odim[R.slow] : P.z_end;
+    Q.m_b = m == 0 ? P.z_begin : 0;
+    Q.m_e = m == 0 ? P.z_end : odim[m];
+    Q.s_y = sdim[R.ay];
+    Q.s_x = sdim[R.ax];
+    Q.s_m = sdim[m];
+    Q.n_mats = P.n_mats;
+    Q.prod_on_fast = R.prod_on_fast;
+    Q.tiles_fast = (Q.o_fast + TS - 1) / TS;
+    for (int k = 0; k < P.n_mats; k++) {
+        const VtMat &M = P.mats[k];
+        Z4Mat &Z = Q.mats[k];
+        Z.ys = M.r[R.ay][R.slow]; Z.yf = M.r[R.ay][R.fast]; Z.yc = M.r[R.ay][3];
+        Z.xs = M.r[R.ax][R.slow]; Z.xf = M.r[R.ax][R.fast]; Z.xc = M.r[R.ax][3];
+        Z.tm = (int)M.r[m][3];
+        ext_y[k] = (fabsf(Z.ys) + fabsf(Z.yf)) * (float)(TS - 1);
+        ext_x[k] = (fabsf(Z.xs) + fabsf(Z.xf)) * (float)(TS - 1);
+    }
+}
+
+template <int INTERP>
+int launch1(const VtResampleParams &P, const float *d_src4, int m, cudaStream_t st)
+{
+    Z4Params Q;
+    float ext_y[VT_MAX_BATCH], ext_x[VT_MAX_BATCH];
+    fill_z4(P, m, Q, ext_y, ext_x);
+    const bool zero = (P.flags & VT_OOB_ZERO) != 0;
+    if (INTERP != VT_CUBIC_SIMPLE && (P.flags & VT_WEIGHTS_EXACT)) return launch2<INTERP, 2>(Q, d_src4, zero, ext_y, ext_x, st);
+    return launch2<INTERP, 0>(Q, d_src4, zero, ext_y, ext_x, st);
+}
+
+}  // namespace
+
+// the axis (0, 1, 2) every matrix of the batch leaves alone in the way this family needs, or -1.  Axis 0 first: it is
+// the one whose layout the prefilter can write directly.
+int vt_z4_axis(const VtResampleParams &P, int interp)
+{
+    (void)interp;
+    const int sdim[3] = {P.s0, P.s1, P.s2};
+    const long long ostr_lim = 0x7fffffffLL;
+    if ((long long)P.o1 * P.o2 > ostr_lim) return -1;
+    for (int m = 0; m < 3; m++) {
+        bool ok = true;
+        for (int k = 0; k < P.n_mats && ok; k++) ok = z4_mat_ok(P.mats[k], m, sdim);
+        if (ok) return m;
+    }
+    return -1;
+}
+
+bool vt_z4_axis_accepts(const VtResampleParams &P, int axis)
+{
+    const int sdim[3] = {P.s0, P.s1, P.s2};
+    if ((long long)P.o1 * P.o2 > 0x7fffffffLL || axis < 0 || axis > 2) return false;
+    for (int k = 0; k < P.n_mats; k++)
+        if (!z4_mat_ok(P.mats[k], axis, sdim)) return false;
+    return true;
+}
+
+size_t vt_z4_floats(int s0, int s1, int s2, int axis)
+{
+    const int d[3] = {s0, s1, s2};
+    const AxisRoles R = roles(axis);
+    return (size_t)((d[axis] + 3) / 4) * (size_t)d[R.ay] * (size_t)d[R.ax] * 4;
+}
+
+int vt_pack_z4_impl(const float *d_src, int s0, int s1, int s2, long long row, long long plane, float *d_dst4, int axis,
+                    cudaStream_t st)
+{
+    const int d[3] = {s0, s1, s2};
+    const long long str[3] = {plane, row, 1};
+    const AxisRoles R = roles(axis);
+    const int groups = (d[axis] + 3) / 4;
+    if (d[R.ay] > 65535 || groups > 65535) return VT_ERR_UNSUPPORTED;
+    dim3 grid((d[R.ax] + 255) / 256, d[R.ay], groups);
+    {
+        VtProf prof(VT_K_PACK_Z4, st);
+        vt_pack_z4_kernel<<<grid, 256, 0, st>>>(d_src, (float4 *)d_dst4, d[axis], d[R.ay], d[R.ax], str[axis], str[R.ay],
+                                                str[R.ax]);
+    }
+    vt_count_launch();
+    VT_CUDA(cudaGetLastError());
+    return VT_OK;
+}
+
+// host-only: the per-matrix decisions (quarter shape, pitch class, simulated wavefronts per quarter-warp load)
+int vt_z4_plan_impl(const VtResampleParams &P, int axis, int interp, int sms, int *chunks, int *m_chunk, int *box_w,
+                    int *box_h, int *shapes, int *pitches, float *wavefronts)
+{
+    Z4Params Q;
+    float ext_y[VT_MAX_BATCH], ext_x[VT_MAX_BATCH];
+    fill_z4(P, axis, Q, ext_y, ext_x);
+    Z4Plan L;
+    int rc;
+    switch (interp) {
+        case VT_LINEAR: rc = plan_z4<VT_LINEAR>(Q, sms, ext_y, ext_x, L); break;
+        case VT_CUBIC_TEX: rc = plan_z4<VT_CUBIC_TEX>(Q, sms, ext_y, ext_x, L); break;
+        case VT_CUBIC_SIMPLE: rc = plan_z4<VT_CUBIC_SIMPLE>(Q, sms, ext_y, ext_x, L); break;
+        default: return VT_ERR_INVALID_ARG;
+    }
+    if (rc) return rc;
+    *chunks = L.chunks;
+    *m_chunk = L.m_chunk;
+    *box_w = L.bw0;
+    *box_h = L.bh;
+    for (int k = 0; k < P.n_mats; k++) {
+        if (shapes) shapes[k] = Q.mats[k].shape;
+        if (pitches) pitches[k] = L.bw0 + Q.mats[k].pitch_idx;
+        if (wavefronts) wavefronts[k] = z4_conflicts(Q.mats[k], Q.prod_on_fast).wf[(L.bw0 + Q.mats[k].pitch_idx) & 7][Q.mats[k].shape];
+    }
+    return VT_OK;
+}
+
+int vt_launch_z4(const VtResampleParams &P, const float *d_src4, int axis, int interp, cudaStream_t st)
+{
+    if (P.z_end <= P.z_begin || P.o0 <= 0 || P.o1 <= 0 || P.o2 <= 0 || P.n_mats <= 0) return VT_OK;
+    if (axis < 0 || axis > 2 || ((uintptr_t)d_src4 % 16) != 0) return VT_ERR_INVALID_ARG;
+    switch (interp) {
+        case VT_LINEAR: return launch1<VT_LINEAR>(P, d_src4, axis, st);
+        case VT_CUBIC_TEX: return launch1<VT_CUBIC_TEX>(P, d_src4, axis, st);
+        case VT_CUBIC_SIMPLE: return launch1<VT_CUBIC_SIMPLE>(P, d_src4, axis, st);
+    }
+    return VT_ERR_INVALID_ARG;
+}

@@ -127,20 +127,25 @@ class CudaEngine:
     def empty(self, shape):
         return self.torch.empty(shape, dtype=self.torch.float32, device=self.device)
 
-    def resample_many(self, buffer, width, interpolation, matrices):
+    def _resident(self, buffer, interpolation, width, complete=True):
+        """StaticVolume view of a received buffer (no copy).  complete=False: the buffer is still being filled
+        (streaming), so no second layout may be derived from it: plain-layout kernels only."""
         from .volume import StaticVolume
         sv = StaticVolume.from_coefficients(buffer, interpolation, width)
-        return sv.affine_many(matrices)
+        sv._plain_only = not complete
+        return sv
+
+    def resample_many(self, buffer, width, interpolation, matrices):
+        return self._resident(buffer, interpolation, width).affine_many(matrices)
 
     def resample_many_range(self, buffer, width, interpolation, matrices, out, z0, z1):
         """Output planes [z0, z1) of every matrix into `out` (K, d0, d1, width); out-of-bounds voxels are zeroed."""
         from . import _native
-        from .volume import StaticVolume
-        sv = StaticVolume.from_coefficients(buffer, interpolation, width)
+        sv = self._resident(buffer, interpolation, width, complete=False)
+        m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
         with self.torch.cuda.device(self.dev):
-            _native.affine(buffer.data_ptr(), sv.shape, out.data_ptr(), sv.shape, matrices, sv._interp, _native.OOB_ZERO,
-                           z_range=(z0, z1), device=self.dev,
-                           stream=self.torch.cuda.current_stream(self.dev).cuda_stream, src_strides=sv._strides)
+            sv._launch(out.data_ptr(), m, _native.OOB_ZERO, self.torch.cuda.current_stream(self.dev).cuda_stream,
+                       z_range=(z0, z1))
 
     def project_many(self, buffer, width, interpolation, matrices, z_range=None):
         """(K, d1, width) projections along axis 0 of the transformed volume (planes z_range of it), fused."""
@@ -150,18 +155,17 @@ class CudaEngine:
 
     def resample_slab(self, buffer, width, interpolation, matrix, z0, z1):
         from . import _native
-        from .volume import StaticVolume
-        sv = StaticVolume.from_coefficients(buffer, interpolation, width)
+        sv = self._resident(buffer, interpolation, width)
         d0, d1, d2 = sv.shape
         out = self.torch.empty((z1 - z0, d1, d2), dtype=self.torch.float32, device=self.device)
         if z1 > z0:
             # the C ABI addresses output plane z at d_dst + z*plane and touches only planes [z0, z1): handing it the
             # slab buffer shifted back by z0 planes makes it write the slab in place
             virtual_base = out.data_ptr() - z0 * d1 * d2 * 4
+            m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(-1, 4, 4)
             with self.torch.cuda.device(self.dev):
-                _native.affine(buffer.data_ptr(), sv.shape, virtual_base, sv.shape, matrix, sv._interp, _native.OOB_ZERO,
-                               z_range=(z0, z1), device=self.dev,
-                               stream=self.torch.cuda.current_stream(self.dev).cuda_stream, src_strides=sv._strides)
+                sv._launch(virtual_base, m, _native.OOB_ZERO, self.torch.cuda.current_stream(self.dev).cuda_stream,
+                           z_range=(z0, z1))
         return out
 
 

@@ -236,29 +236,55 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
             else:
                 src_t = vin.owner if isinstance(vin.owner, torch.Tensor) \
                     else torch.as_tensor(vin.owner, device=f'cuda:{dev}')
+            if src_t.device.index != dev:
+                # (a raw pointer of another GPU handed to a kernel on `dev` would fault, not raise)
+                src_t = src_t.to(f'cuda:{dev}')
+            if vout is not None and vout.device != dev:
+                raise ValueError(f'output lives on gpu:{vout.device}, the transform runs on gpu:{dev}')
             src_ptr = src_t.data_ptr()
-            # the sampled volume lives in a private buffer whose rows are padded to 16 bytes: the kernels can then
-            # stage it with TMA whatever the width is.  The prefilter writes that layout directly (out of place: the
-            # caller's array is never modified); an unfiltered volume with an odd width is copied once.
-            row = _native.padded_row(shape[2])
-            src_strides = (row, shape[1] * row)
-            if needs_prefilter:
-                coef_t = torch.empty((shape[0], shape[1], row), dtype=torch.float32, device=f'cuda:{dev}')
-                _native.prefilter(src_ptr, shape, dev, stream, dst_ptr=coef_t.data_ptr(), dst_strides=src_strides)
-                src_t, src_ptr = coef_t, coef_t.data_ptr()
-            elif row != shape[2]:
-                pad_t = torch.empty((shape[0], shape[1], row), dtype=torch.float32, device=f'cuda:{dev}')
-                pad_t[:, :, :shape[2]].copy_(src_t)
-                src_t, src_ptr = pad_t, pad_t.data_ptr()
             if vout is None:
                 out_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
-                _native.affine(src_ptr, shape, out_t.data_ptr(), shape, m, interp, _native.OOB_ZERO, device=dev,
-                               stream=stream, src_strides=src_strides)
-                result = out_t.cpu().numpy()
+                dst_ptr, flags = out_t.data_ptr(), _native.OOB_ZERO
             else:
-                _native.affine(src_ptr, shape, vout.ptr, shape, m, interp, _native.OOB_SKIP, device=dev, stream=stream,
+                out_t, dst_ptr, flags = None, vout.ptr, _native.OOB_SKIP
+            # A matrix that leaves one axis alone (rotations about an axis through the centre: the slice4 kernels,
+            # vt_resample_z4.cu) samples the Z4 layout of that axis: the prefilter's Z sweep writes it directly for
+            # axis 0, otherwise one pack pass (the reference pays the same pass for its CUDA-array copy,
+            # transforms.py:197-199).
+            axis = _native.z4_axis(shape, shape, m, interp) if _native.z4_wanted(interp, False) else -1
+            if axis >= 0:
+                z4_t = torch.empty(_native.z4_bytes(shape, axis) // 4, dtype=torch.float32, device=f'cuda:{dev}')
+                if needs_prefilter:
+                    ws_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
+                    if axis == 0:
+                        _native.prefilter_z4(src_ptr, shape, z4_t.data_ptr(), ws_t.data_ptr(), ws_t.numel() * 4, dev, stream)
+                    else:
+                        coef_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
+                        _native.prefilter(src_ptr, shape, dev, stream, dst_ptr=coef_t.data_ptr(), workspace=ws_t)
+                        _native.pack_z4(coef_t.data_ptr(), shape, z4_t.data_ptr(), axis, device=dev, stream=stream)
+                        del coef_t
+                    del ws_t
+                else:
+                    _native.pack_z4(src_ptr, shape, z4_t.data_ptr(), axis, device=dev, stream=stream)
+                _native.affine_z4(z4_t.data_ptr(), axis, shape, dst_ptr, shape, m, interp, flags, device=dev, stream=stream)
+                del z4_t
+            else:
+                # the sampled volume lives in a private buffer whose rows are padded to 16 bytes: the kernels can then
+                # stage it with TMA whatever the width is.  The prefilter writes that layout directly (out of place:
+                # the caller's array is never modified); an unfiltered volume with an odd width is copied once.
+                row = _native.padded_row(shape[2])
+                src_strides = (row, shape[1] * row)
+                if needs_prefilter:
+                    coef_t = torch.empty((shape[0], shape[1], row), dtype=torch.float32, device=f'cuda:{dev}')
+                    _native.prefilter(src_ptr, shape, dev, stream, dst_ptr=coef_t.data_ptr(), dst_strides=src_strides)
+                    src_t, src_ptr = coef_t, coef_t.data_ptr()
+                elif row != shape[2]:
+                    pad_t = torch.empty((shape[0], shape[1], row), dtype=torch.float32, device=f'cuda:{dev}')
+                    pad_t[:, :, :shape[2]].copy_(src_t)
+                    src_t, src_ptr = pad_t, pad_t.data_ptr()
+                _native.affine(src_ptr, shape, dst_ptr, shape, m, interp, flags, device=dev, stream=stream,
                                src_strides=src_strides)
-                result = None
+            result = None if out_t is None else _native.download(out_t, stream)
             del src_t
 
         if profile:

@@ -98,13 +98,38 @@ class StaticVolume:
     #: (linear, 340 vs 193 Gvox/s) or 0.55 ms (bspline / filt_bspline, 66 vs 52 Gvox/s) over the brick kernels.
     TEXTURE_AFTER = 16
 
-    def _launch(self, dst_ptr, m, flags, stream):
+    def _z4_buffer(self, axis, stream):
+        """The resident volume in the Z4 layout of `axis` (vt_resample_z4.cu), packed from the plain buffer on first
+        use and kept: the second representation the reference keeps as a CUDA array (volume.py:37-50)."""
+        z4 = getattr(self, '_z4', None)
+        if z4 is None:
+            z4 = self._z4 = {}
+        buf = z4.get(axis)
+        if buf is None:
+            torch = _torch()
+            buf = torch.empty(_native.z4_bytes(self.shape, axis) // 4, dtype=torch.float32, device=f'cuda:{self._dev}')
+            _native.pack_z4(self._coeffs.data_ptr(), self.shape, buf.data_ptr(), axis, device=self._dev, stream=stream,
+                            src_strides=self._strides)
+            z4[axis] = buf
+        return buf
+
+    def _launch(self, dst_ptr, m, flags, stream, z_range=None):
         """One launch set for the matrices `m` (K, 4, 4) on the resident volume.
+
+        Matrices that leave one axis alone (rotations about an axis through the centre ...) run the slice4 kernels
+        on the Z4 layout of that axis.
 
         Matrices of the slice family (rotations about axis 0 ...) always run the plane-marching kernels.  For the
         two interpolators that ARE the texture unit (linear, bspline / filt_bspline) a general matrix runs on a
         hardware texture object once this volume has seen TEXTURE_AFTER such transforms -- the reference keeps the
         same second copy (volume.py:37-50); until then, and always for *_simple, the shared-memory brick kernels."""
+        axis = -1
+        if _native.z4_wanted(self._interp, True) and not getattr(self, '_plain_only', False):
+            axis = _native.z4_axis(self.shape, self.shape, m, self._interp)
+        if axis >= 0:
+            _native.affine_z4(self._z4_buffer(axis, stream).data_ptr(), axis, self.shape, dst_ptr, self.shape, m,
+                              self._interp, flags, z_range=z_range, device=self._dev, stream=stream)
+            return
         use_tex = False
         if self._interp in (_native.LINEAR, _native.CUBIC_TEX) and getattr(self, '_tex', None) is not False:
             if _native.affine_plan(self._coeffs.data_ptr(), self.shape, self.shape, m, self._interp) != 'slice':
@@ -116,10 +141,10 @@ class StaticVolume:
             except RuntimeError:
                 self._tex, use_tex = False, False  # extent beyond the 3-D texture limits / no memory: stay on bricks
         if use_tex:
-            self._tex.affine(dst_ptr, self.shape, m, self._interp, flags, stream=stream)
+            self._tex.affine(dst_ptr, self.shape, m, self._interp, flags, z_range=z_range, stream=stream)
         else:
             _native.affine(self._coeffs.data_ptr(), self.shape, dst_ptr, self.shape, m, self._interp, flags,
-                           device=self._dev, stream=stream, src_strides=self._strides)
+                           z_range=z_range, device=self._dev, stream=stream, src_strides=self._strides)
 
     # -- transforms ---------------------------------------------------------------------------------------
     def affine(self, transform_m: np.ndarray, profile: bool = False, output=None) -> Union[np.ndarray, None]:
@@ -143,7 +168,7 @@ class StaticVolume:
                 t1.record()
                 t1.synchronize()
                 print(f'transform finished in {t0.elapsed_time(t1):.3f}ms')
-            return out_t.cpu().numpy() if vout is None else None
+            return _native.download(out_t, stream) if vout is None else None
 
     def affine_many(self, matrices: Sequence[np.ndarray], output=None, zero_fill: bool = None):
         """Batched `affine`: K matrices -> K volumes, one launch per VT_MAX_BATCH matrices.
