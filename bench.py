@@ -5,25 +5,26 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workloads (BASELINE.json `configs`, inputs per SURVEY.md section 8d):
-  cfg1    (default) configs[1]: transform() of 250^3 float32 volumes, interpolation='filt_bspline' (prefilter +
-          8-fetch cubic), rotation=(0,45,0) 'rzxz' about the centre.  One step = one pass over a batch of 8
-          independent volumes (500 MB in + 500 MB out, larger than the 126 MB L2), each through the public
-          voltools_b200.transform(...).  N > 1: every rank owns its own batch (independent objects, no
-          collective) -> weak scaling.
-  affine512  configs[3]: 512^3 bspline_simple, full affine G6, output= device array.
-  sweep   configs[2]: StaticVolume 256^3 filt_bspline, 180-angle sweep; rank 0 prefilters, one NCCL broadcast of
-          the coefficient volume, the angles are split across ranks (strong scaling).
-  modes   all five interpolation modes at 512^3 (rot45 and full affine) -> reported under "modes" (1 GPU).
-  cpu_baselines  reference CPU path and scipy.ndimage.affine_transform at 100^3 .. 512^3 on this host (no GPU work).
-  project rotate-and-project at 512^3: StaticVolume.project_many vs transform + sum(axis=0) (1 GPU).
+Default run = the headline workload plus the secondary tables, all in the ONE JSON line:
+  headline  BASELINE configs[2] (README.md:26-27 of the reference): StaticVolume 256^3 float32 'filt_bspline',
+            180-angle sweep rotation=(0,i,0) 'rzxz' about the centre.  One step = the whole job: prefilter on rank 0,
+            [N > 1: one NCCL broadcast of the coefficient volume,] the 180 matrices dealt round-robin to the ranks, every
+            rank resamples its share through StaticVolume.affine_many (public API, eager calls).  Strong scaling: the
+            180 transforms are the fixed job; `value` = 180 * 256^3 voxels / step time (CUDA events, max over ranks).
+  modes_512   every interpolation mode at 512^3 through affine(output=): rot45 (configs[1]'s matrix), the full affine
+              G6 (configs[3]), and the mean over random 3-axis rotations (the reference's tests/benchmark.py:52-54 set);
+              ms, Gvox/s, fraction of the 8 (16 for filt_*) B/voxel roofline, in-bounds fraction.  N = 1 only.
+  zslab_1024  configs[4]: 1024^3 filt_bspline, z-slab sharding, distribution and resampling timed separately
+              (a mild rotation and the full affine G6).
+  cfg1        configs[1]: transform() of 250^3 'filt_bspline' rot45, eager calls, batch of 8 volumes.  N = 1 only.
+Single pieces: --workload sweep|modes|zslab|cfg1|project|cpu_baselines.
 
-`value` is device-resident throughput (inputs already in HBM, CUDA events); `e2e` is the same batch through the
-same public call with pinned HOST arrays in and out (H2D + kernels + D2H inside the timed region).
-`roofline` is for the kernel with the largest share of the step, from per-launch CUDA events recorded by the
-library (vt_profile_*), against MEASURED_PEAKS.json.  `cpu_baseline` times the unmodified reference package's
-CPU path (voltools.transform(device='cpu') -> scipy.ndimage.affine_transform), staged under oracle/_ref/py, on
-this host.  `--impl reference` runs that CPU path alone as the reference arm.
+`e2e` is the headline job through the same public API with HOST buffers: the volume starts in pinned host memory
+(H2D inside the timed region) and every output volume is returned to the host (`sv.transform(...)` -> numpy).
+`roofline` is for the kernel with the largest share of the headline step (per-launch CUDA events recorded by the
+library, vt_profile_*), against MEASURED_PEAKS.json.  `cpu_baseline` / `--impl reference` time the unmodified reference
+package's CPU path (voltools.transform(device='cpu') -> scipy.ndimage.affine_transform), staged under oracle/_ref/py,
+on this host's cores.
 """
 import argparse
 import json
@@ -41,13 +42,14 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = 'Gvoxels/s'
-E2E_THREADS = 2  # host threads issuing the e2e leg's independent transform() calls (PCIe duplex overlap)
 ROT45 = dict(rotation=(0, 45, 0), rotation_order='rzxz')
 FULL_AFFINE = dict(scale=(1.1, 0.9, 1.05), shear=(0.05, -0.03, 0.02), rotation=(30, 45, 60), rotation_order='rzxz',
                    translation=(5.5, -3.25, 2.0))
-CFG1 = dict(n=250, batch=8, interpolation='filt_bspline', kw=ROT45,
-            name="configs[1]: transform() 250^3 float32 interpolation='filt_bspline' rotation=(0,45,0) rzxz; "
-                 "step = batch of 8 independent volumes")
+MILD = dict(rotation=(5, 8, -6), rotation_order='sxyz', translation=(3.5, -2.0, 1.0))
+SWEEP = dict(n=256, angles=180, interpolation='filt_bspline',
+             name="configs[2]: StaticVolume 256^3 float32 'filt_bspline', 180-angle sweep rotation=(0,i,0) rzxz "
+                  '(prefilter on rank 0 + one NCCL broadcast + angles dealt round-robin; step = the whole sweep)')
+CFG1 = dict(n=250, batch=8, interpolation='filt_bspline', kw=ROT45)
 
 
 def peaks():
@@ -59,6 +61,17 @@ def peaks():
 
 def dist_env():
     return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+def inbounds_fraction(shape, m):
+    """Fraction of output voxels whose sample point lies inside the source (transforms.py:276-278); float64 on a
+    strided sub-grid, informational."""
+    step = max(1, min(shape) // 64)
+    idx = [np.arange(0, s, step, dtype=np.float64) for s in shape]
+    a = np.stack(np.meshgrid(*idx, indexing='ij'), axis=-1).reshape(-1, 3)
+    p = a @ np.asarray(m, np.float64)[:3, :3].T + np.asarray(m, np.float64)[:3, 3] + 0.5
+    ok = np.all((p >= 0) & (p < np.asarray(shape, np.float64)), axis=1)
+    return float(ok.mean())
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -107,6 +120,11 @@ class ClockSampler:
         return out
 
 
+def clock_sampler(torch, dev):
+    uuid = str(getattr(torch.cuda.get_device_properties(dev), 'uuid', dev))
+    return ClockSampler(uuid if uuid.startswith('GPU-') or uuid.isdigit() else 'GPU-' + uuid)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # reference CPU path (the unmodified reference package, staged by oracle/build_ref.py under oracle/_ref/py)
 # ------------------------------------------------------------------------------------------------------------
@@ -136,17 +154,24 @@ def _ref_worker(job):
     return dt, float(out[shape[0] // 2, shape[1] // 2, shape[2] // 2])
 
 
+def _sweep_kw(i):
+    return dict(rotation=(0, i, 0), rotation_order='rzxz')
+
+
 def cpu_baseline_leg(cfg):
-    """Reference CPU path on ONE full volume of the workload, one core (scipy.ndimage is single-threaded)."""
+    """Reference CPU path on a bounded sample of the headline job, one core (scipy.ndimage is single-threaded): a few
+    of the 180 angles on the full 256^3 volume (~3.6 s each)."""
     ref_vt = _ref_voltools()
     if ref_vt is None:
         return {'value': None, 'unit': METRIC, 'cores': 0, 'kind': 'reference', 'sample': 'reference package not staged'}
     n = cfg['n']
-    dt, _ = _ref_worker((0, (n, n, n), cfg['interpolation'], cfg['kw']))
-    out = {'value': n ** 3 / dt / 1e9, 'unit': METRIC, 'cores': 1, 'kind': 'reference',
-           'sample': f"1 of the step's {cfg['batch']} volumes ({n}^3) through the unmodified reference "
-                     f"voltools.transform(device='cpu') = scipy.ndimage.affine_transform(order=3, prefilter=True); "
-                     f'{dt:.2f} s on 1 of {os.cpu_count()} host cores'}
+    angles = (0, 45, 90, 135)
+    dt = sum(_ref_worker((0, (n, n, n), cfg['interpolation'], _sweep_kw(a)))[0] for a in angles)
+    out = {'value': len(angles) * n ** 3 / dt / 1e9, 'unit': METRIC, 'cores': 1, 'kind': 'reference',
+           'sample': f"{len(angles)} of the sweep's {cfg['angles']} angles {angles} on the full {n}^3 volume through the "
+                     f"unmodified reference voltools.transform(device='cpu') = scipy.ndimage.affine_transform(order=3, "
+                     f'prefilter=True); {dt:.2f} s on 1 of {os.cpu_count()} host cores (the reference has no resident '
+                     'CPU volume: every call prefilters again)'}
     # scipy.ndimage.affine_transform directly (tests/benchmark.py:60), order 1 and 3, 100^3 (BASELINE configs[0] shape)
     try:
         from scipy import ndimage
@@ -200,8 +225,9 @@ def run_cpu_baselines(args):
 
 
 def reference_arm(args, cfg):
-    """--impl reference: the reference's own CPU implementation, all the host parallelism it can use (one process
-    per independent volume of the batch; each call is single-threaded inside SciPy)."""
+    """--impl reference: the reference's own CPU implementation of the headline job, all the host parallelism it can
+    use (one process per angle; each call is single-threaded inside SciPy).  Bounded sample per step: every process
+    transforms a z-slab of the 256^3 volume for its own angle (rotation about axis 0: every output plane costs the same)."""
     import multiprocessing as mp
     rank, _, world = dist_env()
     if rank != 0:
@@ -210,15 +236,13 @@ def reference_arm(args, cfg):
         print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref/py (reference package) not staged'}))
         return
     n = cfg['n']
-    procs = max(1, min(os.cpu_count() or 1, cfg['batch']))
-    # bounded sample: a z-slab of `planes` planes of each volume (in-plane rotation about axis 0: every output
-    # plane costs the same), sized so that (steps + warmup) steps fit in ~150 s
-    t_probe, _ = _ref_worker((0, (16, n, n), cfg['interpolation'], cfg['kw']))
+    procs = max(1, min(os.cpu_count() or 1, 32))
+    t_probe, _ = _ref_worker((0, (16, n, n), cfg['interpolation'], _sweep_kw(45)))
     per_plane = t_probe / 16
     budget = 150.0 / (args.steps + args.warmup)
     planes = int(max(8, min(n, budget / per_plane)))
     shape = (planes, n, n)
-    jobs = [(1000 + i, shape, cfg['interpolation'], cfg['kw']) for i in range(procs)]
+    jobs = [(1000, shape, cfg['interpolation'], _sweep_kw((i * cfg['angles']) // procs)) for i in range(procs)]
     with mp.get_context('fork').Pool(procs) as pool:
         for _ in range(args.warmup):
             pool.map(_ref_worker, jobs)
@@ -228,12 +252,13 @@ def reference_arm(args, cfg):
         dt = time.perf_counter() - t0
     vox = procs * planes * n * n * args.steps
     value = vox / dt / 1e9
-    sample = (f'{procs} processes x one {planes}x{n}x{n} z-slab of a {n}^3 volume per step, unmodified reference '
-              f"voltools.transform(interpolation='{cfg['interpolation']}', device='cpu')")
+    sample = (f'{procs} processes (of {os.cpu_count()} host cores) x one {planes}x{n}x{n} z-slab of the {n}^3 volume per '
+              f"step, each at its own angle of the sweep, unmodified reference voltools.transform(interpolation="
+              f"'{cfg['interpolation']}', device='cpu')")
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': cfg['name'], 'sample': sample},
         'cpu_baseline': {'value': value, 'unit': METRIC, 'cores': procs, 'kind': 'reference', 'sample': sample},
         'e2e': {'value': value, 'unit': METRIC, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -259,109 +284,80 @@ def timed(torch, fn, steps, warmup, barrier):
     return e0.elapsed_time(e1) / 1e3
 
 
-def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
-    from voltools_b200 import _native
-    n, batch, interp, kw = cfg['n'], cfg['batch'], cfg['interpolation'], cfg['kw']
-    shape = (n, n, n)
-    device = f'gpu:{dev}'
+def med_ms(torch, fn, steps, warmup, flush=None):
+    ts = []
+    for it in range(warmup + steps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        if it >= warmup:
+            ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def run_sweep(args, torch, vt, dev, barrier, reduce_max, with_e2e=True):
+    """The headline: BASELINE configs[2]."""
+    from voltools_b200 import _native, multigpu
     rank, _, world = dist_env()
-    gen = torch.Generator(device=f'cuda:{dev}').manual_seed(1234 + rank)
-    vols = [torch.rand(shape, generator=gen, device=f'cuda:{dev}', dtype=torch.float32) for _ in range(batch)]
-    outs = [torch.zeros(shape, device=f'cuda:{dev}', dtype=torch.float32) for _ in range(batch)]
-
-    # The batch's volumes are independent: the calls are issued round-robin on `args.streams` CUDA streams (the API is
-    # stream-ordered on torch's current stream), so one volume's small kernels (250 CTAs do not fill 148 SMs x 2-3
-    # resident CTAs) overlap the next volume's.  The timed region starts and ends on the default stream, which the
-    # side streams fork from and join back into every step.
-    side = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else []
-
-    def step_on(streams):
-        if not streams:
-            for v, o in zip(vols, outs):
-                vt.transform(v, interpolation=interp, output=o, device=device, **kw)
-            return
-        main_stream = torch.cuda.current_stream(dev)  # the capture stream while a CUDA graph is being recorded
-        for s in streams:
-            s.wait_stream(main_stream)
-        for i, (v, o) in enumerate(zip(vols, outs)):
-            with torch.cuda.stream(streams[i % len(streams)]):
-                vt.transform(v, interpolation=interp, output=o, device=device, **kw)
-        for s in streams:
-            main_stream.wait_stream(s)
-
-    def step_eager():
-        step_on(side)
-
-    for _ in range(max(3, args.warmup)):
-        step_eager()
-    torch.cuda.synchronize()
-    # A step is 24 kernels of 30-80 us behind 8 Python calls: the host barely keeps ahead of the GPU (and falls behind
-    # with several ranks sharing the host's cores).  The same calls are therefore recorded once into a CUDA graph --
-    # same kernels, same streams, same buffers -- and the timed steps replay it.  --no-graph times the eager calls.
-    graph, launches_per_step = None, None
-    if not args.no_graph:
-        try:
-            l_cap = _native.launch_count()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                step_eager()
-            launches_per_step = _native.launch_count() - l_cap
-            g.replay()
-            torch.cuda.synchronize()
-            graph = g
-        except Exception as e:  # capture not possible here: eager calls
-            print(f'bench: CUDA graph capture failed ({e!r}); timing eager calls', file=sys.stderr)
-            torch.cuda.synchronize()
+    cfg = SWEEP
+    n = args.size if args.workload == 'sweep' and args.size != 512 else cfg['n']
+    shape = (n, n, n)
+    interp = cfg['interpolation']
+    c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+    mats = [vt.utils.transform_matrix(center=c, **_sweep_kw(i)) for i in range(cfg['angles'])]
+    vol = torch.rand(shape, device=f'cuda:{dev}', generator=torch.Generator(f'cuda:{dev}').manual_seed(7)) \
+        if rank == 0 else None
+    mine = multigpu.split_strided(len(mats), world, rank)
+    my_mats = np.stack([mats[i] for i in mine]) if len(mine) else np.zeros((0, 4, 4), np.float32)
+    out = torch.empty((len(mine),) + shape, device=f'cuda:{dev}')
+    eng = multigpu.CudaEngine(dev)
 
     def step():
-        if graph is not None:
-            graph.replay()
+        if world > 1:
+            buf, width = multigpu.prepare_and_broadcast(eng, vol, interp, src=0, shape=shape)
+            sv = vt.StaticVolume.from_coefficients(buf, interp, width)
         else:
-            step_eager()
+            sv = vt.StaticVolume(vol, interpolation=interp, device=f'gpu:{dev}')
+        if len(mine):
+            sv.affine_many(my_mats, output=out, zero_fill=True)
 
-    for _ in range(3):
+    for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
-    uuid = str(getattr(torch.cuda.get_device_properties(dev), 'uuid', dev))
-    clocks = ClockSampler(uuid if uuid.startswith('GPU-') or uuid.isdigit() else 'GPU-' + uuid)
-    # keep the GPU under the same load for >= 0.5 s before the timed region so that nvidia-smi (100 ms period)
-    # gets samples of the clocks this workload runs at; the sampler stays on through the timed region
+    clocks = clock_sampler(torch, dev)
     t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.6:
+    while time.perf_counter() - t_load < 0.6:  # nvidia-smi (100 ms period) needs samples under this load
         step()
         torch.cuda.synchronize()
     l0 = _native.launch_count()
-    sec = timed(torch, step, args.steps, 0, barrier)
-    launches = launches_per_step * args.steps if graph is not None else _native.launch_count() - l0
+    sec = reduce_max(timed(torch, step, args.steps, 0, barrier))
+    launches = _native.launch_count() - l0
     clk = clocks.stop()
-    sec = reduce_max(sec)
-    vox_step = batch * n ** 3
-    value = world * vox_step * args.steps / sec / 1e9
-    single_stream_value = value
-    if side:
-        sec1 = reduce_max(timed(torch, lambda: step_on([]), args.steps, 2, barrier))
-        single_stream_value = world * vox_step * args.steps / sec1 / 1e9
-    eager_value = value
-    if graph is not None:
-        sec2 = reduce_max(timed(torch, step_eager, args.steps, 2, barrier))
-        eager_value = world * vox_step * args.steps / sec2 / 1e9
+    vox_step = len(mats) * n ** 3
+    value = vox_step * args.steps / sec / 1e9
 
-    # per-kernel durations over the same K steps (CUDA events inside the library, on the launch stream), with the
-    # calls on ONE stream so that each kernel is timed alone
+    # per-kernel durations over K more steps (CUDA events inside the library, on the launch stream)
     _native.profile_enable(True)
     for _ in range(args.steps):
-        step_on([])
+        step()
     torch.cuda.synchronize()
     prof = _native.profile_read()
     _native.profile_enable(False)
     peak, peak_src = peaks()
     kernels = {}
     total_ms = sum(ms for ms, _ in prof.values()) or 1.0
+    my_vox = len(mine) * n ** 3
     for name, (ms, cnt) in prof.items():
-        avg = ms / cnt
-        ach = 8.0 * n ** 3 / (avg * 1e-3) / 1e9
-        kernels[name] = {'launches_per_step': cnt / args.steps, 'avg_ms': avg, 'share': ms / total_ms,
-                         'achieved_gbs': ach, 'frac': ach / peak}
+        # voxels this kernel processed on this rank over the K steps: the resampling kernels cover the rank's share of
+        # the matrices, the prefilter / pack kernels one volume per step
+        vox = my_vox * args.steps if ('cubic' in name or 'linear' in name) else n ** 3 * args.steps
+        ach = 8.0 * vox / (ms * 1e-3) / 1e9
+        kernels[name] = {'launches_per_step': cnt / args.steps, 'avg_ms': ms / cnt, 'share': ms / total_ms,
+                         'voxels_per_launch': vox / cnt, 'achieved_gbs': ach, 'frac': ach / peak}
     dom = max(prof, key=lambda k: prof[k][0]) if prof else None
     traffic = None
     tfile = ROOT / 'profiles' / 'traffic.json'
@@ -369,110 +365,196 @@ def run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max):
         traffic = json.loads(tfile.read_text()).get(dom, {}).get('dram_bytes_per_launch')
     roofline = None
     if dom:
-        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom]['achieved_gbs'], 'peak': peak,
-                    'unit': 'GB/s', 'frac': kernels[dom]['frac'], 'traffic': traffic, 'peak_source': peak_src,
-                    'algorithmic_bytes_per_launch': 8 * n ** 3,
-                    'step_frac': 16.0 * vox_step * args.steps / sec / 1e9 / peak,
-                    'note': 'achieved = 8 B/voxel x 250^3 voxels / average launch duration; step_frac = 16 B/voxel '
-                            '(prefilter 8 + resample 8) x voxels per step / step time / peak',
+        inb = float(np.mean([inbounds_fraction(shape, m) for m in mats[::6]]))
+        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
+                    'frac': kernels[dom]['frac'], 'traffic': traffic, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': 8.0 * kernels[dom]['voxels_per_launch'],
+                    'inbounds_fraction': inb,
+                    'step_frac': 8.0 * vox_step * args.steps / sec / 1e9 / peak / world,
+                    'note': 'achieved = 8 B/voxel (4 B compulsory read + 4 B write) x voxels per launch / average launch '
+                            'duration on rank 0; out-of-bounds voxels (1 - inbounds_fraction) are counted although they are '
+                            'neither read nor written; the 64 MiB coefficient volume is L2-resident across a sweep, so the '
+                            'real HBM traffic is the 4 B/voxel of writes; step_frac = the same for the whole step per GPU',
                     'kernels': kernels}
 
-    # end to end: pinned host arrays in and out through the same public call
-    h_vols = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(batch)]
-    h_outs = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(batch)]
-    for h, v in zip(h_vols, vols):
-        h.copy_(v)
-    np_vols, np_outs = [h.numpy() for h in h_vols], [h.numpy() for h in h_outs]
-
-    def one_e2e(i):
-        vt.transform(np_vols[i], interpolation=interp, output=np_outs[i], device=device, **kw)
-
-    # The batch's volumes are independent, so the public call is made from E2E_THREADS host threads (ctypes releases
-    # the GIL inside the library): one call's upload overlaps another's download on the full-duplex PCIe link.  The
-    # single-thread figure (calls strictly one after another) is reported next to it.
-    from concurrent.futures import ThreadPoolExecutor
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_by_threads = {}
-    for nthreads in (1, E2E_THREADS):
-        pool = ThreadPoolExecutor(nthreads) if nthreads > 1 else None
-
-        def step_e2e():
-            if pool is None:
-                for i in range(batch):
-                    one_e2e(i)
-            else:
-                list(pool.map(one_e2e, range(batch)))
-
-        step_e2e()
-        step_e2e()
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_e2e()
-        torch.cuda.synchronize()
-        e2e_by_threads[nthreads] = reduce_max(time.perf_counter() - t0)
-        barrier()
-        if pool is not None:
-            pool.shutdown()
-    e2e_sec = e2e_by_threads[E2E_THREADS]
-    e2e_value = world * vox_step * e2e_steps / e2e_sec / 1e9
-    # the host path must agree with the device path
-    err = float((torch.from_numpy(np_outs[0]).to(f'cuda:{dev}') - outs[0]).abs().max())
-    assert err <= 1e-5 * 16, f'host path differs from device path: {err}'
-
     line = {
-        'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
-        'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': cfg['name'], 'voxels_per_step_per_gpu': vox_step, 'parallelism': f'dp{world}',
-                   'l2': 'inputs larger than L2: 8 distinct volumes per step (500 MB in + 500 MB out per GPU)',
-                   'call': "voltools_b200.transform(vol, rotation=(0,45,0), rotation_order='rzxz', "
-                           "interpolation='filt_bspline', output=out, device='gpu:X')",
-                   'cuda_streams': max(1, args.streams), 'cuda_graph': graph is not None,
-                   'eager_value': eager_value, 'single_stream_eager_value': single_stream_value},
+        'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(3, args.warmup), 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['name'].replace('256^3', f'{n}^3'), 'voxels_per_step': vox_step,
+                   'parallelism': f'dp{world} over the matrix batch',
+                   'l2': 'outputs (180 x 64 MiB per step) exceed L2; the 64 MiB coefficient volume is L2-resident by design',
+                   'call': "StaticVolume(vol, 'filt_bspline').affine_many(matrices, output=device array) -- eager calls, "
+                           'no CUDA graph', 'timing': 'CUDA events around K steps, barrier + synchronize on both sides, '
+                                                      'max over ranks'},
         'clocks': {'sm_mhz': clk['sm_mhz'], 'sm_max_mhz': clk['sm_max_mhz'], 'reasons': clk['reasons'],
                    'samples': clk['samples']},
-        'e2e': {'value': e2e_value, 'unit': METRIC, 'h2d_bytes_per_step': vox_step * 4, 'd2h_bytes_per_step': vox_step * 4,
-                'steps': e2e_steps, 'ms_per_step': e2e_sec / e2e_steps * 1e3,
-                'call': f'same call with pinned numpy arrays for volume and output, issued from {E2E_THREADS} host threads '
-                        '(independent volumes)', 'host_threads': E2E_THREADS,
-                'single_thread_value': world * vox_step * e2e_steps / e2e_by_threads[1] / 1e9},
         'gpu_launches': int(launches),
         'roofline': roofline,
     }
+    if with_e2e:
+        line['e2e'] = sweep_e2e(args, torch, vt, dev, barrier, reduce_max, shape, interp, mats, mine, vol, out)
     return line
 
 
-def run_modes(args, torch, vt, dev):
-    """All five modes at 512^3 (north-star target shape): kernel-only Gvox/s, rot45 and full affine."""
-    from voltools_b200 import _native
-    n = args.size
+def sweep_e2e(args, torch, vt, dev, barrier, reduce_max, shape, interp, mats, mine, vol, out_dev):
+    """The headline job end to end through the public API with HOST buffers: the volume starts in pinned host memory on
+    rank 0, every output volume ends in host memory (`sv.affine(m)` returns numpy, like the reference's .get())."""
+    from voltools_b200 import multigpu
+    rank, _, world = dist_env()
+    n = shape[0]
+    h_vol = None
+    if rank == 0:
+        h_vol = torch.empty(shape, dtype=torch.float32).pin_memory()
+        h_vol.copy_(vol)
+        h_vol = h_vol.numpy()
+    eng = multigpu.CudaEngine(dev)
+    check = {}
+
+    def step():
+        if world > 1:
+            buf, width = multigpu.prepare_and_broadcast(eng, h_vol, interp, src=0, shape=shape)
+            sv = vt.StaticVolume.from_coefficients(buf, interp, width)
+        else:
+            sv = vt.StaticVolume(h_vol, interpolation=interp, device=f'gpu:{dev}')
+        for k, i in enumerate(mine):
+            res = sv.affine(mats[i])  # numpy (pinned staging inside the library)
+            if k == len(mine) // 2:
+                check['res'], check['k'] = res, k
+
+    steps = max(1, min(args.steps, 3))
+    step()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    sec = reduce_max(time.perf_counter() - t0)
+    barrier()
+    if 'res' in check:  # the host path must agree with the device path
+        err = float((torch.from_numpy(check['res']).to(f'cuda:{dev}') - out_dev[check['k']]).abs().max())
+        assert err <= 1e-5 * 16, f'host path differs from device path: {err}'
+    vox = len(mats) * n ** 3
+    return {'value': vox * steps / sec / 1e9, 'unit': METRIC, 'h2d_bytes_per_step': n ** 3 * 4,
+            'd2h_bytes_per_step': vox * 4, 'steps': steps, 'ms_per_step': sec / steps * 1e3,
+            'call': "StaticVolume(host volume, 'filt_bspline') then sv.affine(m) -> numpy for each of the rank's angles "
+                    '(H2D of the volume and D2H of every output volume inside the timed region; wall clock, max over ranks)',
+            'bound': 'PCIe D2H: 180 x 64 MiB per step'}
+
+
+def random_rotation_mats(vt, n, count):
+    """The reference benchmark's matrices (tests/benchmark.py:52-54): 100 random 3-axis rotations, order 'sxyz', about
+    centre = size/2 -- here the first `count` of a seeded set."""
+    rots = np.random.default_rng(1).uniform(-180, 180, (100, 3))[:count]
+    c = (n / 2, n / 2, n / 2)
+    return [vt.utils.transform_matrix(rotation=tuple(r), rotation_units='deg', rotation_order='sxyz', center=c) for r in rots]
+
+
+def run_modes(args, torch, vt, dev, n=None, steps=None, warmup=None, random_count=8):
+    """All five modes at n^3 through affine(output=): kernel-level Gvox/s for rot45, the full affine and the reference
+    benchmark's random rotations; L2 flushed between iterations, median."""
+    n = n or args.size
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
     shape = (n, n, n)
     peak, _ = peaks()
     c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
-    mats = {'rot45': vt.utils.transform_matrix(center=c, **ROT45),
-            'full_affine': vt.utils.transform_matrix(center=c, **FULL_AFFINE)}
+    mats = {'rot45': [vt.utils.transform_matrix(center=c, **ROT45)],
+            'full_affine': [vt.utils.transform_matrix(center=c, **FULL_AFFINE)],
+            'random_rotations': random_rotation_mats(vt, n, random_count)}
     src = torch.rand(shape, device=f'cuda:{dev}')
     dst = torch.zeros(shape, device=f'cuda:{dev}')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f'cuda:{dev}')
     res = {}
     for mode in vt.AVAILABLE_INTERPOLATIONS:
-        for mname, m in mats.items():
-            ts = []
-            for it in range(args.warmup + args.steps):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                vt.affine(src, m, interpolation=mode, output=dst, device=f'gpu:{dev}')
-                e1.record()
-                e1.synchronize()
-                if it >= args.warmup:
-                    ts.append(e0.elapsed_time(e1))
-            ms = statistics.median(ts)
+        for mname, ms_list in mats.items():
+            per = []
+            for m in ms_list:
+                k = steps if len(ms_list) == 1 else max(2, steps // 3)
+                per.append(med_ms(torch, lambda: vt.affine(src, m, interpolation=mode, output=dst, device=f'gpu:{dev}'),
+                                  k, warmup if len(ms_list) == 1 else 1, flush))
+            ms = float(np.mean(per))
             bytes_per_vox = 16 if mode.startswith('filt') else 8
             res[f'{mode}/{mname}'] = {'ms': ms, 'gvox_s': n ** 3 / ms / 1e6,
-                                      'roofline_frac': bytes_per_vox * n ** 3 / (ms * 1e-3) / 1e9 / peak}
+                                      'roofline_frac': bytes_per_vox * n ** 3 / (ms * 1e-3) / 1e9 / peak,
+                                      'inbounds_fraction': float(np.mean([inbounds_fraction(shape, m) for m in ms_list])),
+                                      'matrices': len(ms_list)}
+    # resident volumes (StaticVolume: prefilter / layouts paid once): the same three matrix classes
+    for mode in vt.AVAILABLE_INTERPOLATIONS:
+        sv = vt.StaticVolume(src, interpolation=mode, device=f'gpu:{dev}')
+        for mname, ms_list in mats.items():
+            per = [med_ms(torch, lambda: sv.affine(m, output=dst), max(2, steps // 2), 2, flush) for m in ms_list]
+            ms = float(np.mean(per))
+            res[f'static/{mode}/{mname}'] = {'ms': ms, 'gvox_s': n ** 3 / ms / 1e6,
+                                             'roofline_frac': 8 * n ** 3 / (ms * 1e-3) / 1e9 / peak}
+        del sv
+    return res
+
+
+def run_cfg1(args, torch, vt, dev):
+    """configs[1]: transform() of 250^3 'filt_bspline' rot45, a batch of 8 independent device-resident volumes per step
+    through the public API -- eager calls on one stream (`value`), and the same calls on two streams replayed from a CUDA
+    graph (labelled)."""
+    cfg = CFG1
+    n, batch, interp, kw = cfg['n'], cfg['batch'], cfg['interpolation'], cfg['kw']
+    shape = (n, n, n)
+    device = f'gpu:{dev}'
+    gen = torch.Generator(device=f'cuda:{dev}').manual_seed(1234)
+    vols = [torch.rand(shape, generator=gen, device=f'cuda:{dev}', dtype=torch.float32) for _ in range(batch)]
+    outs = [torch.zeros(shape, device=f'cuda:{dev}', dtype=torch.float32) for _ in range(batch)]
+
+    def step():
+        for v, o in zip(vols, outs):
+            vt.transform(v, interpolation=interp, output=o, device=device, **kw)
+
+    sec = timed(torch, step, args.steps, 3, lambda: None)
+    res = {'workload': "configs[1]: transform() 250^3 float32 'filt_bspline' rotation=(0,45,0) rzxz, batch of 8 volumes "
+                       '(inputs larger than L2), eager calls on one stream',
+           'value': batch * n ** 3 * args.steps / sec / 1e9, 'unit': METRIC, 'ms_per_volume': sec / args.steps / batch * 1e3,
+           'roofline_frac_16B_per_voxel': 16.0 * batch * n ** 3 * args.steps / sec / 1e9 / peaks()[0]}
+    # labelled extra: two streams + CUDA graph replay of the same calls
+    try:
+        side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
+        def step2():
+            main_stream = torch.cuda.current_stream(dev)
+            for s in side:
+                s.wait_stream(main_stream)
+            for i, (v, o) in enumerate(zip(vols, outs)):
+                with torch.cuda.stream(side[i % 2]):
+                    vt.transform(v, interpolation=interp, output=o, device=device, **kw)
+            for s in side:
+                main_stream.wait_stream(s)
+
+        step2()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step2()
+        g.replay()
+        torch.cuda.synchronize()
+        sec_g = timed(torch, g.replay, args.steps, 2, lambda: None)
+        res['graph_replay_2_streams_value'] = batch * n ** 3 * args.steps / sec_g / 1e9
+    except Exception as e:  # informational
+        res['graph_replay_2_streams_value'] = None
+        res['graph_error'] = repr(e)
+        torch.cuda.synchronize()
+    # host path: pinned and pageable numpy in -> numpy out, one thread
+    h_vol = torch.empty(shape, dtype=torch.float32).pin_memory()
+    h_vol.copy_(vols[0])
+    h_out = torch.empty(shape, dtype=torch.float32).pin_memory()
+    pinned_in, pinned_out = h_vol.numpy(), h_out.numpy()
+    pageable_in = np.array(pinned_in, copy=True)
+    for label, call in (('pinned', lambda: vt.transform(pinned_in, interpolation=interp, output=pinned_out, device=device, **kw)),
+                        ('pageable', lambda: vt.transform(pageable_in, interpolation=interp, device=device, **kw))):
+        call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            call()
+        torch.cuda.synchronize()
+        res[f'e2e_{label}_numpy_value'] = 5 * n ** 3 / (time.perf_counter() - t0) / 1e9
     return res
 
 
@@ -489,20 +571,6 @@ def run_project(args, torch, vt, dev):
     dst = torch.zeros(shape, device=f'cuda:{dev}')
     proj = torch.zeros((1, n, n), device=f'cuda:{dev}')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f'cuda:{dev}')
-
-    def med(fn):
-        ts = []
-        for it in range(args.warmup + args.steps):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            e1.synchronize()
-            if it >= args.warmup:
-                ts.append(e0.elapsed_time(e1))
-        return statistics.median(ts)
-
     res = {}
     for mode in ('linear', 'filt_bspline', 'filt_bspline_simple'):
         sv = vt.StaticVolume(src, interpolation=mode, device=f'gpu:{dev}')
@@ -511,83 +579,52 @@ def run_project(args, torch, vt, dev):
                 dst.zero_()
                 sv.affine(m, output=dst)
                 return dst.sum(dim=0)
-            ms_u = med(unfused)
-            ms_f = med(lambda: sv.project_many([m], output=proj))
+            ms_u = med_ms(torch, unfused, args.steps, args.warmup, flush)
+            ms_f = med_ms(torch, lambda: sv.project_many([m], output=proj), args.steps, args.warmup, flush)
             err = float((proj[0].double() - unfused().double()).abs().max()) / (float(dst.max() - dst.min()) * n)
             res[f'{mode}/{mname}'] = {'fused_ms': ms_f, 'transform_then_sum_ms': ms_u, 'speedup': ms_u / ms_f,
                                       'fused_gvox_s': n ** 3 / ms_f / 1e6, 'max_err_of_scale': err}
     return res
 
 
-def run_sweep(args, torch, vt, dev, barrier, reduce_max):
-    """configs[2]: StaticVolume 256^3 filt_bspline, 180-angle sweep rotation=(0,i,0); root prefilters, one broadcast of
-    the coefficient buffer (NCCL), angles split across ranks.  Strong scaling: the 180 angles are the fixed job."""
-    from voltools_b200 import _native, multigpu
-    import torch.distributed as dist
-    rank, _, world = dist_env()
-    n = args.size if args.size != 512 else 256
-    shape = (n, n, n)
-    c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
-    mats = [vt.utils.transform_matrix(rotation=(0, i, 0), rotation_order='rzxz', center=c) for i in range(180)]
-    vol = torch.rand(shape, device=f'cuda:{dev}', generator=torch.Generator(f'cuda:{dev}').manual_seed(7)) \
-        if rank == 0 else None
-    mine = multigpu.split_strided(len(mats), world, rank)
-    out = torch.empty((len(mine),) + shape, device=f'cuda:{dev}')
-    eng = multigpu.CudaEngine(dev)
-
-    def step():
-        if world > 1:
-            outs, _ = multigpu.sweep(vol, mats, 'filt_bspline', src=0, engine=eng, shape=shape)
-        else:
-            buf, width = eng.prepare(vol, 'filt_bspline')
-            sv = vt.StaticVolume.from_coefficients(buf, 'filt_bspline', width)
-            sv.affine_many(mats, output=out, zero_fill=True)
-
-    l0 = _native.launch_count()
-    sec = reduce_max(timed(torch, step, args.steps, max(3, args.warmup), barrier))
-    launches = _native.launch_count() - l0
-    value = len(mats) * n ** 3 * args.steps / sec / 1e9
-    peak, _ = peaks()
-    return {'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(3, args.warmup), 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'configs[2]: StaticVolume {n}^3 filt_bspline, 180-angle sweep rotation=(0,i,0), '
-                                   'prefilter on rank 0 + 1 NCCL broadcast + angles split across ranks',
-                       'parallelism': f'dp{world}', 'l2': 'outputs (180 volumes) exceed L2; the coefficient volume is '
-                                                         'L2-resident by design'},
-            'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'note': '8 B/voxel/matrix', 'frac': 8.0 * value / peak / world, 'peak': peak}}
-
-
-def run_zslab(args, torch, vt, dev, barrier, reduce_max):
-    """configs[4]: one large filt_bspline full-affine transform, output z-slabs split across ranks."""
+def run_zslab(args, torch, vt, dev, barrier, reduce_max, n=None, steps=None):
+    """configs[4]: one large filt_bspline transform, the output split into z-slabs across the ranks.  The raw volume
+    starts on rank 0; distribution (prefilter + getting every rank the input footprint of its slab) and resampling are
+    timed separately with CUDA events (max over ranks each)."""
     from voltools_b200 import _native, multigpu
     rank, _, world = dist_env()
-    n = args.size
+    n = n or args.size
+    steps = steps or args.steps
     shape = (n, n, n)
     c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
-    m = vt.utils.transform_matrix(center=c, **FULL_AFFINE)
     vol = torch.rand(shape, device=f'cuda:{dev}', generator=torch.Generator(f'cuda:{dev}').manual_seed(7)) \
         if rank == 0 else None
     eng = multigpu.CudaEngine(dev)
+    res = {}
+    for label, kw in (('mild_rotation', MILD), ('full_affine', FULL_AFFINE)):
+        m = vt.utils.transform_matrix(center=c, **kw)
+        phases = []
 
-    def step():
-        if world > 1:
-            multigpu.zslab_affine(vol, m, 'filt_bspline', src=0, engine=eng, shape=shape)
-        else:
-            buf, width = eng.prepare(vol, 'filt_bspline')
-            eng.resample_slab(buf, width, 'filt_bspline', m, 0, n)
+        def step():
+            t = {}
+            multigpu.zslab_affine(vol, m, 'filt_bspline', src=0, engine=eng, shape=shape, timings=t)
+            phases.append(t)
 
-    l0 = _native.launch_count()
-    sec = reduce_max(timed(torch, step, args.steps, max(3, args.warmup), barrier))
-    launches = _native.launch_count() - l0
-    value = n ** 3 * args.steps / sec / 1e9
-    return {'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(3, args.warmup), 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'configs[4]: {n}^3 filt_bspline full affine, prefilter on rank 0 + NCCL broadcast of '
-                                   'the coefficients + output z-slabs across ranks', 'parallelism': f'dp{world}'},
-            'gpu_launches': int(launches)}
+        for _ in range(2):
+            step()
+        phases.clear()
+        l0 = _native.launch_count()
+        sec = reduce_max(timed(torch, step, steps, 0, barrier))
+        launches = _native.launch_count() - l0
+        dist_ms = reduce_max(statistics.median(p['distribute_ms']() for p in phases))
+        res_ms = reduce_max(statistics.median(p['resample_ms']() for p in phases))
+        info = phases[-1].get('info', {})
+        res[label] = {'value': n ** 3 * steps / sec / 1e9, 'unit': METRIC, 'ms_per_step': sec / steps * 1e3,
+                      'distribute_ms': dist_ms, 'resample_ms': res_ms, 'gpu_launches': int(launches),
+                      'inbounds_fraction': inbounds_fraction(shape, m), **info}
+    res['workload'] = (f'configs[4]: {n}^3 filt_bspline, raw volume on rank 0, output z-slabs across {world} rank(s); '
+                       'strong scaling')
+    return res
 
 
 def main():
@@ -596,19 +633,14 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg1', choices=['cfg1', 'modes', 'sweep', 'zslab', 'project', 'cpu_baselines'])
+    ap.add_argument('--workload', default='all',
+                    choices=['all', 'sweep', 'modes', 'zslab', 'cfg1', 'project', 'cpu_baselines'])
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-graph', action='store_true', help='time eager calls instead of replaying a captured CUDA graph')
-    ap.add_argument('--streams', type=int, default=2, help="CUDA streams the step's independent volumes are issued on")
-    ap.add_argument('--batch', type=int, default=None, help='volumes per step (default 8; smaller only for profiling)')
+    ap.add_argument('--no-extras', action='store_true', help='headline only (no modes_512 / zslab_1024 / cfg1 tables)')
     args = ap.parse_args()
-    cfg = dict(CFG1)
-    if args.batch:
-        cfg['batch'] = args.batch
-        cfg['name'] = cfg['name'].replace('batch of 8', f'batch of {args.batch}')
     if args.impl == 'reference':
-        reference_arm(args, cfg)
+        reference_arm(args, SWEEP)
         return
     if args.workload == 'cpu_baselines':
         print(json.dumps({'metric': METRIC, 'workload': 'CPU baselines (SURVEY 8d), rot45, one core',
@@ -621,8 +653,8 @@ def main():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback)')
     dev = local_rank % torch.cuda.device_count()
     torch.cuda.set_device(dev)
+    import torch.distributed as dist
     if world > 1:
-        import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{dev}'))
 
         def barrier():
@@ -639,36 +671,40 @@ def main():
         def reduce_max(x):
             return x
 
-    if args.workload == 'modes':
-        res = run_modes(args, torch, vt, dev)
-        if rank == 0:
-            print(json.dumps({'metric': METRIC, 'workload': f'modes {args.size}^3', 'modes': res}))
-        return
-    if args.workload == 'project':
-        res = run_project(args, torch, vt, dev)
-        if rank == 0:
-            print(json.dumps({'metric': METRIC, 'workload': f'rotate-and-project {args.size}^3', 'project': res}))
-        return
-    if args.workload in ('sweep', 'zslab'):
-        if world == 1:  # single-process: the helpers still want a process group for get_rank()
-            import torch.distributed as dist
-            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-            os.environ.setdefault('MASTER_PORT', '29533')
-            dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device(f'cuda:{dev}'))
-        line = (run_sweep if args.workload == 'sweep' else run_zslab)(args, torch, vt, dev, barrier, reduce_max)
-        if rank == 0:
-            print(json.dumps(line))
-        import torch.distributed as dist
-        dist.destroy_process_group()
-        return
-    line = run_cfg1(args, cfg, torch, vt, dev, barrier, reduce_max)
-    if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline_leg(cfg)
-        print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    try:
+        if args.workload == 'modes':
+            res = run_modes(args, torch, vt, dev)
+            if rank == 0:
+                print(json.dumps({'metric': METRIC, 'workload': f'modes {args.size}^3', 'modes': res}))
+        elif args.workload == 'project':
+            res = run_project(args, torch, vt, dev)
+            if rank == 0:
+                print(json.dumps({'metric': METRIC, 'workload': f'rotate-and-project {args.size}^3', 'project': res}))
+        elif args.workload == 'cfg1':
+            res = run_cfg1(args, torch, vt, dev)
+            if rank == 0:
+                print(json.dumps({'metric': METRIC, 'cfg1': res}))
+        elif args.workload == 'zslab':
+            res = run_zslab(args, torch, vt, dev, barrier, reduce_max)
+            if rank == 0:
+                print(json.dumps({'metric': METRIC, 'n_gpus': world, 'zslab': res}))
+        else:
+            line = run_sweep(args, torch, vt, dev, barrier, reduce_max)
+            if args.workload == 'all' and not args.no_extras:
+                torch.cuda.empty_cache()
+                line['zslab_1024'] = run_zslab(args, torch, vt, dev, barrier, reduce_max, n=1024, steps=3)
+                torch.cuda.empty_cache()
+                if world == 1:
+                    line['modes_512'] = run_modes(args, torch, vt, dev, n=512, steps=6, warmup=2)
+                    torch.cuda.empty_cache()
+                    line['cfg1'] = run_cfg1(args, torch, vt, dev)
+            if rank == 0:
+                if world == 1 and not args.no_cpu_baseline:
+                    line['cpu_baseline'] = cpu_baseline_leg(SWEEP)
+                print(json.dumps(line))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -52,6 +52,52 @@ def test_partitions_cover_everything_once():
             assert z[0][0] == 0 and z[-1][1] == n and all(z[i][1] == z[i + 1][0] for i in range(world - 1))
 
 
+def test_slab_footprints_cover_every_tap():
+    """Every texel a slab's kernels can multiply into a result lies in a box / block its rank receives (or owns)."""
+    rng = np.random.default_rng(5)
+    for shape, world in (((32, 32, 64), 2), ((64, 32, 32), 4), ((24, 20, 28), 3)):
+        c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+        for trial in range(6):
+            m = transform_matrix(rotation=tuple(rng.uniform(-40, 40, 3)), rotation_order='sxyz', center=c,
+                                 scale=tuple(rng.uniform(0.8, 1.25, 3)), translation=tuple(rng.uniform(-4, 4, 3)))
+            boxes = multigpu.slab_footprint_boxes(m, shape, world)
+            block = multigpu.footprint_block_size(shape, world)
+            blocks = multigpu.slab_footprint_blocks(m, shape, shape[2], world, block) if block else None
+            assert (block is None) == (shape == (24, 20, 28))
+            a = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing='ij'), -1).reshape(-1, 3).astype(np.float32)
+            p = a @ m[:3, :3].T.astype(np.float32) + m[:3, 3]  # index-space sample points (float32 like the kernels)
+            ok = np.all((p + 0.5 >= 0) & (p + 0.5 < np.array(shape)), axis=1)
+            base = np.floor(p).astype(int)
+            for q in range(world):
+                z0, z1 = multigpu.split_slabs(shape[0], world, q)
+                sel = ok & (a[:, 0] >= z0) & (a[:, 0] < z1)
+                have = np.zeros(shape, bool)
+                for (r, qq), bx in boxes.items():
+                    if qq == q:
+                        lo, hi = bx
+                        have[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = True
+                have_b = np.zeros(shape, bool)
+                if blocks is not None:
+                    for (r, qq), idx in blocks.items():
+                        if qq == q:
+                            for iz, iy, ix in idx:
+                                have_b[iz * block[0]:(iz + 1) * block[0], iy * block[1]:(iy + 1) * block[1],
+                                       ix * block[2]:(ix + 1) * block[2]] = True
+                for dz in (-1, 0, 1, 2):
+                    for dy in (-1, 0, 1, 2):
+                        for dx in (-1, 0, 1, 2):
+                            t = base[sel] + np.array([dz, dy, dx])
+                            inside = np.all((t >= 0) & (t < np.array(shape)), axis=1)
+                            t = t[inside]
+                            assert have[t[:, 0], t[:, 1], t[:, 2]].all(), (shape, world, trial, q, 'boxes')
+                            if blocks is not None:
+                                assert have_b[t[:, 0], t[:, 1], t[:, 2]].all(), (shape, world, trial, q, 'blocks')
+            # an owner only sends what it owns
+            for (r, q), (lo, hi) in boxes.items():
+                i0, i1 = multigpu.split_slabs(shape[0], world, r)
+                assert i0 <= lo[0] < hi[0] <= i1
+
+
 class OracleEngine:
     """CPU stand-in for CudaEngine (test infrastructure): same interface, oracle arithmetic, torch CPU tensors."""
 
@@ -88,6 +134,17 @@ class OracleEngine:
     def empty(self, shape):
         import torch
         return torch.empty(shape, dtype=torch.float32)
+
+    def to_device(self, volume):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(volume, np.float32))
+
+    def prefilter_slab(self, raw_slab, buffer, shape, interpolation, xy0, xy1, z0, z1):
+        import torch
+        v = raw_slab.numpy()
+        # the sub-volume's ends stand in for the true ends 12 planes away: |pole|^12 = 1.4e-7 of the range
+        coef = oracle.prefilter(v) if interpolation.startswith('filt') else v
+        buffer[z0:z1].copy_(torch.from_numpy(np.ascontiguousarray(coef[z0 - xy0:z1 - xy0])))
 
     @staticmethod
     def _mode(interpolation):  # the buffer already holds coefficients
@@ -140,6 +197,17 @@ def _worker(rank, world, init_file, outdir):
         full = multigpu.gather_slabs(slab, dst=0)
         np.savez(os.path.join(outdir, f'slab_{rank}.npz'), slab=slab.numpy(), z=np.array([z0, z1]),
                  full=full.numpy() if full is not None else np.zeros(0))
+        # footprint path: raw z-slabs scattered, per-rank prefilter, block-sparse / boxed exchange of what each slab reads
+        big = np.random.default_rng(44).random((64, 32, 48), dtype=np.float32)
+        cb = np.divide(np.subtract(big.shape, 1), 2, dtype=np.float32)
+        for tag, mm, shp, v in (('blocks', transform_matrix(rotation=(5, 8, -6), rotation_order='sxyz', center=cb,
+                                                            translation=(1.5, -2, 1)), big.shape, big),
+                                ('boxes', m, shape, vol)):
+            info = {}
+            slab_f, zr = multigpu.zslab_affine(v if rank == 0 else None, mm, 'filt_bspline', src=0, engine=eng, shape=shp,
+                                               footprint=True, timings=info)
+            np.savez(os.path.join(outdir, f'fp_{tag}_{rank}.npz'), slab=slab_f.numpy(), z=np.array(zr),
+                     path=np.array([info['info']['path']]), block=np.array(info['info']['footprint_block'] or (0, 0, 0)))
         # rotate-and-project: a tilt series split across the ranks, and one projection summed from z-slabs (all-reduce)
         tilts = [transform_matrix(rotation=(a, 0, 0), rotation_order='sxyz', center=c) for a in (-60, -20, 15, 50, 72)]
         proj, pidx = multigpu.project_sweep(vol if rank == 0 else None, tilts, 'filt_bspline', src=0, engine=eng)
@@ -185,6 +253,20 @@ def test_sweep_and_zslab_two_ranks_gloo():
         assert tuple(z0['z']) == (0, 7) and tuple(z1['z']) == (7, 13)
         assert np.array_equal(z0['slab'], want[0:7]) and np.array_equal(z1['slab'], want[7:13])
         assert np.array_equal(z0['full'], want)
+        # footprint path: every rank only ever held its slab's input footprint; results agree with the one-GPU answer to
+        # the windowed prefilter's 1e-6 of the coefficient range
+        big = np.random.default_rng(44).random((64, 32, 48), dtype=np.float32)
+        cb = np.divide(np.subtract(big.shape, 1), 2, dtype=np.float32)
+        mb = transform_matrix(rotation=(5, 8, -6), rotation_order='sxyz', center=cb, translation=(1.5, -2, 1))
+        for tag, mm, v in (('blocks', mb, big), ('boxes', m, vol)):
+            ref = oracle.affine(v, mm, 'filt_bspline')
+            tol = 2e-6 * float(np.ptp(oracle.prefilter(v)))
+            for r in range(world):
+                z = np.load(os.path.join(d, f'fp_{tag}_{r}.npz'))
+                assert str(z['path'][0]) == 'footprint'
+                assert (tuple(z['block']) != (0, 0, 0)) == (tag == 'blocks')
+                a, b = (int(t) for t in z['z'])
+                assert np.abs(z['slab'] - ref[a:b]).max() <= tol, (tag, r)
         tilts = [transform_matrix(rotation=(a, 0, 0), rotation_order='sxyz', center=c) for a in (-60, -20, 15, 50, 72)]
         seen = []
         for r in range(world):

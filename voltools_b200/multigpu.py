@@ -127,6 +127,43 @@ class CudaEngine:
     def empty(self, shape):
         return self.torch.empty(shape, dtype=self.torch.float32, device=self.device)
 
+    def to_device(self, volume):
+        """The raw samples as a contiguous float32 tensor on this rank's GPU (root only)."""
+        torch = self.torch
+        if isinstance(volume, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(volume, np.float32)).to(self.device)
+        return torch.as_tensor(volume, dtype=torch.float32, device=self.device).contiguous()
+
+    def prefilter_slab(self, raw_slab, buffer, shape, interpolation, xy0, xy1, z0, z1):
+        """`raw_slab` holds sample planes [xy0, xy1) of a volume of `shape`; makes planes [z0, z1) of the full-size
+        resident `buffer` (padded rows) final.  The windowed prefilter treats xy1 as an artificial end 12 planes past z1
+        (vt_prefilter_planes_f32), so a z-slab of coefficients costs its own planes plus a 12-plane halo of samples."""
+        from . import _native
+        from ._native import INTERPOLATIONS
+        torch = self.torch
+        _, filtered = INTERPOLATIONS[interpolation]
+        d0, d1, d2 = (int(v) for v in shape)
+        row = int(buffer.shape[2])
+        if not filtered:
+            if z1 > z0:
+                buffer[z0:z1, :, :d2].copy_(raw_slab[z0 - xy0:z1 - xy0])
+                if row != d2:
+                    buffer[z0:z1, :, d2:].zero_()
+            return
+        ws = torch.empty((xy1 - xy0, d1, row), dtype=torch.float32, device=self.device)
+        # the ABI addresses planes absolutely: hand it the slab buffers shifted back by xy0 planes
+        raw_base = raw_slab.data_ptr() - xy0 * d1 * d2 * 4
+        ws_base = ws.data_ptr() - xy0 * d1 * row * 4
+        with torch.cuda.device(self.dev):
+            _native.prefilter_planes(raw_base, ws_base, buffer.data_ptr(), (xy1, d1, d2), (row, d1 * row), (xy0, xy1),
+                                     (z0, z1), self.dev, torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def timer(self):
+        """A stream-ordered time stamp: returns a callable giving milliseconds since `since` (another stamp)."""
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.torch.cuda.current_stream(self.device))
+        return ev
+
     def _resident(self, buffer, interpolation, width, complete=True):
         """StaticVolume view of a received buffer (no copy).  complete=False: the buffer is still being filled
         (streaming), so no second layout may be derived from it: plain-layout kernels only."""
@@ -169,7 +206,7 @@ class CudaEngine:
         return out
 
 
-def _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape=None, on_planes=None, chunks=None):
+def _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape=None, on_planes=None, chunks=None):  # noqa: E501
     """Root: upload + prefilter; everyone: receive the resident buffer.  Pipelined in z-chunks: the broadcast of the
     planes that are final runs (async, on the communicator's stream) while the root prefilters the next chunk.
     `shape`: the volume's shape if every rank knows it (saves the metadata broadcast, a host round trip).
@@ -203,6 +240,139 @@ def _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shap
         if on_planes is not None:
             on_planes(buffer, width, z1)
     return buffer, width
+
+
+def prepare_and_broadcast(engine, volume, interpolation, src: int = 0, group=None, shape=None, chunks=None):
+    """Public form of the sweep's first phase: the root uploads + prefilters, one (z-chunk pipelined) NCCL broadcast
+    ships the coefficient buffer; returns (buffer, width) on every rank -- wrap it with
+    StaticVolume.from_coefficients(buffer, interpolation, width)."""
+    import torch.distributed as dist
+    return _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape, None, chunks)
+
+
+# ----------------------------------------------------------------------------------------------------
+# z-slab sharding with per-slab input footprints
+# ----------------------------------------------------------------------------------------------------
+def _clip_image_bbox(m64, obox, z_lo, z_hi):
+    """Bounding box (float, input index space) of {M a : a in the output index box} intersected with the input slab
+    z_lo <= p0 <= z_hi, or None if empty.  The image is a parallelepiped: its intersection with the slab is spanned by
+    the vertices inside it and the points where its 12 edges cross the two bounding planes."""
+    corners = np.array([[a0, a1, a2, 1.0] for a0 in obox[0] for a1 in obox[1] for a2 in obox[2]])
+    p = corners @ m64[:3].T  # (8, 3)
+    pts = [v for v in p if z_lo <= v[0] <= z_hi]
+    for i in range(8):
+        for j in range(i + 1, 8):
+            if bin(i ^ j).count('1') != 1:
+                continue
+            d = p[j][0] - p[i][0]
+            if d == 0.0:
+                continue
+            for zc in (z_lo, z_hi):
+                t = (zc - p[i][0]) / d
+                if 0.0 <= t <= 1.0:
+                    pts.append(p[i] + t * (p[j] - p[i]))
+    if not pts:
+        return None
+    pts = np.asarray(pts)
+    return pts.min(axis=0), pts.max(axis=0)
+
+
+def slab_footprint_boxes(matrix, shape, world: int, halo: int = 3):
+    """Which part of the sampled volume each output z-slab reads, owner by owner.
+
+    The sampled (coefficient) volume is owned in z-slabs I_r = split_slabs(d0, world, r); output slab q =
+    split_slabs(d0, world, q) samples the affine image of its index box, a parallelepiped.  Returns {(r, q): (lo, hi)}:
+    the integer box [lo, hi) inside I_r that contains every texel rank q's kernels can multiply into a result -- the
+    bounding box of (image of slab q) intersected with I_r, grown by `halo` texels (filter support: taps reach
+    floor(p) - 1 .. floor(p) + 2) and clipped to the volume; pairs with nothing to send are absent.  Pure host
+    arithmetic, identical on every rank."""
+    m64 = np.asarray(matrix, dtype=np.float64).reshape(4, 4)
+    d = [int(v) for v in shape]
+    boxes = {}
+    for q in range(world):
+        z0, z1 = split_slabs(d[0], world, q)
+        if z1 <= z0:
+            continue
+        obox = ((z0, z1 - 1), (0, d[1] - 1), (0, d[2] - 1))
+        for r in range(world):
+            i0, i1 = split_slabs(d[0], world, r)
+            if i1 <= i0:
+                continue
+            bb = _clip_image_bbox(m64, obox, i0 - halo - 1, i1 + halo)
+            if bb is None:
+                continue
+            lo = np.floor(bb[0]).astype(np.int64) - halo
+            hi = np.ceil(bb[1]).astype(np.int64) + halo + 1
+            lo = np.maximum(lo, 0)
+            hi = np.minimum(hi, d)
+            lo[0], hi[0] = max(lo[0], i0), min(hi[0], i1)
+            if np.all(hi > lo):
+                boxes[(r, q)] = (tuple(int(v) for v in lo), tuple(int(v) for v in hi))
+    return boxes
+
+
+def footprint_block_size(buf_shape, world: int):
+    """Block edge lengths (bz, by, bx) for `slab_footprint_blocks`, or None: blocks must tile the resident buffer
+    exactly and must not straddle two owners' z-slabs."""
+    d0, d1, row = (int(v) for v in buf_shape)
+    pick = []
+    for extent, cands, unit in ((d0, (32, 16, 8), world), (d1, (64, 32, 16), 1), (row, (64, 32, 16), 1)):
+        b = next((c for c in cands if extent % (c * unit) == 0), None)
+        if b is None:
+            return None
+        pick.append(b)
+    return tuple(pick)
+
+
+def slab_footprint_blocks(matrix, buf_shape, width: int, world: int, block, halo: int = 3):
+    """Block-sparse form of `slab_footprint_boxes`: the resident buffer (d0, d1, row) is tiled by `block` =
+    (bz, by, bx) texels; returns {(r, q): int64 array (n, 3) of block indices} -- the blocks owned by rank r (its z-slab
+    of the sampled volume) that output slab q can sample.  A block, grown by `halo` texels of filter support, is needed
+    iff its pre-image under the matrix meets the slab's output index box; the pre-image's extent along each output axis
+    is attained at the block's corners (the inverse map is affine), so the test is exact.  An oblique slab of a 1024^3
+    volume under BASELINE's full affine needs 20 % of the volume this way (its bounding boxes: 57 %)."""
+    m64 = np.asarray(matrix, dtype=np.float64).reshape(4, 4)
+    inv = np.linalg.inv(m64)
+    d0, d1, row = (int(v) for v in buf_shape)
+    bz, by, bx = block
+    nb = (d0 // bz, d1 // by, row // bx)
+    g = np.stack(np.meshgrid(*[np.arange(n) for n in nb], indexing='ij'), axis=-1).reshape(-1, 3)
+    lo = g * np.array(block) - halo
+    hi = lo + np.array(block) + 2 * halo - 1  # inclusive texel range the block's taps may serve
+    mins = np.full((len(g), 3), np.inf)
+    maxs = -mins
+    for corner in range(8):
+        sel = np.array([(corner >> 2) & 1, (corner >> 1) & 1, corner & 1])
+        p = np.where(sel == 1, hi, lo).astype(np.float64)
+        a = p @ inv[:3, :3].T + inv[:3, 3]
+        mins = np.minimum(mins, a)
+        maxs = np.maximum(maxs, a)
+    out_hi = np.array([d0 - 1, d1 - 1, width - 1], dtype=np.float64)
+    inside = np.all(maxs[:, 1:] >= -1.0, axis=1) & np.all(mins[:, 1:] <= out_hi[1:] + 1.0, axis=1)
+    slab_planes = d0 // world
+    owner = (g[:, 0] * bz) // slab_planes
+    res = {}
+    for q in range(world):
+        z0, z1 = split_slabs(d0, world, q)
+        need = inside & (maxs[:, 0] >= z0 - 1.0) & (mins[:, 0] <= z1)
+        for r in range(world):
+            sel = g[need & (owner == r)]
+            if len(sel):
+                res[(r, q)] = sel.astype(np.int64)
+    return res
+
+
+def footprint_fraction(boxes, shape, world: int, block=None):
+    """Largest share of the volume any rank has to RECEIVE from the others under `boxes` (or block lists)."""
+    vol = float(np.prod([int(v) for v in shape]))
+    worst = 0.0
+    for q in range(world):
+        if block is None:
+            got = sum(float(np.prod(np.subtract(hi, lo))) for (r, qq), (lo, hi) in boxes.items() if qq == q and r != q)
+        else:
+            got = sum(float(len(idx)) * float(np.prod(block)) for (r, qq), idx in boxes.items() if qq == q and r != q)
+        worst = max(worst, got / vol)
+    return worst
 
 
 def streaming_margin(matrices: np.ndarray, interpolation: str):
@@ -265,10 +435,24 @@ def sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = 'filt_bsp
     return out, list(mine)
 
 
+_FOOTPRINT_PLANS = {}
+
+
 def zslab_affine(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline', src: int = 0, group=None,
-                 engine=None, shape=None):
+                 engine=None, shape=None, timings: dict = None, footprint='auto'):
     """One transform of one (large) volume, the output split into z-slabs across the ranks of `group`.
 
+    The raw volume lives on rank `src`.  Two ways of getting every rank what its slab samples:
+      * footprint path (needs `shape` on every rank): the root scatters raw z-slabs (+ 12 planes of prefilter halo),
+        every rank prefilters ITS slab (vt_prefilter_planes_f32), then the ranks exchange, pairwise and all at once,
+        only the boxes of coefficients each output slab reads from each owner (`slab_footprint_boxes`: the affine
+        image of the slab, owner by owner, + filter halo).  No rank ever holds more than its slab's input footprint;
+        the root sends (world-1)/world of the volume once instead of broadcasting all of it.
+      * broadcast path: the root prefilters everything and one NCCL broadcast ships the whole coefficient volume --
+        used when the footprints are nearly the whole volume anyway (`footprint='auto'`: largest receive share >= 0.9
+        minus the rank's own slab) or when the shape is not known everywhere.
+    timings (optional dict): filled with 'distribute_ms' / 'resample_ms' callables (CUDA events on the engine's stream;
+    call them after a synchronize) and 'info'.
     Returns (slab, (z0, z1)): this rank's output planes, resident on this rank.
     """
     import torch.distributed as dist
@@ -276,10 +460,130 @@ def zslab_affine(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline'
     if engine is None:
         import torch
         engine = CudaEngine(torch.cuda.current_device())
-    buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape)
-    z0, z1 = split_slabs(int(buffer.shape[0]), world, rank)
     m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(4, 4)
-    return engine.resample_slab(buffer, width, interpolation, m, z0, z1), (z0, z1)
+    stamp = getattr(engine, 'timer', None)
+    t0 = stamp() if (timings is not None and stamp) else None
+    info = {'path': 'broadcast'}
+    use_fp = bool(footprint) and shape is not None and world > 1 and hasattr(engine, 'prefilter_slab')
+    if use_fp:
+        shape = tuple(int(v) for v in shape)
+        buf_shape, width = engine.describe_shape(shape)
+        block = footprint_block_size(buf_shape, world)
+        # the plan is a pure function of (matrix, shape, world): a few ms of host arithmetic, memoised
+        key = (m.tobytes(), tuple(buf_shape), width, world, block)
+        plan = _FOOTPRINT_PLANS.get(key)
+        if plan is None:
+            if block is not None:
+                boxes = slab_footprint_blocks(m, buf_shape, width, world, block)
+                frac = footprint_fraction(boxes, buf_shape, world, block)
+            else:  # the blocks do not tile this shape: one bounding box per (owner, slab) pair
+                boxes = slab_footprint_boxes(m, shape, world)
+                frac = footprint_fraction(boxes, shape, world)
+            if len(_FOOTPRINT_PLANS) >= 16:
+                _FOOTPRINT_PLANS.clear()
+            plan = _FOOTPRINT_PLANS[key] = (boxes, frac)
+        boxes, frac = plan
+        info['largest_receive_share'] = frac
+        info['footprint_block'] = block
+        if footprint == 'auto' and frac + 1.0 / world >= 0.9:
+            use_fp = False
+    if use_fp:
+        info['path'] = 'footprint'
+        buffer, width = _scatter_prefilter_exchange(engine, dist, group, src, volume, interpolation, shape, boxes, block)
+    else:
+        buffer, width = _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shape)
+    t1 = stamp() if t0 is not None else None
+    z0, z1 = split_slabs(int(buffer.shape[0]), world, rank)
+    slab = engine.resample_slab(buffer, width, interpolation, m, z0, z1)
+    if t0 is not None:
+        t2 = stamp()
+        timings['distribute_ms'] = lambda: t0.elapsed_time(t1)
+        timings['resample_ms'] = lambda: t1.elapsed_time(t2)
+    if timings is not None:
+        timings['info'] = info
+    return slab, (z0, z1)
+
+
+def _scatter_prefilter_exchange(engine, dist, group, src, volume, interpolation, shape, boxes, block=None):
+    """Footprint path of `zslab_affine`; returns (full-size resident buffer of which only this rank's footprint is
+    filled, width)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    filtered = interpolation.startswith('filt')
+    d0, d1, d2 = shape
+    halo = PREFILTER_LOOKAHEAD if filtered else 0
+    buf_shape, width = engine.describe_shape(shape)
+    buffer = engine.empty(tuple(buf_shape))
+
+    def raw_range(r):
+        i0, i1 = split_slabs(d0, world, r)
+        return max(0, i0 - halo), min(d0, i1 + halo)
+
+    # 1) raw z-slabs (+ prefilter halo) leave the root: contiguous plane ranges, no packing
+    xy0, xy1 = raw_range(rank)
+    ops = []
+    if rank == src:
+        raw = engine.to_device(volume)
+        raw_slab = raw[xy0:xy1]
+        for r in range(world):
+            a, b = raw_range(r)
+            if r != src and b > a:
+                ops.append(dist.P2POp(dist.isend, raw[a:b], _global_rank(dist, group, r), group))
+    else:
+        raw_slab = engine.empty((xy1 - xy0, d1, d2))
+        if xy1 > xy0:
+            ops.append(dist.P2POp(dist.irecv, raw_slab, _global_rank(dist, group, src), group))
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    # 2) every rank prefilters its own slab straight into its place in the full-size buffer
+    i0, i1 = split_slabs(d0, world, rank)
+    if i1 > i0:
+        engine.prefilter_slab(raw_slab, buffer, shape, interpolation, xy0, xy1, i0, i1)
+    del raw_slab
+    # 3) pairwise exchange of what each output slab reads from each owner, all pairs in one group
+    ops, sends, recvs = [], [], []
+    if block is not None:
+        import torch
+        bz, by, bx = block
+        D0, D1, ROW = (int(v) for v in buffer.shape)
+        # (Zb, Yb, Xb, bz, by, bx) view of the buffer: indexing its first three axes gathers / scatters whole blocks
+        blocks = buffer.view(D0 // bz, bz, D1 // by, by, ROW // bx, bx).permute(0, 2, 4, 1, 3, 5)
+
+        def index(idx):
+            t = torch.from_numpy(idx).to(buffer.device, non_blocking=True)
+            return t[:, 0], t[:, 1], t[:, 2]
+    for q in range(world):
+        bxs = boxes.get((rank, q))
+        if q != rank and bxs is not None:
+            if block is not None:
+                t = blocks[index(bxs)]  # (n, bz, by, bx), contiguous
+            else:
+                lo, hi = bxs
+                t = buffer[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].contiguous()
+            sends.append(t)
+            ops.append(dist.P2POp(dist.isend, t, _global_rank(dist, group, q), group))
+    for r in range(world):
+        bxs = boxes.get((r, rank))
+        if r != rank and bxs is not None:
+            if block is not None:
+                t = engine.empty((len(bxs),) + tuple(block))
+            else:
+                t = engine.empty(tuple(h - l for l, h in zip(*bxs)))
+            recvs.append((t, bxs))
+            ops.append(dist.P2POp(dist.irecv, t, _global_rank(dist, group, r), group))
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    for t, bxs in recvs:
+        if block is not None:
+            blocks[index(bxs)] = t
+        else:
+            lo, hi = bxs
+            buffer[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].copy_(t)
+    del sends, recvs
+    return buffer, width
+
+
+def _global_rank(dist, group, r):
+    return r if group is None else dist.get_global_rank(group, r)
 
 
 def project_sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = 'filt_bspline', src: int = 0, group=None,
