@@ -227,13 +227,18 @@ int vt_slice_plan(const void *d_src, int s0, int s1, int s2, long long src_row_s
 
 /*
  * Host-buffer path: numpy in -> numpy out, as transforms.affine() with output=None
- * (voltools/transforms.py:180-223: H2D, [prefilter], kernel, D2H).  Blocking.  The context owns pinned
- * staging and device buffers that grow to the largest volume seen, and pipelines the copies with the
- * kernels in z-slabs.
+ * (voltools/transforms.py:180-223: H2D, [prefilter], kernel, D2H).  Blocking.  The context owns three streams and
+ * device buffers that grow to the largest volume seen (vt_host_ctx_trim releases them; the context stays usable), and
+ * pipelines the copies with the kernels in z-chunks.  It copies straight from / to the caller's arrays: the copies only
+ * overlap the kernels when h_src and h_dst are page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory);
+ * with pageable arrays the CUDA runtime stages every copy through its own bounce buffer and blocks the calling thread.
+ * The Python layer therefore stages pageable numpy inputs through a pinned buffer and returns pinned-backed results.
+ * On failure every copy that touches the caller's arrays has completed when the call returns.
  */
 typedef struct vt_host_ctx vt_host_ctx;
 int vt_host_ctx_create(int device, vt_host_ctx **ctx);
 int vt_host_ctx_destroy(vt_host_ctx *ctx);
+int vt_host_ctx_trim(vt_host_ctx *ctx);
 int vt_host_affine_f32(vt_host_ctx *ctx, const float *h_src, int s0, int s1, int s2, float *h_dst, int o0, int o1,
                        int o2, const float *h_m16, int interp, int prefilter, unsigned flags);
 

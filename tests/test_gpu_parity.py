@@ -68,8 +68,13 @@ def test_affine_vs_oracle(vt, shape, mode):
         assert got.shape == vol.shape and got.dtype == np.float32
         e = _err(got, want, r)
         assert e <= TOL[mode], f'{mode} {name} {shape}: {e:.3e}'
-        # the set of skipped (zero) voxels must be identical, not just close
-        assert np.array_equal(got == 0, want == 0), f'{mode} {name} {shape}: skipped voxel sets differ'
+        # the set of skipped voxels must be identical, not just close: read it off a sentinel the output is prefilled
+        # with (with signed coefficients a result can be exactly 0.0, and not in the same voxel for two implementations)
+        import torch
+        out = torch.full(shape, -7.0, device='cuda')
+        vt.affine(torch.from_numpy(vol).cuda(), m, interpolation=mode, output=out, device='gpu:0')
+        want_s = oracle.affine(vol, m, mode, output=np.full(shape, -7.0, np.float32))
+        assert np.array_equal(out.cpu().numpy() == -7.0, want_s == -7.0), f'{mode} {name} {shape}: skipped voxel sets differ'
 
 
 @pytest.mark.parametrize('mode', MODES)
@@ -242,8 +247,8 @@ def test_slice_family(vt, shape, interp):
 @pytest.mark.parametrize('shape', [(20, 24, 28), (33, 47, 44), (9, 70, 132), (64, 64, 64)])
 @pytest.mark.parametrize('interp', [0, 1, 2])
 def test_brick_family(vt, shape, interp):
-    """General matrices on 16-byte aligned rows run on the TMA-staged brick kernels: linear / cubic_tex bit-identical
-    to the gather kernels, cubic_simple equal up to float32 summation order; also against the oracle."""
+    """General matrices on 16-byte aligned rows run on the TMA-staged brick kernels: equal to the gather kernels up to
+    float32 summation order (<= 1e-6), identical skipped-voxel sets; also against the oracle."""
     import torch
     N = vt._native
     rng = np.random.default_rng(23)
@@ -269,11 +274,10 @@ def test_brick_family(vt, shape, interp):
             b = torch.full(shape, -7.0, device='cuda')
             N.affine(vol.data_ptr(), shape, a.data_ptr(), shape, m, interp, flag | N.KERNEL_BRICK)
             N.affine(vol.data_ptr(), shape, b.data_ptr(), shape, m, interp, flag | N.KERNEL_GATHER)
-            if interp == 2:
-                assert float((a - b).abs().max()) <= 1e-6, name
-                assert torch.equal(a == -7.0, b == -7.0), name
-            else:
-                assert torch.equal(a, b), (name, float((a - b).abs().max()))
+            # same weights as the gather kernels (the float-pipeline form of the texture rule is exact); the float32
+            # summation order differs (z-near / z-far halves in FFMA2 pairs; separable sums for cubic_simple)
+            assert float((a - b).abs().max()) <= 1e-6, (name, float((a - b).abs().max()))
+            assert torch.equal(a == -7.0, b == -7.0), name
         want = oracle.affine(vol_np, m, mode)
         got = np.where(a.cpu().numpy() == -7.0, 0, a.cpu().numpy())
         assert _err(got, want, 1.0) <= 1e-6, name
@@ -476,7 +480,8 @@ def test_reshape(vt, mode, mname):
     m2 = (vt.utils.translation_matrix(-1 * pb) @ m @ vt.utils.translation_matrix(pb)).astype(np.float32)
     want = oracle.affine(padded, m2, mode)
     assert _err(got, want, _range(padded, mode)) <= TOL[mode]
-    assert np.array_equal(got == 0, want == 0)
+    if not mode.startswith('filt'):  # (positive samples, non-negative weights: zero <=> skipped)
+        assert np.array_equal(got == 0, want == 0)
     got_dev = vt.affine(torch.from_numpy(vol).cuda(), m, interpolation=mode, reshape=True, device='gpu:0')
     assert got_dev.shape == got.shape and _err(got_dev, want, _range(padded, mode)) <= TOL[mode]
 
@@ -504,7 +509,6 @@ def test_convenience_wrappers(vt, mode):
         want = oracle.affine(vol, m, mode)
         got = getattr(vt, name)(vol, *args, interpolation=mode, device='gpu:0', **kw)
         assert got.dtype == np.float32 and _err(got, want, r) <= TOL[mode], (name, args)
-        assert np.array_equal(got == 0, want == 0), (name, args)
         got_sv = getattr(sv, name)(*args, **kw)
         assert _err(got_sv, want, r) <= TOL[mode], ('StaticVolume.' + name, args)
         out = torch.full(shape, 9.0, device='cuda')

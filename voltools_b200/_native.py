@@ -70,6 +70,7 @@ def lib():
                                     ctypes.c_uint, _i] + [ctypes.POINTER(_i)] * 7
         L.vt_host_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
         L.vt_host_ctx_destroy.argtypes = [_vp]
+        L.vt_host_ctx_trim.argtypes = [_vp]
         L.vt_host_affine_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f32p, _i, _i, ctypes.c_uint]
         L.vt_z4_bytes.restype = ctypes.c_size_t
         L.vt_z4_bytes.argtypes = [_i, _i, _i, _i]
@@ -183,14 +184,19 @@ def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, ba
 import os as _os
 
 
-def z4_wanted(interp, resident):
-    """Policy: does a slice-family launch of `interp` go to the slice4 kernels?  A resident volume always (the Z4
-    copy is packed once); a one-shot call when the pack pass (8 B/voxel) is paid back by the faster kernel: the cubic
-    modes (measured).  VT_Z4=0/1 forces it off/on (A/B measurements)."""
+def z4_wanted(interp, resident, axis=0, filtered=False):
+    """Policy: does a launch whose matrices leave `axis` alone go to the slice4 kernels?  A resident volume always
+    (the Z4 copy is packed once and kept).  A one-shot call pays a pack pass (8 B/voxel) unless the prefilter writes
+    the layout directly (filt_*, axis 0): measured at 512^3 the pass is paid back whenever
+    the alternative is the general-matrix kernels (axes 1 and 2: 2-6x), and for axis 0 only with the prefilter
+    (pack + slice4 221 / 236 Gvox/s against 250 / 280 for the plain-layout slice kernels, bspline / bspline_simple).
+    VT_Z4=0/1 forces it off/on (A/B measurements)."""
     force = _os.environ.get('VT_Z4')
     if force is not None:
         return force != '0'
-    return True if resident else interp != LINEAR
+    if resident or axis != 0:
+        return True
+    return bool(filtered)
 
 
 def z4_bytes(shape, axis):
@@ -352,6 +358,11 @@ class HostContext:
         check(lib().vt_host_affine_f32(self._h, src.ctypes.data, *src.shape, dst.ctypes.data, *dst.shape, mp, interp,
                                        int(prefilter), flags))
 
+    def trim(self):
+        """Release the context's device buffers (they grow to the largest volume seen); it stays usable."""
+        if self._h:
+            check(lib().vt_host_ctx_trim(self._h))
+
     def close(self):
         if self._h:
             lib().vt_host_ctx_destroy(self._h)
@@ -362,3 +373,21 @@ class HostContext:
             self.close()
         except Exception:
             pass
+
+
+def pinned_empty(shape):
+    """A float32 numpy array backed by page-locked memory from torch's caching host allocator (the block returns to the
+    cache when the array is garbage-collected): device copies into / out of it are asynchronous and run at link speed."""
+    import torch
+    return torch.empty(tuple(int(v) for v in shape), dtype=torch.float32, pin_memory=True).numpy()
+
+
+def as_pinned(a):
+    """`a` if it is already page-locked, else a pinned copy (ATen's multi-threaded host copy)."""
+    import torch
+    t = torch.from_numpy(a)
+    if t.is_pinned():
+        return a
+    p = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    p.copy_(t)
+    return p.numpy()

@@ -651,7 +651,7 @@ struct vt_host_ctx {
 // and leaving the download direction idle.  Measured at 250^3 filt_bspline, 8 volumes from 2 threads: 1.63 ms per
 // volume without the chain (1.82 ms from one thread; duplex floor 1.29 ms).
 constexpr int VT_MAX_DEVICES = 64;
-std::mutex g_upload_mu;
+std::mutex g_upload_mu[VT_MAX_DEVICES];     // one per device: calls on different GPUs do not serialise each other
 cudaEvent_t g_upload_done[VT_MAX_DEVICES];  // created on first use, never destroyed (process lifetime)
 
 int vt_host_ctx_create(int device, vt_host_ctx **out)
@@ -662,14 +662,48 @@ int vt_host_ctx_create(int device, vt_host_ctx **out)
     vt_host_ctx *c = new (std::nothrow) vt_host_ctx();
     if (!c) return VT_ERR_ALLOC;
     memset(c, 0, sizeof *c);
-    if (device < 0) VT_CUDA(cudaGetDevice(&device));
-    c->device = device;
-    VT_CUDA(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
-    VT_CUDA(cudaStreamCreateWithFlags(&c->st_k, cudaStreamNonBlocking));
-    VT_CUDA(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
-    VT_CUDA(cudaEventCreateWithFlags(&c->ev_k, cudaEventDisableTiming));
-    for (int i = 0; i < VT_HOST_MAX_CHUNKS; i++) VT_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    // anything that fails below releases what was created so far
+    auto build = [&]() -> int {
+        if (device < 0) VT_CUDA(cudaGetDevice(&device));
+        c->device = device;
+        VT_CUDA(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+        VT_CUDA(cudaStreamCreateWithFlags(&c->st_k, cudaStreamNonBlocking));
+        VT_CUDA(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
+        VT_CUDA(cudaEventCreateWithFlags(&c->ev_k, cudaEventDisableTiming));
+        for (int i = 0; i < VT_HOST_MAX_CHUNKS; i++) VT_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        return VT_OK;
+    };
+    const int rc = build();
+    if (rc) {
+        if (c->ev_k) cudaEventDestroy(c->ev_k);
+        for (int i = 0; i < VT_HOST_MAX_CHUNKS; i++)
+            if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->st_in) cudaStreamDestroy(c->st_in);
+        if (c->st_k) cudaStreamDestroy(c->st_k);
+        if (c->st_out) cudaStreamDestroy(c->st_out);
+        delete c;
+        return rc;
+    }
     *out = c;
+    return VT_OK;
+}
+
+// releases the device buffers of a context (they grow to the largest volume seen: d_src, d_coef, d_ws, d_dst --
+// 16 GiB after one 1024^3 filt_* call); the context stays usable and re-allocates on demand
+int vt_host_ctx_trim(vt_host_ctx *c)
+{
+    if (!c) return VT_OK;
+    DeviceGuard g(c->device);
+    if (g.status) return g.status;
+    cudaStreamSynchronize(c->st_in);
+    cudaStreamSynchronize(c->st_k);
+    cudaStreamSynchronize(c->st_out);
+    cudaFree(c->d_src);
+    cudaFree(c->d_dst);
+    cudaFree(c->d_coef);
+    cudaFree(c->d_ws);
+    c->d_src = c->d_dst = c->d_coef = c->d_ws = nullptr;
+    c->cap_src = c->cap_dst = c->cap_coef = c->cap_ws = 0;
     return VT_OK;
 }
 
@@ -723,6 +757,9 @@ static int ensure(float **p, size_t *cap, size_t bytes)
 // matrix of the slice family (output plane z reads input planes z + t0 - 1 .. z + t0 + 1); for a general matrix
 // every output plane can read any input plane, so the resampling waits for the whole volume and only the download
 // is overlapped (in z-slabs).
+static int host_affine_impl(vt_host_ctx *c, const float *h_src, int s0, int s1, int s2, float *h_dst, int o0, int o1, int o2,
+                            const float *h_m16, int interp, int prefilter, unsigned flags, cudaEvent_t *dbg);
+
 int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s2, float *h_dst, int o0, int o1, int o2,
                        const float *h_m16, int interp, int prefilter, unsigned flags)
 {
@@ -731,6 +768,28 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
     if (interp != VT_LINEAR && interp != VT_CUBIC_TEX && interp != VT_CUBIC_SIMPLE) return VT_ERR_INVALID_ARG;
     DeviceGuard g(c->device);
     if (g.status) return g.status;
+    static const bool debug = getenv("VT_HOST_DEBUG") != nullptr;  // prints the timeline of the three streams
+    cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (debug)
+        for (auto &e : dbg) cudaEventCreate(&e);
+    const int rc = host_affine_impl(c, h_src, s0, s1, s2, h_dst, o0, o1, o2, h_m16, interp, prefilter, flags,
+                                    debug ? dbg : nullptr);
+    if (rc) {
+        // ONE exit for every failure inside the pipeline: copies on the caller's arrays may still be in flight, and the
+        // caller is free to release h_src / h_dst as soon as this returns
+        cudaStreamSynchronize(c->st_in);
+        cudaStreamSynchronize(c->st_k);
+        cudaStreamSynchronize(c->st_out);
+    }
+    for (auto &e : dbg)
+        if (e) cudaEventDestroy(e);
+    return rc;
+}
+
+static int host_affine_impl(vt_host_ctx *c, const float *h_src, int s0, int s1, int s2, float *h_dst, int o0, int o1, int o2,
+                            const float *h_m16, int interp, int prefilter, unsigned flags, cudaEvent_t *dbg)
+{
+    const bool debug = dbg != nullptr;
     const size_t plane_in = (size_t)s1 * s2, plane_out = (size_t)o1 * o2;
     // device copies keep their rows padded to 16 bytes so that the resampling kernels can stage with TMA whatever
     // the width is; the upload itself does the padding (2-D copy), the prefilter writes padded rows directly
@@ -781,15 +840,10 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
         if (tail_total)
             for (int i = 0; i < 3; i++) { bounds[nch + 1] = bounds[nch] + tail[i]; nch++; }
     }
-    static const bool debug = getenv("VT_HOST_DEBUG") != nullptr;  // prints the timeline of the three streams
-    cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (debug) {
-        for (auto &e : dbg) cudaEventCreate(&e);
-        cudaEventRecord(dbg[0], c->st_in);
-    }
+    if (debug) cudaEventRecord(dbg[0], c->st_in);
     // 1) the whole upload, chunk by chunk, on the copy stream, after the previous call's upload on this device
     static const bool chain = getenv("VT_HOST_NO_CHAIN") == nullptr;  // A/B knob
-    std::unique_lock<std::mutex> upload_turn(g_upload_mu, std::defer_lock);
+    std::unique_lock<std::mutex> upload_turn(g_upload_mu[(unsigned)c->device % VT_MAX_DEVICES], std::defer_lock);
     cudaEvent_t *turn = (chain && c->device < VT_MAX_DEVICES) ? &g_upload_done[c->device] : nullptr;
     if (turn) {
         upload_turn.lock();
@@ -870,7 +924,6 @@ int vt_host_affine_f32(vt_host_ctx *c, const float *h_src, int s0, int s1, int s
         cudaEventElapsedTime(&t3, dbg[0], dbg[3]);
         fprintf(stderr, "vt_host_affine_f32: %d chunks; since the first upload started: uploads done %.3f ms, kernels done "
                         "%.3f ms, downloads done %.3f ms\n", nch, t1, t2, t3);
-        for (auto &e : dbg) cudaEventDestroy(e);
     }
     return VT_OK;
 }

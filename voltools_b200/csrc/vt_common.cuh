@@ -256,6 +256,78 @@ __device__ __forceinline__ vt_f2 vt_fma2(vt_f2 a, vt_f2 b, vt_f2 c)
     return r;
 }
 
+__device__ __forceinline__ vt_f2 vt_fma2_rm(vt_f2 a, vt_f2 b, vt_f2 c)
+{
+    vt_f2 r;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ vt_f2 vt_add2(vt_f2 a, vt_f2 b)
+{
+    vt_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ vt_f2 vt_add2_rm(vt_f2 a, vt_f2 b)
+{
+    vt_f2 r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ vt_f2 vt_mul2(vt_f2 a, vt_f2 b)
+{
+    vt_f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ vt_f2 vt_bc(float x) { return vt_pk(x, x); }
+__device__ __forceinline__ float vt_lo(vt_f2 v) { float a, b; vt_unpk(v, a, b); return a; }
+__device__ __forceinline__ float vt_hi(vt_f2 v) { float a, b; vt_unpk(v, a, b); return b; }
+
+// ---------------------------------------------------------------------------------------------------
+// The texture-unit model again, entirely on the float pipes and two values per instruction.  Every quantity of the
+// rule is a small integer (< 2^17), so float32 holds it exactly; the only inexact steps of the integer code are its
+// floors, reproduced with round-toward-minus-infinity adds against VT_MAGIC = 1.5 * 2^23 (for |n| < 2^22 the sum
+// MAGIC + n is exact at unit spacing, so RM(x + MAGIC) - MAGIC == floor(x)).  Same weights as vt_tex_fix_hw /
+// vt_tex_hw_side bit for bit -- no F2I, no integer multiplies, no int->float conversions: the general-matrix kernels
+// were bound by exactly those (154 / 573 instructions per voxel).
+// ---------------------------------------------------------------------------------------------------
+#define VT_MAGIC 12582912.0f
+#define VT_MAGIC_BITS 0x4B400000
+// two coordinates at once: alpha (float, 0..255) and base texel (int) of each
+__device__ __forceinline__ void vt_tex_fix2(vt_f2 x, vt_f2 &alpha, int &base_lo, int &base_hi)
+{
+    const vt_f2 u = vt_fma2(x, vt_bc(256.0f), vt_bc(0.5f));          // the same fma as vt_tex_fix_hw
+    const vt_f2 t = vt_add2_rm(u, vt_bc(VT_MAGIC));                   // MAGIC + floor(u)
+    const vt_f2 X = vt_add2(t, vt_bc(-(VT_MAGIC + 128.0f)));          // floor(u) - 128, exact
+    const vt_f2 bm = vt_fma2_rm(X, vt_bc(1.0f / 256.0f), vt_bc(VT_MAGIC));  // MAGIC + floor(X / 256)
+    const vt_f2 base = vt_add2(bm, vt_bc(-VT_MAGIC));
+    alpha = vt_fma2(base, vt_bc(-256.0f), X);                         // X - 256 * base, exact
+    base_lo = __float_as_int(vt_lo(bm)) - VT_MAGIC_BITS;
+    base_hi = __float_as_int(vt_hi(bm)) - VT_MAGIC_BITS;
+}
+// floor((v + 128) / 256) for integer-valued v, both halves
+__device__ __forceinline__ vt_f2 vt_round8_2(vt_f2 v_plus_128)
+{
+    return vt_add2(vt_fma2_rm(v_plus_128, vt_bc(1.0f / 256.0f), vt_bc(VT_MAGIC)), vt_bc(-VT_MAGIC));
+}
+// the eight texel weights (1/256ths) of one fetch, as four {z-near, z-far} pairs; a, b, c = alphas along x, y, z
+struct VtTexW {
+    vt_f2 nn, fn, nf, ff;  // (x near, y near), (x far, y near), (x near, y far), (x far, y far)
+};
+__device__ __forceinline__ VtTexW vt_tex_weights2(float a, float b, float c)
+{
+    const vt_f2 S = vt_fma2(vt_bc(c), vt_pk(-1.0f, 1.0f), vt_pk(256.0f, 0.0f));  // {256 - c, c}
+    const vt_f2 XF = vt_round8_2(vt_fma2(vt_bc(a), S, vt_bc(128.0f)));
+    const vt_f2 XN = vt_fma2(XF, vt_bc(-1.0f), S);  // S - XF, exact
+    VtTexW w;
+    w.ff = vt_round8_2(vt_fma2(vt_bc(b), XF, vt_bc(128.0f)));
+    w.nn = vt_round8_2(vt_fma2(vt_bc(256.0f - b), XN, vt_bc(128.0f)));
+    w.fn = vt_fma2(w.ff, vt_bc(-1.0f), XF);  // XF - ff, exact
+    w.nf = vt_fma2(w.nn, vt_bc(-1.0f), XN);  // XN - nn, exact
+    return w;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // cubic B-spline pieces
 // ---------------------------------------------------------------------------------------------------

@@ -31,22 +31,26 @@ constexpr int MAX_BRICK_BYTES = 72 * 1024;    // 3 CTAs per SM
 struct VtBrickStaging {
     CUtensorMap tmap;
     int bw, bh, bd;  // box = brick dimensions (bw multiple of 4; also the row pitch)
-    int layout;      // how a warp's 32 lanes tile (a1, a2): 0 = 2 x 16, 1 = 4 x 8 (chosen against bank conflicts)
+    int layout;      // which sub-box of the CTA's 16 x 8 x 2 thread block a warp covers (thread_pos; chosen against bank conflicts)
 };
 
-// thread -> position inside the 8 x 8 x 16 tile (tz selects a group of VPT consecutive planes)
+// thread -> position inside the 8 x 8 x 16 tile (tz selects a group of VPT consecutive planes).  The CTA's threads
+// form a 16 (x) x 8 (y) x 2 (z groups) block; `layout` is the sub-box of it a warp covers: which one spreads a warp's
+// 32 brick addresses over the most banks depends on the matrix (tune_brick).
+constexpr int N_BRICK_LAYOUTS = 6;
 __host__ __device__ __forceinline__ void thread_pos(int tid, int layout, int &tx, int &ty, int &tz)
 {
-    if (layout == 0) {
-        tx = tid & 15;
-        ty = (tid >> 4) & 7;
-        tz = tid >> 7;
-    } else {
-        const int lane = tid & 31, warp = tid >> 5;
-        tx = (warp & 1) * 8 + (lane & 7);
-        ty = ((warp >> 1) & 1) * 4 + (lane >> 3);
-        tz = warp >> 2;
-    }
+    // log2 of the warp's extent along x and y (the rest of its 32 lanes goes along z)
+    const int lwx = layout == 0 ? 4 : (layout == 1 ? 3 : (layout == 2 ? 2 : (layout == 3 ? 3 : (layout == 4 ? 2 : 4))));
+    const int lwy = layout == 0 ? 1 : (layout == 1 ? 2 : (layout == 2 ? 3 : (layout == 3 ? 1 : (layout == 4 ? 2 : 0))));
+    const int lwz = 5 - lwx - lwy;  // 0 or 1
+    const int lane = tid & 31, warp = tid >> 5;
+    const int lx = lane & ((1 << lwx) - 1), ly = (lane >> lwx) & ((1 << lwy) - 1), lz = lane >> (lwx + lwy);
+    const int nwx = 4 - lwx, nwy = 3 - lwy;  // log2 of the number of warps along x and y
+    const int wx = warp & ((1 << nwx) - 1), wy = (warp >> nwx) & ((1 << nwy) - 1), wz = warp >> (nwx + nwy);
+    tx = (wx << lwx) + lx;
+    ty = (wy << lwy) + ly;
+    tz = (wz << lwz) + lz;
 }
 
 struct Brick {
@@ -59,29 +63,82 @@ struct Brick {
     }
 };
 
+// one trilinear fetch with the float-pipeline weights (vt_tex_weights2): q = the (x near, y near, z near) texel.  The
+// four FFMA2 carry the z-near and z-far partial sums side by side; they are added once at the end, so the float32
+// summation order differs from the gather family's single chain (<= 1 ulp of the result; the unit itself rounds once).
+__device__ __forceinline__ float tex_fetch_f(const float *q, int py, int pz, const VtTexW &w)
+{
+    const float *qz = q + pz;
+    vt_f2 r = vt_mul2(w.nn, vt_pk(q[0], qz[0]));
+    r = vt_fma2(w.fn, vt_pk(q[1], qz[1]), r);
+    r = vt_fma2(w.nf, vt_pk(q[py], qz[py]), r);
+    r = vt_fma2(w.ff, vt_pk(q[py + 1], qz[py + 1]), r);
+    return __fmul_rn(__fadd_rn(vt_lo(r), vt_hi(r)), 1.0f / 256.0f);
+}
+
+// cubicTex3D (helper_interpolation.h:8-40) with the float-pipeline weights: the two fetch positions of an axis go
+// through vt_tex_fix2 as a pair, and the x-side products of the weight rule, which depend on (x alpha, z side) only,
+// are shared by the four fetches that use them: ~330 instructions per voxel instead of ~730.
+__device__ __forceinline__ float cubic_tex_brick_f(const float *s, int py, int pz, int xlo, int ylo, int zlo, float x, float y,
+                                                   float z)
+{
+    float g0x, g1x, h0x, h1x, g0y, g1y, h0y, h1y, g0z, g1z, h0z, h1z;
+    vt_ruijters(x, g0x, g1x, h0x, h1x);
+    vt_ruijters(y, g0y, g1y, h0y, h1y);
+    vt_ruijters(z, g0z, g1z, h0z, h1z);
+    vt_f2 ax, ay, az;
+    int bx[2], by[2], bz[2];
+    vt_tex_fix2(vt_pk(h0x, h1x), ax, bx[0], bx[1]);
+    vt_tex_fix2(vt_pk(h0y, h1y), ay, by[0], by[1]);
+    vt_tex_fix2(vt_pk(h0z, h1z), az, bz[0], bz[1]);
+    const float a[2] = {vt_lo(ax), vt_hi(ax)}, b[2] = {vt_lo(ay), vt_hi(ay)}, c[2] = {vt_lo(az), vt_hi(az)};
+    vt_f2 XF[2][2], XN[2][2];  // [x fetch i][z fetch k], halves = z near / far side
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const vt_f2 S = vt_fma2(vt_bc(c[k]), vt_pk(-1.0f, 1.0f), vt_pk(256.0f, 0.0f));  // {256 - c, c}
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            XF[i][k] = vt_round8_2(vt_fma2(vt_bc(a[i]), S, vt_bc(128.0f)));
+            XN[i][k] = vt_fma2(XF[i][k], vt_bc(-1.0f), S);
+        }
+    }
+    const int ox[2] = {bx[0] - xlo, bx[1] - xlo};
+    float tz[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        float tyv[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const float *row = s + (bz[k] - zlo) * pz + (by[j] - ylo) * py;
+            const vt_f2 bj = vt_bc(b[j]), nbj = vt_bc(256.0f - b[j]);
+            float tx[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                VtTexW w;
+                w.ff = vt_round8_2(vt_fma2(bj, XF[i][k], vt_bc(128.0f)));
+                w.nn = vt_round8_2(vt_fma2(nbj, XN[i][k], vt_bc(128.0f)));
+                w.fn = vt_fma2(w.ff, vt_bc(-1.0f), XF[i][k]);
+                w.nf = vt_fma2(w.nn, vt_bc(-1.0f), XN[i][k]);
+                tx[i] = tex_fetch_f(row + ox[i], py, pz, w);
+            }
+            tyv[j] = __fmaf_rn(g0x, tx[0], __fmul_rn(g1x, tx[1]));
+        }
+        tz[k] = __fmaf_rn(g0y, tyv[0], __fmul_rn(g1y, tyv[1]));
+    }
+    return __fmaf_rn(g0z, tz[0], __fmul_rn(g1z, tz[1]));
+}
+
 // tex3D<float> on the brick (x along axis 2, y along axis 1, z along axis 0); see vt_common.cuh for the weight rule
 template <int RULE>
 __device__ __forceinline__ float tex3d_brick(const Brick &b, float x, float y, float z)
 {
     int i2, i1, i0;
     if (RULE == 0) {
-        int a, bb, c;
-        vt_tex_fix_hw(x, i2, a);
-        vt_tex_fix_hw(y, i1, bb);
-        vt_tex_fix_hw(z, i0, c);
-        const float *q = b.at(i0, i1, i2);
-        int wn[4], wf[4];
-        vt_tex_hw_side(a, bb, 256 - c, wn);
-        vt_tex_hw_side(a, bb, c, wf);
-        float r = __fmul_rn(vt_u2f(wn[0]), q[0]);
-        r = __fmaf_rn(vt_u2f(wn[1]), q[1], r);
-        r = __fmaf_rn(vt_u2f(wn[2]), q[b.py], r);
-        r = __fmaf_rn(vt_u2f(wn[3]), q[b.py + 1], r);
-        r = __fmaf_rn(vt_u2f(wf[0]), q[b.pz], r);
-        r = __fmaf_rn(vt_u2f(wf[1]), q[b.pz + 1], r);
-        r = __fmaf_rn(vt_u2f(wf[2]), q[b.pz + b.py], r);
-        r = __fmaf_rn(vt_u2f(wf[3]), q[b.pz + b.py + 1], r);
-        return __fmul_rn(r, 1.0f / 256.0f);
+        vt_f2 axy, az;
+        int unused;
+        vt_tex_fix2(vt_pk(x, y), axy, i2, i1);
+        vt_tex_fix2(vt_pk(z, z), az, i0, unused);
+        return tex_fetch_f(b.at(i0, i1, i2), b.py, b.pz, vt_tex_weights2(vt_lo(axy), vt_hi(axy), vt_lo(az)));
     } else {
         float ax, ay, az;
         vt_tex_fix<2>(x, i2, ax);
@@ -166,17 +223,21 @@ __global__ void __launch_bounds__(NT, 3)
     // brick origin: per input axis the extremes are at tile corners (the float recipe is monotone in each index)
     constexpr int LO = INTERP == VT_LINEAR ? 0 : -1;
     int lo[3];
+    bool interior = true;  // every voxel of the tile samples inside the source: no per-voxel bounds tests
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        float mn = 3.0e38f;
+        float mn = 3.0e38f, mx = -3.0e38f;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             const float fa0 = (float)((c & 4) ? a0_1 : a0_0), fa1 = (float)((c & 2) ? a1_1 : a1_0);
             const float fa2 = (float)((c & 1) ? a2_1 : a2_0);
-            mn = fminf(mn, vt_row_finish(M.r[r], vt_row_base(M.r[r], fa0, fa1), fa2));
+            const float p = vt_row_finish(M.r[r], vt_row_base(M.r[r], fa0, fa1), fa2);
+            mn = fminf(mn, p);
+            mx = fmaxf(mx, p);
         }
         // sample points further out than 2 texels are out of bounds anyway: keep the conversion safe
         const float dim = (float)(r == 0 ? P.s0 : (r == 1 ? P.s1 : P.s2));
+        interior = interior && mn >= 0.0f && mx < dim;  // transforms.py:276-278 holds for the extremes, hence for all
         mn = fminf(fmaxf(mn, -2.0f), dim + 2.0f);
         lo[r] = (int)floorf(mn - 0.5f) + LO;
     }
@@ -204,25 +265,58 @@ __global__ void __launch_bounds__(NT, 3)
     constexpr bool project = MODE == 2;  // sum along axis 0 instead of storing
     constexpr bool OOB_ZERO = MODE == 1;
     float acc = 0.0f;
+    const int av0 = a0_0 + tz * VPT;
+    if (INTERP == VT_LINEAR && RULE == 0 && interior && av0 + VPT - 1 <= a0_1) {
+        // Fast path of the trilinear kernel: whole tile in bounds, all VPT voxels present.  Two voxels per instruction
+        // through the coordinate recipe and vt_tex_fix2; weights on the float pipes (vt_tex_weights2).
+        const float b0 = __fmul_rn(fa1, M.r[0][1]), b1 = __fmul_rn(fa1, M.r[1][1]), b2 = __fmul_rn(fa1, M.r[2][1]);
 #pragma unroll
-    for (int v = 0; v < VPT; v++) {
-        const int a0 = a0_0 + tz * VPT + v;
-        if (a0 > a0_1) break;
-        const float fa0 = (float)a0;
-        const float p0 = vt_row_finish(M.r[0], vt_row_base(M.r[0], fa0, fa1), fa2);
-        const float p1 = vt_row_finish(M.r[1], vt_row_base(M.r[1], fa0, fa1), fa2);
-        const float p2 = vt_row_finish(M.r[2], vt_row_base(M.r[2], fa0, fa1), fa2);
-        // transforms.py:276-278
-        if (p2 < 0 || p1 < 0 || p0 < 0 || p2 >= f2 || p1 >= f1 || p0 >= f0) {
-            if (OOB_ZERO && !project) dst[(size_t)a0 * oplane] = 0.0f;
-            continue;
+        for (int v = 0; v < VPT; v += 2) {
+            const vt_f2 a0p = vt_pk((float)(av0 + v), (float)(av0 + v + 1));
+            vt_f2 al[3];
+            int bl[3], bh[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const float br = r == 0 ? b0 : (r == 1 ? b1 : b2);
+                // vt_row_base / vt_row_finish, both voxels at once
+                vt_f2 t = vt_fma2(a0p, vt_bc(M.r[r][0]), vt_bc(br));
+                t = vt_fma2(vt_bc(fa2), vt_bc(M.r[r][2]), t);
+                t = vt_add2(vt_add2(vt_bc(M.r[r][3]), t), vt_bc(0.5f));
+                vt_tex_fix2(t, al[r], bl[r], bh[r]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float a = h ? vt_hi(al[2]) : vt_lo(al[2]), bb = h ? vt_hi(al[1]) : vt_lo(al[1]);
+                const float c = h ? vt_hi(al[0]) : vt_lo(al[0]);
+                const VtTexW w = vt_tex_weights2(a, bb, c);
+                const float r = tex_fetch_f(b.at(h ? bh[0] : bl[0], h ? bh[1] : bl[1], h ? bh[2] : bl[2]), b.py, b.pz, w);
+                if (project) acc += r;
+                else dst[(size_t)(av0 + v + h) * oplane] = r;
+            }
         }
-        float r;
-        if (INTERP == VT_LINEAR) r = tex3d_brick<RULE>(b, p2, p1, p0);
-        else if (INTERP == VT_CUBIC_TEX) r = cubic_tex_brick<RULE>(b, p2, p1, p0);
-        else r = cubic_simple_brick(b, p2, p1, p0);
-        if (project) acc += r;
-        else dst[(size_t)a0 * oplane] = r;
+    } else {
+#pragma unroll
+        for (int v = 0; v < VPT; v++) {
+            const int a0 = av0 + v;
+            if (a0 > a0_1) break;
+            const float fa0 = (float)a0;
+            const float p0 = vt_row_finish(M.r[0], vt_row_base(M.r[0], fa0, fa1), fa2);
+            const float p1 = vt_row_finish(M.r[1], vt_row_base(M.r[1], fa0, fa1), fa2);
+            const float p2 = vt_row_finish(M.r[2], vt_row_base(M.r[2], fa0, fa1), fa2);
+            // transforms.py:276-278
+            if (!interior && (p2 < 0 || p1 < 0 || p0 < 0 || p2 >= f2 || p1 >= f1 || p0 >= f0)) {
+                if (OOB_ZERO && !project) dst[(size_t)a0 * oplane] = 0.0f;
+                continue;
+            }
+            float r;
+            if (INTERP == VT_LINEAR) r = tex3d_brick<RULE>(b, p2, p1, p0);
+            else if (INTERP == VT_CUBIC_TEX) {
+                if (RULE == 0) r = cubic_tex_brick_f(b.s, b.py, b.pz, b.xlo, b.ylo, b.zlo, p2, p1, p0);
+                else r = cubic_tex_brick<RULE>(b, p2, p1, p0);
+            } else r = cubic_simple_brick(b, p2, p1, p0);
+            if (project) acc += r;
+            else dst[(size_t)a0 * oplane] = r;
+        }
     }
     if (project && acc != 0.0f) atomicAdd(dst, acc);
 }
@@ -292,8 +386,8 @@ void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
     slot.m = M;
     memcpy(slot.key, key, sizeof key);
     slot.valid = false;
-    static thread_local int iz[2][NS][NT], iy[2][NS][NT], ix[2][NS][NT];
-    for (int layout = 0; layout < 2; layout++)
+    static thread_local int iz[N_BRICK_LAYOUTS][NS][NT], iy[N_BRICK_LAYOUTS][NS][NT], ix[N_BRICK_LAYOUTS][NS][NT];
+    for (int layout = 0; layout < N_BRICK_LAYOUTS; layout++)
         for (int smp = 0; smp < NS; smp++) {
             const int a0_0 = P.z_begin + ((P.z_end - P.z_begin) / 3 * (smp + 1)) / TZ * TZ;
             const int a1_0 = (P.o1 / 3 * (smp + 1)) / TY * TY, a2_0 = (P.o2 / 3 * (2 - smp)) / TX * TX;
@@ -311,7 +405,7 @@ void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
     for (int bw = bw0; bw <= bw0 + 8; bw += 4)
         for (int bh = bh0; bh <= bh0 + 7; bh++) {
             if ((size_t)bw * bh * G.bd * 4 > (size_t)MAX_BRICK_BYTES) continue;
-            for (int layout = 0; layout < 2; layout++) {
+            for (int layout = 0; layout < N_BRICK_LAYOUTS; layout++) {
                 long cost = 0;
                 for (int smp = 0; smp < NS; smp++)
                     for (int w = 0; w < NT / 32; w++) {
@@ -328,8 +422,9 @@ void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
                         }
                         cost += worst;
                     }
-                // prefer smaller bricks on ties (less shared memory, less L2 traffic)
-                cost = cost * 4096 + (long)bw * bh / 8;
+                // prefer smaller bricks on ties (less shared memory, less L2 traffic); a warp whose lanes cover only 4
+                // consecutive x writes 16-byte pieces of a row: a small handicap
+                cost = cost * 4096 + (long)bw * bh / 8 + ((layout == 2 || layout == 4) ? cost * 4096 / 16 : 0);
                 if (best < 0 || cost < best) {
                     best = cost;
                     G.bw = bw;
@@ -350,7 +445,7 @@ int launch2(const VtResampleParams &P, cudaStream_t st)
     VtBrickStaging G;
     memset(&G, 0, sizeof G);
     if (!brick_dims(P, INTERP, G.bw, G.bh, G.bd)) return VT_ERR_UNSUPPORTED;
-    if (INTERP != VT_LINEAR) tune_brick(P, G);
+    tune_brick(P, G);  // (linear too: a rotation that sends a warp's x run down the brick's z axis is 8-way conflicted untuned)
     const unsigned long long gdim[3] = {(unsigned long long)P.s2, (unsigned long long)P.s1, (unsigned long long)P.s0};
     const unsigned long long gstr[2] = {(unsigned long long)P.src_row * 4, (unsigned long long)P.src_plane * 4};
     const unsigned box[3] = {(unsigned)G.bw, (unsigned)G.bh, (unsigned)G.bd};

@@ -46,9 +46,10 @@ constexpr int TS = 16;        // tile edge
 constexpr int NT = TS * TS;   // threads per CTA, one column each
 constexpr int BH_MAX = 32;    // max footprint rows (texels)
 constexpr int BW_MAX = 40;    // max box width (texels): footprint <= 33 + 7 pitch classes
-constexpr int STAGE_BYTES = BH_MAX * BW_MAX * 16;  // one ring stage: a footprint of four planes (20 KB)
-constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES_MAX = BH_MAX * BW_MAX * 16;  // one ring stage: a footprint of four planes (<= 20 KB)
+constexpr int SMEM_HEADER = 128;  // "full" mbarriers at 0, "empty" mbarriers at 32, refill counters at 64
 constexpr int NPITCH = 8;     // tensor maps per launch: box widths bw0 .. bw0+7 (pitch mod 8 is what matters)
+constexpr bool Z4_DEFAULT_LOOSE = false;  // ring without a block-wide barrier: measured SLOWER
 constexpr int N_SHAPES = 4;   // quarter-warp shapes 1x8, 2x4, 4x2, 8x1 (rows x columns of the tile)
 
 struct Z4Mat {
@@ -71,6 +72,7 @@ struct Z4Params {
     int bw0, bh;                       // box width of map 0 (map k: bw0 + k) and box height, texels
     int tiles_fast;
     int march;                         // the march axis (0..2): selects the slots of the texture-weight rule
+    int vec_store;                     // march axis contiguous in the output and 16-byte alignable: STG.128 quads
     Z4Mat mats[VT_MAX_BATCH];
 };
 
@@ -142,14 +144,13 @@ struct Taps4<VT_LINEAR> {
         r0 = 16u * (unsigned)((by - ylo) * pitch + (bx - xlo));
         r1 = r0 + 16u * (unsigned)pitch;
     }
-    template <unsigned SOFF>
     __device__ __forceinline__ void planes(unsigned ring, float (&out)[4]) const
     {
         vt_f2 a01 = 0ull, a23 = 0ull;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             vt_f2 lo, hi;
-            lds128(ring + (k < 2 ? r0 : r1) + (SOFF + 16u * (k & 1)), lo, hi);
+            lds128(ring + (k < 2 ? r0 : r1) + 16u * (k & 1), lo, hi);
             const vt_f2 ww = vt_pk(w[k], w[k]);
             a01 = vt_fma2(lo, ww, a01);
             a23 = vt_fma2(hi, ww, a23);
@@ -188,7 +189,6 @@ struct Taps4<VT_CUBIC_SIMPLE> {
         wz2 = vt_bspline(1.0f);
     }
     // in-plane sums of the group's four planes, two FFMA2 per tap
-    template <unsigned SOFF>
     __device__ __forceinline__ void planes(unsigned ring, float (&out)[4]) const
     {
         vt_f2 a01 = 0ull, a23 = 0ull;
@@ -197,7 +197,7 @@ struct Taps4<VT_CUBIC_SIMPLE> {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 vt_f2 lo, hi;
-                lds128(ring + row[j] + (SOFF + 16u * i), lo, hi);
+                lds128(ring + row[j] + 16u * i, lo, hi);
                 const vt_f2 ww = vt_pk(w[j * 4 + i], w[j * 4 + i]);
                 a01 = vt_fma2(lo, ww, a01);
                 a23 = vt_fma2(hi, ww, a23);
@@ -291,7 +291,6 @@ struct Taps4<VT_CUBIC_TEX> {
     }
     // A-, B- and C-weighted in-plane sums of the group's four planes: per tap {wa, wb} x {t, t} for each plane (the
     // scalar texel is FFMA2's broadcast operand) and {t0, t1} x {wc, wc}, {t2, t3} x {wc, wc}: 6 FFMA2 per LDS.128
-    template <unsigned SOFF>
     __device__ __forceinline__ void planes3(unsigned ring, float (&qa)[4], float (&qb)[4], float (&qc)[4]) const
     {
         vt_f2 ab[4] = {0ull, 0ull, 0ull, 0ull}, c01 = 0ull, c23 = 0ull;
@@ -300,7 +299,7 @@ struct Taps4<VT_CUBIC_TEX> {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 vt_f2 lo, hi;
-                lds128(ring + adr[j * 2 + (i >> 1)] + (SOFF + 16u * (i & 1)), lo, hi);
+                lds128(ring + adr[j * 2 + (i >> 1)] + 16u * (i & 1), lo, hi);
                 const vt_f2 wab = vt_pk(wa[j * 4 + i], wb[j * 4 + i]);
                 const vt_f2 wcc = vt_pk(wc[j * 4 + i], wc[j * 4 + i]);
                 float t0, t1, t2, t3;
@@ -322,13 +321,27 @@ struct Taps4<VT_CUBIC_TEX> {
 
 __host__ __device__ __forceinline__ int floordiv4(int v) { return v >> 2; }  // arithmetic shift: floor for negatives
 
-template <int INTERP, int RULE, bool OOB_ZERO>
-__global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
-    vt_z4_kernel(const __grid_constant__ Z4Params P, const __grid_constant__ Z4Maps G, int m_chunk)
+__device__ __forceinline__ unsigned atom_inc_shared(unsigned addr)
 {
-    // [128 B: "full" mbarriers of the ring stages][NSTAGE stages of STAGE_BYTES]
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+    return old;
+}
+
+// LOOSE = false: one block-wide barrier per step (everyone is done with the previous stage -> thread 0 refills it).
+// LOOSE = true:  no block-wide barrier in the march.  Every warp waits for its stage on the "full" mbarrier, arrives on
+//                the stage's "empty" mbarrier when it has read it and bumps a counter; the warp whose bump is the
+//                eighth -- the LAST one to finish the stage -- refills it.  Nobody ever blocks on "empty" (the refiller's
+//                wait on it returns at once: it only orders the refill after the other warps' reads), so warps drift up
+//                to NSTAGE - 1 stages apart instead of meeting every step.
+template <int INTERP, int RULE, bool OOB_ZERO, int NSTAGE, bool LOOSE>
+__global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
+    vt_z4_kernel(const __grid_constant__ Z4Params P, const __grid_constant__ Z4Maps G, int m_chunk, unsigned stage_bytes)
+{
+    // [SMEM_HEADER: mbarriers, counters][NSTAGE stages of stage_bytes]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using T = Taps4<INTERP>;
+    static_assert(NSTAGE == 3 || NSTAGE == 4, "the ring loop is unrolled for 3 or 4 stages");
     const int tid = threadIdx.x;
     const int tile_y = blockIdx.x / P.tiles_fast, tile_x = blockIdx.x - tile_y * P.tiles_fast;
     const int mat = blockIdx.z;
@@ -362,11 +375,15 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
     const int ylo = (int)floorf(y_min - 0.5f) + T::LO, xlo = (int)floorf(x_min - 0.5f) + T::LO;
 
     const unsigned bars_s = vt_smem_u32(smem_raw);
-    const unsigned ring_s = bars_s + 128u;
+    const unsigned ring_s = bars_s + (unsigned)SMEM_HEADER;
     if (tid == 0) {
         vt_tma_prefetch_desc(&G.map[pidx]);
 #pragma unroll
-        for (int i = 0; i < NSTAGE; i++) vt_mbar_init(bars_s + 8u * i, 1);
+        for (int i = 0; i < NSTAGE; i++) {
+            vt_mbar_init(bars_s + 8u * i, 1);
+            vt_mbar_init(bars_s + 32u + 8u * i, NT / 32);  // one arrival per warp
+            ((unsigned *)(smem_raw + 64))[i] = 0u;
+        }
         vt_mbar_fence_init();
     }
     __syncthreads();
@@ -387,39 +404,79 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
     int g = floordiv4(q_first);
     const unsigned tx_bytes = 16u * (unsigned)(pitch * P.bh);
 
-    auto issue = [&](int gg, unsigned st) {
-        if (tid == 0 && gg <= g_last) {
-            const unsigned bar = bars_s + 8u * st;
-            vt_mbar_expect_tx(bar, tx_bytes);
-            // groups / rows / columns outside the source arrive as zeros (= the texture's border mode)
-            vt_tma_load_3d(ring_s + st * (unsigned)STAGE_BYTES, &G.map[pidx], bar, 4 * xlo, ylo, gg);
-        }
+    // one elected thread: stage group gg into ring stage st
+    auto load_group = [&](int gg, unsigned st) {
+        const unsigned bar = bars_s + 8u * st;
+        vt_mbar_expect_tx(bar, tx_bytes);
+        // groups / rows / columns outside the source arrive as zeros (= the texture's border mode)
+        vt_tma_load_3d(ring_s + st * stage_bytes, &G.map[pidx], bar, 4 * xlo, ylo, gg);
     };
+    constexpr int AHEAD = LOOSE ? NSTAGE : NSTAGE - 1;  // groups in flight after the prologue
+    if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < NSTAGE - 1; i++) issue(g + i, (unsigned)i);
+        for (int i = 0; i < AHEAD; i++)
+            if (g + i <= g_last) load_group(g + i, (unsigned)i);
+    }
     // the column's weights are computed while those first loads are in flight
     T taps;
     if (inplane) taps.template init<RULE>(py, px, ylo, xlo, pitch, P.march);
     float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // sliding window of per-plane sums
     unsigned phase = 0;
+    const long long osm = P.os_m;
     // output pointer of this column at the output plane that input plane 4g is the LAST tap plane of
     float *dstp = P.dst + (size_t)mat * P.dst_batch_stride + (long long)a_s * P.os_slow + (long long)a_f * P.os_fast +
                   (long long)(4 * g - T::AFTER - tm) * P.os_m;
 
+    // vector-store path (march axis = contiguous output axis)
+    float prev[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    // a step's first output index is 4*gg - AFTER - tm: how many values of an aligned output quad come from the
+    // previous step
+    const int qshift = (4 - ((T::AFTER + tm) & 3)) & 3;
+    float *const dcol = P.dst + (size_t)mat * P.dst_batch_stride + (long long)a_s * P.os_slow + (long long)a_f * P.os_fast;
+    auto emit_quad = [&](int zq, const float (&v)[4]) {  // outputs zq .. zq+3 (zq a multiple of 4) of this column
+        const bool all_in = zq >= zc0 && zq + 3 < zc1;                             // uniform
+        const bool all_src = zq + tm >= 0 && zq + 3 + tm < P.s_m;                 // uniform
+        if (all_in && (OOB_ZERO || all_src)) {
+            if (OOB_ZERO ? live : inplane) {
+                const float4 q = (inplane && all_src) ? make_float4(v[0], v[1], v[2], v[3])
+                                                      : make_float4(inplane && (unsigned)(zq + tm) < (unsigned)P.s_m ? v[0] : 0.0f,
+                                                                    inplane && (unsigned)(zq + 1 + tm) < (unsigned)P.s_m ? v[1] : 0.0f,
+                                                                    inplane && (unsigned)(zq + 2 + tm) < (unsigned)P.s_m ? v[2] : 0.0f,
+                                                                    inplane && (unsigned)(zq + 3 + tm) < (unsigned)P.s_m ? v[3] : 0.0f);
+                *reinterpret_cast<float4 *>(dcol + zq) = q;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int zo = zq + j;
+                if (zo >= zc0 && zo < zc1) {
+                    const bool ok = inplane && (unsigned)(zo + tm) < (unsigned)P.s_m;
+                    if (OOB_ZERO) {
+                        if (live) dcol[zo] = ok ? v[j] : 0.0f;
+                    } else if (ok) {
+                        dcol[zo] = v[j];
+                    }
+                }
+            }
+        }
+    };
+
     auto stage_step = [&](auto cur_c, int gg) {
         constexpr unsigned CUR = decltype(cur_c)::value;
         constexpr unsigned FILL = (CUR + NSTAGE - 1) % NSTAGE;
-        constexpr unsigned SOFF = CUR * (unsigned)STAGE_BYTES;
+        const unsigned ring = ring_s + CUR * stage_bytes;
         vt_mbar_wait(bars_s + 8u * CUR, phase);
-        __syncthreads();  // everyone is done with the stage consumed in the previous step: refill it
-        issue(gg + NSTAGE - 1, FILL);
+        if constexpr (!LOOSE) {
+            __syncthreads();  // everyone is done with the stage consumed in the previous step: refill it
+            if (tid == 0 && gg + NSTAGE - 1 <= g_last) load_group(gg + NSTAGE - 1, FILL);
+        }
         float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (inplane) {
             if constexpr (INTERP == VT_LINEAR) {
-                taps.template planes<SOFF>(ring_s, r);
+                taps.planes(ring, r);
             } else if constexpr (INTERP == VT_CUBIC_SIMPLE) {
                 float pq[4];
-                taps.template planes<SOFF>(ring_s, pq);
+                taps.planes(ring, pq);
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
                     // the reference accumulates kz = -1, 0, 1 in that order (helper_interpolation.h:51)
@@ -429,7 +486,7 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
                 }
             } else {
                 float qa[4], qb[4], qc[4];
-                taps.template planes3<SOFF>(ring_s, qa, qb, qc);
+                taps.planes3(ring, qa, qb, qc);
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
                     r[p] = (s3 + s1) + qc[p];  // s3 = A-sum of plane q-2, s1 = B-sum of plane q-1
@@ -439,20 +496,61 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
                 }
             }
         }
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const int zi = 4 * gg + p - T::AFTER;  // input plane at the centre of the output voxel
-            const int zo = zi - tm;               // output index along the march axis
-            if (zo >= zc0 && zo < zc1) {          // uniform: past the warm-up planes, inside the chunk
-                const bool ok = inplane && (unsigned)zi < (unsigned)P.s_m;  // 0 <= p_m < s_m with p_m = zi + 0.5
-                if (OOB_ZERO) {
-                    if (live) dstp[(long long)p * P.os_m] = ok ? r[p] : 0.0f;
-                } else if (ok) {
-                    dstp[(long long)p * P.os_m] = r[p];
+        if constexpr (LOOSE) {
+            // this warp is done reading stage CUR (its loads have landed in registers: the sums above depend on them)
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                vt_mbar_arrive(bars_s + 32u + 8u * CUR);
+                const unsigned old = atom_inc_shared(bars_s + 64u + 4u * CUR);
+                if ((old & (NT / 32 - 1)) == NT / 32 - 1 && gg + NSTAGE <= g_last) {  // the last warp out refills
+                    vt_mbar_wait(bars_s + 32u + 8u * CUR, phase);
+                    load_group(gg + NSTAGE, CUR);
                 }
             }
         }
-        dstp += 4 * P.os_m;
+        if (P.vec_store) {
+            // The march axis is the contiguous output axis (march 2): a thread's four values are neighbours in memory.
+            // Re-cut them into 16-byte aligned quads -- `qa` values of a quad come from the previous step -- and store
+            // each quad with one STG.128 (elements outside the chunk / the source fall back to scalar stores).
+            float v[4];
+            switch (qshift) {  // uniform
+                case 0: v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3]; break;
+                case 1: v[0] = prev[3]; v[1] = r[0]; v[2] = r[1]; v[3] = r[2]; break;
+                case 2: v[0] = prev[2]; v[1] = prev[3]; v[2] = r[0]; v[3] = r[1]; break;
+                default: v[0] = prev[1]; v[1] = prev[2]; v[2] = prev[3]; v[3] = r[0]; break;
+            }
+            emit_quad(4 * gg - T::AFTER - tm - qshift, v);
+#pragma unroll
+            for (int p = 0; p < 4; p++) prev[p] = r[p];
+        } else {
+            const int zi0 = 4 * gg - T::AFTER;  // input plane at the centre of the step's first output voxel
+            const int zo0 = zi0 - tm;          // its output index along the march axis
+            // (r[] is zero for columns outside the source in-plane)
+            if (zo0 >= zc0 && zo0 + 3 < zc1 && zi0 >= 0 && zi0 + 3 < P.s_m) {  // uniform: a step in the interior
+                if (OOB_ZERO ? live : inplane) {
+                    float *d = dstp;
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        *d = r[p];
+                        d += osm;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const int zi = zi0 + p, zo = zo0 + p;
+                    if (zo >= zc0 && zo < zc1) {  // uniform: past the warm-up planes, inside the chunk
+                        const bool ok = inplane && (unsigned)zi < (unsigned)P.s_m;  // 0 <= p_m < s_m with p_m = zi + 0.5
+                        if (OOB_ZERO) {
+                            if (live) dstp[(long long)p * osm] = ok ? r[p] : 0.0f;
+                        } else if (ok) {
+                            dstp[(long long)p * osm] = r[p];
+                        }
+                    }
+                }
+            }
+        }
+        dstp += 4 * osm;
     };
     for (;;) {
         stage_step(std::integral_constant<unsigned, 0>{}, g);
@@ -461,7 +559,20 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
         if (++g > g_last) break;
         stage_step(std::integral_constant<unsigned, 2>{}, g);
         if (++g > g_last) break;
+        if constexpr (NSTAGE == 4) {
+            stage_step(std::integral_constant<unsigned, 3>{}, g);
+            if (++g > g_last) break;
+        }
         phase ^= 1u;
+    }
+    if (P.vec_store && qshift) {  // the values of the last, incomplete quad
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        switch (qshift) {  // uniform
+            case 1: v[0] = prev[3]; break;
+            case 2: v[0] = prev[2]; v[1] = prev[3]; break;
+            default: v[0] = prev[1]; v[1] = prev[2]; v[2] = prev[3]; break;
+        }
+        emit_quad(4 * (g_last + 1) - T::AFTER - tm - qshift, v);
     }
 }
 
@@ -713,19 +824,38 @@ int launch2(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
                 L.bh, P.mats[0].shape, P.mats[0].pitch_idx, L.cost, L.chunks, L.m_chunk);
     const int tiles = ((P.slow_e - P.slow_b + TS - 1) / TS) * P.tiles_fast;
     dim3 grid(tiles, L.chunks, P.n_mats);
-    const size_t smem = 128 + (size_t)NSTAGE * STAGE_BYTES;
+    // ring: stages sized for this launch's box; four stages when the resident CTAs still fit, else three
+    const unsigned stage_bytes = ((unsigned)(16 * (L.bw0 + NPITCH - 1) * L.bh) + 127u) & ~127u;
+    constexpr int RESIDENT = INTERP == VT_CUBIC_TEX ? 2 : 3;
+    static const int force_stages = getenv("VT_Z4_STAGES") ? atoi(getenv("VT_Z4_STAGES")) : 0;  // tuning knobs
+    static const int force_sync = getenv("VT_Z4_LOOSE") ? atoi(getenv("VT_Z4_LOOSE")) : -1;
+    int nstage = ((size_t)SMEM_HEADER + 4u * (size_t)stage_bytes) * RESIDENT <= (size_t)220 * 1024 ? 4 : 3;
+    if (force_stages == 3 || force_stages == 4) nstage = force_stages;
+    const bool loose = force_sync >= 0 ? force_sync != 0 : Z4_DEFAULT_LOOSE;
+    const size_t smem = SMEM_HEADER + (size_t)nstage * stage_bytes;
     // the attribute is per device and per function: one flag per device (a process may drive several GPUs)
     static std::atomic<bool> attr_set_dev[64];
     std::atomic<bool> &attr_set = attr_set_dev[dev & 63];
     if (!attr_set.load(std::memory_order_acquire)) {
-        VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int mx = SMEM_HEADER + 4 * STAGE_BYTES_MAX;
+#define VT_Z4_ATTR(Z, N, LS) \
+    VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, Z, N, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
+        VT_Z4_ATTR(true, 3, false); VT_Z4_ATTR(false, 3, false); VT_Z4_ATTR(true, 4, false); VT_Z4_ATTR(false, 4, false);
+        VT_Z4_ATTR(true, 3, true); VT_Z4_ATTR(false, 3, true); VT_Z4_ATTR(true, 4, true); VT_Z4_ATTR(false, 4, true);
+#undef VT_Z4_ATTR
         attr_set.store(true, std::memory_order_release);
     }
     {
         VtProf prof(VT_K_Z4_LINEAR + INTERP, st);
-        if (oob_zero) vt_z4_kernel<INTERP, RULE, true><<<grid, NT, smem, st>>>(P, G, L.m_chunk);
-        else vt_z4_kernel<INTERP, RULE, false><<<grid, NT, smem, st>>>(P, G, L.m_chunk);
+#define VT_Z4_GO(Z, N, LS) vt_z4_kernel<INTERP, RULE, Z, N, LS><<<grid, NT, smem, st>>>(P, G, L.m_chunk, stage_bytes)
+        if (oob_zero) {
+            if (nstage == 4) { if (loose) VT_Z4_GO(true, 4, true); else VT_Z4_GO(true, 4, false); }
+            else { if (loose) VT_Z4_GO(true, 3, true); else VT_Z4_GO(true, 3, false); }
+        } else {
+            if (nstage == 4) { if (loose) VT_Z4_GO(false, 4, true); else VT_Z4_GO(false, 4, false); }
+            else { if (loose) VT_Z4_GO(false, 3, true); else VT_Z4_GO(false, 3, false); }
+        }
+#undef VT_Z4_GO
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
@@ -756,6 +886,8 @@ void fill_z4(const VtResampleParams &P, int m, Z4Params &Q, float ext_y[], float
     Q.n_mats = P.n_mats;
     Q.prod_on_fast = R.prod_on_fast;
     Q.march = m;
+    Q.vec_store = (m == 2 && (P.o2 % 4) == 0 && (P.dst_batch_stride % 4) == 0 && ((uintptr_t)P.dst % 16) == 0 &&
+                   !getenv("VT_Z4_NO_VEC")) ? 1 : 0;
     Q.tiles_fast = (Q.o_fast + TS - 1) / TS;
     for (int k = 0; k < P.n_mats; k++) {
         const VtMat &M = P.mats[k];

@@ -25,6 +25,14 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 
+def _rank_world(dist, group):
+    """(rank, world) of this process; a process that never initialised torch.distributed is a world of one (every
+    function here then degenerates to its single-GPU form: no collective is issued)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
 def split_batch(n_items: int, world: int, rank: int) -> range:
     """Contiguous block of a batch of `n_items` for `rank`: sizes differ by at most one, earlier ranks get the
     larger blocks, every item belongs to exactly one rank."""
@@ -97,6 +105,11 @@ class CudaEngine:
             self._side = torch.cuda.Stream(device=self.device)
         self._side.wait_stream(torch.cuda.current_stream(self.device))
         return torch.cuda.stream(self._side)
+
+    def join_producer(self):
+        """The current stream waits for everything enqueued on the producer stream so far."""
+        if getattr(self, '_side', None) is not None:
+            self.torch.cuda.current_stream(self.device).wait_stream(self._side)
 
     def prepare_stream(self, volume, interpolation, buffer, plan):
         """Root only: returns step(i), which enqueues (on the current stream) the work that makes planes
@@ -213,13 +226,14 @@ def _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shap
     `on_planes(buffer, width, ready)`: called on every rank each time planes [0, ready) of the buffer have arrived
     (stream-ordered: work enqueued from it runs after them), so that consumers can start before the rest is there.
     Returns (buffer, width) on every rank."""
-    rank = dist.get_rank(group)
+    rank, world = _rank_world(dist, group)
     filtered = interpolation.startswith('filt')
     if shape is not None:
         buf_shape, width = engine.describe_shape(tuple(int(v) for v in shape))
     else:
         box = [engine.describe(volume, interpolation) if rank == src else None]
-        dist.broadcast_object_list(box, src=src, group=group)
+        if world > 1:
+            dist.broadcast_object_list(box, src=src, group=group)
         buf_shape, width = box[0]
     buffer = engine.empty(tuple(buf_shape))
     plan = stream_plan(buf_shape[0], filtered, chunks)
@@ -232,13 +246,19 @@ def _prepare_and_broadcast(engine, dist, group, src, volume, interpolation, shap
         for i, (_, _, z0, z1) in enumerate(plan):
             if step is not None:
                 step(i)
-            if z1 > z0:
+            if z1 > z0 and world > 1:
                 # NCCL over NVLink / NVSwitch on a GPU node
                 works.append((dist.broadcast(buffer[z0:z1], src=src, group=group, async_op=True), z1))
     for w, z1 in works:
         w.wait()  # the consumer's stream waits for these planes; the host does not
         if on_planes is not None:
             on_planes(buffer, width, z1)
+    if not works:  # a world of one: nothing was shipped, the consumer's stream just waits for the producer's
+        join = getattr(engine, 'join_producer', None)
+        if join is not None:
+            join()
+        if on_planes is not None:
+            on_planes(buffer, width, int(buf_shape[0]))
     return buffer, width
 
 
@@ -406,7 +426,7 @@ def sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = 'filt_bsp
     default; it pays when the broadcast is long against the resampling (few matrices per rank, large volumes).
     """
     import torch.distributed as dist
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = _rank_world(dist, group)
     if engine is None:
         import torch
         engine = CudaEngine(torch.cuda.current_device())
@@ -456,7 +476,7 @@ def zslab_affine(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline'
     Returns (slab, (z0, z1)): this rank's output planes, resident on this rank.
     """
     import torch.distributed as dist
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = _rank_world(dist, group)
     if engine is None:
         import torch
         engine = CudaEngine(torch.cuda.current_device())
@@ -507,7 +527,7 @@ def zslab_affine(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline'
 def _scatter_prefilter_exchange(engine, dist, group, src, volume, interpolation, shape, boxes, block=None):
     """Footprint path of `zslab_affine`; returns (full-size resident buffer of which only this rank's footprint is
     filled, width)."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = _rank_world(dist, group)
     filtered = interpolation.startswith('filt')
     d0, d1, d2 = shape
     halo = PREFILTER_LOOKAHEAD if filtered else 0
@@ -592,7 +612,7 @@ def project_sweep(volume, matrices: Sequence[np.ndarray], interpolation: str = '
     the ranks of `group` like `sweep`; the transformed volumes are never written (vt_project_strided_f32).
     Returns (projections, indices): `projections[i]` (d1, d2) belongs to `matrices[indices[i]]`, resident on this rank."""
     import torch.distributed as dist
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = _rank_world(dist, group)
     if engine is None:
         import torch
         engine = CudaEngine(torch.cuda.current_device())
@@ -611,7 +631,7 @@ def zslab_project(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline
     exchange step of the path besides the coefficient broadcast, d1 x d2 floats.  Returns the full (d1, d2) projection
     on every rank."""
     import torch.distributed as dist
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = _rank_world(dist, group)
     if engine is None:
         import torch
         engine = CudaEngine(torch.cuda.current_device())
@@ -619,7 +639,8 @@ def zslab_project(volume, matrix: np.ndarray, interpolation: str = 'filt_bspline
     z0, z1 = split_slabs(int(buffer.shape[0]), world, rank)
     m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(1, 4, 4)
     part = engine.project_many(buffer, width, interpolation, m, z_range=(z0, z1))[0].contiguous()
-    dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    if world > 1:
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
     return part
 
 
@@ -627,7 +648,9 @@ def gather_slabs(slab, group=None, dst: int = 0):
     """Convenience for tests / small volumes: concatenates the z-slabs on rank `dst` (None elsewhere)."""
     import torch
     import torch.distributed as dist
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = _rank_world(dist, group)
+    if world == 1:
+        return slab
     shapes: List = [None] * world
     dist.all_gather_object(shapes, tuple(slab.shape), group=group)
     if rank != dst:

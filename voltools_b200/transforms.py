@@ -31,6 +31,35 @@ AVAILABLE_DEVICES = utils.get_available_devices()
 _host_tls = threading.local()
 
 
+_host_registry = []  # every HostContext ever created (weak): release_host_buffers() reaches other threads' contexts too
+
+
+def _host_context(dev):
+    ctxs = getattr(_host_tls, 'ctx', None)
+    if ctxs is None:
+        ctxs = _host_tls.ctx = {}
+    ctx = ctxs.get(dev)
+    if ctx is None:
+        import weakref
+        ctx = ctxs[dev] = _native.HostContext(dev)
+        _host_registry.append(weakref.ref(ctx))
+    return ctx
+
+
+def release_host_buffers():
+    """Free the device buffers held by the numpy-in / numpy-out contexts of every thread (one context per host thread
+    and device; each keeps source, coefficient, workspace and output buffers sized for the largest volume it has seen --
+    16 GiB after one 1024^3 filt_* call).  The contexts stay usable and re-allocate on demand.  Not to be called while
+    another thread is inside transform() / affine()."""
+    alive = []
+    for ref in _host_registry:
+        ctx = ref()
+        if ctx is not None:
+            ctx.trim()
+            alive.append(ref)
+    _host_registry[:] = alive
+
+
 # ----------------------------------------------------------------------------------------------------
 # array adapters (plumbing only: pointers go to the C ABI)
 # ----------------------------------------------------------------------------------------------------
@@ -218,14 +247,12 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
 
         if host_in and vout is None:
             # numpy in -> numpy out (transforms.py:180-223): pipelined host path inside the library
-            src = np.ascontiguousarray(volume, dtype=np.float32)
-            result = output if host_out else np.empty(shape, dtype=np.float32)
-            ctxs = getattr(_host_tls, 'ctx', None)
-            if ctxs is None:
-                ctxs = _host_tls.ctx = {}
-            ctx = ctxs.get(dev)
-            if ctx is None:
-                ctx = ctxs[dev] = _native.HostContext(dev)
+            # The library copies straight from / to these arrays, and only page-locked memory copies asynchronously at
+            # link speed: a pageable input is staged through a pinned buffer (multi-threaded host copy), the result
+            # lives in pinned memory from torch's caching host allocator (returned as an ordinary numpy array).
+            src = _native.as_pinned(np.ascontiguousarray(volume, dtype=np.float32))
+            result = output if host_out else _native.pinned_empty(shape)
+            ctx = _host_context(dev)
             ctx.affine(src, result, m, interp, needs_prefilter)
             if host_out:
                 result = None
@@ -251,8 +278,8 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
             # vt_resample_z4.cu) samples the Z4 layout of that axis: the prefilter's Z sweep writes it directly for
             # axis 0, otherwise one pack pass (the reference pays the same pass for its CUDA-array copy,
             # transforms.py:197-199).
-            axis = _native.z4_axis(shape, shape, m, interp) if _native.z4_wanted(interp, False) else -1
-            if axis >= 0:
+            axis = _native.z4_axis(shape, shape, m, interp)
+            if axis >= 0 and _native.z4_wanted(interp, False, axis, needs_prefilter):
                 z4_t = torch.empty(_native.z4_bytes(shape, axis) // 4, dtype=torch.float32, device=f'cuda:{dev}')
                 if needs_prefilter:
                     ws_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')

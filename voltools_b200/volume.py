@@ -124,7 +124,7 @@ class StaticVolume:
         hardware texture object once this volume has seen TEXTURE_AFTER such transforms -- the reference keeps the
         same second copy (volume.py:37-50); until then, and always for *_simple, the shared-memory brick kernels."""
         axis = -1
-        if _native.z4_wanted(self._interp, True) and not getattr(self, '_plain_only', False):
+        if _native.z4_wanted(self._interp, True) and not getattr(self, '_plain_only', False):  # (resident: always)
             axis = _native.z4_axis(self.shape, self.shape, m, self._interp)
         if axis >= 0:
             _native.affine_z4(self._z4_buffer(axis, stream).data_ptr(), axis, self.shape, dst_ptr, self.shape, m,
