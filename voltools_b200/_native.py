@@ -301,6 +301,16 @@ def affine_plan(src_ptr, src_shape, dst_shape, matrices, interp, flags=0):
     return {1: 'gather', 2: 'brick', 3: 'slice'}[fam.value]
 
 
+def launch_plan(src_ptr, src_shape, dst_shape, matrices, interp, resident=True, filtered=False):
+    """Which kernel family the PYTHON layer runs for these matrices (it routes matrices that leave one axis alone to
+    the slice4 kernels before asking the plain-layout planner): {'family': 'slice4', 'axis': m} or
+    {'family': 'slice' | 'brick' | 'gather'}."""
+    axis = z4_axis(src_shape, dst_shape, matrices, interp)
+    if axis >= 0 and z4_wanted(interp, resident, axis, filtered):
+        return {'family': 'slice4', 'axis': axis}
+    return {'family': affine_plan(src_ptr, src_shape, dst_shape, matrices, interp)}
+
+
 class Texture:
     """Owner of a vt_tex: the sampled volume as a 3-D CUDA array + texture object (texture kernel family)."""
 

@@ -23,10 +23,14 @@
 
 namespace {
 
-constexpr int TZ = 8, TY = 8, TX = 16;        // output tile
-constexpr int NT = 256;                       // threads: 16 (x) x 8 (y) x 2 (z halves), 4 voxels each along z
-constexpr int VPT = TZ * TY * TX / NT;        // 4
-constexpr int MAX_BRICK_BYTES = 72 * 1024;    // 3 CTAs per SM
+constexpr int TY = 8, TX = 16;                // output tile in (a1, a2); along a0 it is 2 * VPT planes
+constexpr int NT = 256;                       // threads: 16 (x) x 8 (y) x 2 (z halves), VPT voxels each along z
+// Two tile depths.  8 planes (VPT = 4, the default): bricks <= 72 KB, 3 CTAs per SM.  16 planes (VPT = 8, knob
+// VT_BRICK_VPT=8): bricks <= 110 KB, 2 CTAs per SM, ~25 % less L2 -> shared-memory traffic per voxel and half the per-tile
+// set-up -- measured SLOWER at 512^3 (linear 173 vs 209, cubic_tex 56 vs 67 Gvox/s under the full affine): a CTA waits
+// for its whole brick before it computes, so the third resident CTA hides more than the deeper tile saves.
+constexpr int MAX_BRICK_BYTES_4 = 72 * 1024, MAX_BRICK_BYTES_8 = 110 * 1024;
+__host__ __device__ constexpr int max_brick_bytes(int vpt) { return vpt == 4 ? MAX_BRICK_BYTES_4 : MAX_BRICK_BYTES_8; }
 
 struct VtBrickStaging {
     CUtensorMap tmap;
@@ -38,7 +42,7 @@ struct VtBrickStaging {
 // form a 16 (x) x 8 (y) x 2 (z groups) block; `layout` is the sub-box of it a warp covers: which one spreads a warp's
 // 32 brick addresses over the most banks depends on the matrix (tune_brick).
 constexpr int N_BRICK_LAYOUTS = 6;
-__host__ __device__ __forceinline__ void thread_pos(int tid, int layout, int &tx, int &ty, int &tz)
+__host__ __device__ __forceinline__ void thread_pos(int tid, int layout, int &tx, int &ty, int &tz)  // tz: 0 / 1
 {
     // log2 of the warp's extent along x and y (the rest of its 32 lanes goes along z)
     const int lwx = layout == 0 ? 4 : (layout == 1 ? 3 : (layout == 2 ? 2 : (layout == 3 ? 3 : (layout == 4 ? 2 : 4))));
@@ -204,10 +208,11 @@ __device__ __forceinline__ float cubic_simple_brick(const Brick &b, float x, flo
 }
 
 // MODE: 0 = out-of-bounds voxels are skipped, 1 = written as zero, 2 = rotate-and-project (voxels are summed along axis 0)
-template <int INTERP, int RULE, int MODE>
-__global__ void __launch_bounds__(NT, 3)
+template <int INTERP, int RULE, int MODE, int VPT>
+__global__ void __launch_bounds__(NT, VPT == 4 ? 3 : 2)
     vt_brick_kernel(const __grid_constant__ VtResampleParams P, const __grid_constant__ VtBrickStaging G)
 {
+    constexpr int TZ = 2 * VPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];  // [128 B: mbarrier][brick]
     const unsigned bar = vt_smem_u32(smem_raw);
     const float *brick = (const float *)(smem_raw + 128);
@@ -220,36 +225,50 @@ __global__ void __launch_bounds__(NT, 3)
     const int a0_0 = P.z_begin + zt * TZ, a1_0 = blockIdx.y * TY, a2_0 = blockIdx.x * TX;
     const int a0_1 = min(a0_0 + TZ, P.z_end) - 1, a1_1 = min(a1_0 + TY, P.o1) - 1, a2_1 = min(a2_0 + TX, P.o2) - 1;
 
-    // brick origin: per input axis the extremes are at tile corners (the float recipe is monotone in each index)
+    // Brick origin: per input axis the extremes are at tile corners (the float recipe is monotone in each index).
+    // Eight lanes of warp 0 take one corner each and min / max are reduced with shuffles: the per-tile set-up costs a
+    // few dozen instructions on one warp instead of ~300 on every thread (a thread only produces VPT = 4 voxels, so
+    // that redundant prologue was more than half of the trilinear kernel's instruction count).
     constexpr int LO = INTERP == VT_LINEAR ? 0 : -1;
-    int lo[3];
-    bool interior = true;  // every voxel of the tile samples inside the source: no per-voxel bounds tests
+    int *setup = (int *)(smem_raw + 16);  // [lo0, lo1, lo2, interior], after the mbarrier
+    if (tid < 32) {
+        const int c = tid & 7;
+        const float fa0 = (float)((c & 4) ? a0_1 : a0_0), fa1 = (float)((c & 2) ? a1_1 : a1_0);
+        const float fa2 = (float)((c & 1) ? a2_1 : a2_0);
+        int lo_[3];
+        bool inside = true;  // every voxel of the tile samples inside the source: no per-voxel bounds tests
 #pragma unroll
-    for (int r = 0; r < 3; r++) {
-        float mn = 3.0e38f, mx = -3.0e38f;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const float fa0 = (float)((c & 4) ? a0_1 : a0_0), fa1 = (float)((c & 2) ? a1_1 : a1_0);
-            const float fa2 = (float)((c & 1) ? a2_1 : a2_0);
+        for (int r = 0; r < 3; r++) {
             const float p = vt_row_finish(M.r[r], vt_row_base(M.r[r], fa0, fa1), fa2);
-            mn = fminf(mn, p);
-            mx = fmaxf(mx, p);
+            float mn = p, mx = p;
+#pragma unroll
+            for (int off = 4; off >= 1; off >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            }
+            // sample points further out than 2 texels are out of bounds anyway: keep the conversion safe
+            const float dim = (float)(r == 0 ? P.s0 : (r == 1 ? P.s1 : P.s2));
+            inside = inside && mn >= 0.0f && mx < dim;  // transforms.py:276-278 holds for the extremes, hence for all
+            mn = fminf(fmaxf(mn, -2.0f), dim + 2.0f);
+            lo_[r] = (int)floorf(mn - 0.5f) + LO;
         }
-        // sample points further out than 2 texels are out of bounds anyway: keep the conversion safe
-        const float dim = (float)(r == 0 ? P.s0 : (r == 1 ? P.s1 : P.s2));
-        interior = interior && mn >= 0.0f && mx < dim;  // transforms.py:276-278 holds for the extremes, hence for all
-        mn = fminf(fmaxf(mn, -2.0f), dim + 2.0f);
-        lo[r] = (int)floorf(mn - 0.5f) + LO;
+        lo_[2] &= ~3;  // the TMA box must start on a 16-byte boundary of the row
+        if (tid == 0) {
+            vt_tma_prefetch_desc(&G.tmap);
+            vt_mbar_init(bar, 1);
+            vt_mbar_fence_init();
+            vt_mbar_expect_tx(bar, (unsigned)(G.bw * G.bh * G.bd) * 4u);
+            vt_tma_load_3d(vt_smem_u32(brick), &G.tmap, bar, lo_[2], lo_[1], lo_[0]);
+            setup[0] = lo_[0];
+            setup[1] = lo_[1];
+            setup[2] = lo_[2];
+            setup[3] = inside ? 1 : 0;
+        }
     }
-    lo[2] &= ~3;  // the TMA box must start on a 16-byte boundary of the row
-    if (tid == 0) {
-        vt_tma_prefetch_desc(&G.tmap);
-        vt_mbar_init(bar, 1);
-        vt_mbar_fence_init();
-        vt_mbar_expect_tx(bar, (unsigned)(G.bw * G.bh * G.bd) * 4u);
-        vt_tma_load_3d(vt_smem_u32(brick), &G.tmap, bar, lo[2], lo[1], lo[0]);
-    }
-    const Brick b{brick, G.bw, G.bw * G.bh, lo[0], lo[1], lo[2]};
+    __syncthreads();  // the barrier is initialised and the set-up published before anyone goes on
+    const int4 su = *reinterpret_cast<const int4 *>(setup);
+    const bool interior = su.w != 0;
+    const Brick b{brick, G.bw, G.bw * G.bh, su.x, su.y, su.z};
     // this thread's voxels: (a0 = a0_0 + tz*VPT + v, a1, a2)
     int tx, ty, tz;
     thread_pos(tid, G.layout, tx, ty, tz);
@@ -259,7 +278,6 @@ __global__ void __launch_bounds__(NT, 3)
     const float fa1 = (float)a1, fa2 = (float)a2;
     float *__restrict__ dst = P.dst + (size_t)mat * P.dst_batch_stride + ((size_t)a1 * P.o2 + a2);
     const size_t oplane = (size_t)P.o1 * P.o2;
-    __syncthreads();  // the barrier is initialised before anyone polls it
     vt_mbar_wait(bar, 0);
     if (!live) return;
     constexpr bool project = MODE == 2;  // sum along axis 0 instead of storing
@@ -322,8 +340,9 @@ __global__ void __launch_bounds__(NT, 3)
 }
 
 // brick dimensions needed by the batch (max over matrices), or false if some matrix needs more than fits
-bool brick_dims(const VtResampleParams &P, int interp, int &bw, int &bh, int &bd)
+bool brick_dims(const VtResampleParams &P, int interp, int vpt, int &bw, int &bh, int &bd)
 {
+    const int TZ = 2 * vpt;
     if ((P.src_row % 4) != 0 || (P.src_plane % 4) != 0 || ((uintptr_t)P.src % 16) != 0) return false;
     if (P.n_mats < 1) return false;
     const int t[3] = {TZ - 1, TY - 1, TX - 1};
@@ -342,7 +361,7 @@ bool brick_dims(const VtResampleParams &P, int interp, int &bw, int &bh, int &bd
     bh = need[1];
     bw = (need[2] + 3 + 3) / 4 * 4;  // + 3: the box start is rounded down to a multiple of 4 texels
     if (bd > 256 || bh > 256 || bw > 256) return false;
-    return (size_t)bw * bh * bd * 4 <= (size_t)MAX_BRICK_BYTES;
+    return (size_t)bw * bh * bd * 4 <= (size_t)max_brick_bytes(vpt);
 }
 
 // host copy of the coordinate recipe (same operations; used only to predict bank conflicts)
@@ -358,8 +377,10 @@ float host_coord(const float *row, float a0, float a1, float a2)
 // lanes hit bank (z*bw*bh + y*bw + x) mod 32.  The brick may be padded (bw by multiples of 4 texels, bh by a few
 // rows) and the warp may tile the output 2 x 16 or 4 x 8; pick the combination with the fewest predicted conflicts
 // for the first matrix of the batch over a couple of sample tiles.
-void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
+void tune_brick(const VtResampleParams &P, VtBrickStaging &G, int VPT)
 {
+    const int TZ = 2 * VPT;
+    const int MAX_BRICK_BYTES = max_brick_bytes(VPT);
     const VtMat &M = P.mats[0];
     constexpr int NS = 2;
     // The search below costs ~100 us of host time.  Small launches cannot win that back (tools/latency_probe.py: a 16^3
@@ -374,7 +395,7 @@ void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
     };
     static thread_local Memo memo[8];
     static thread_local unsigned memo_next = 0;
-    const int key[7] = {P.o1, P.o2, P.z_begin, P.z_end, G.bw, G.bh, G.bd};
+    const int key[7] = {P.o1, P.o2, P.z_begin + 4096 * VPT, P.z_end, G.bw, G.bh, G.bd};
     for (const Memo &e : memo)
         if (e.valid && memcmp(&e.m, &M, sizeof M) == 0 && memcmp(e.key, key, sizeof key) == 0) {
             G.bw = e.bw;
@@ -439,13 +460,14 @@ void tune_brick(const VtResampleParams &P, VtBrickStaging &G)
     slot.valid = true;
 }
 
-template <int INTERP, int RULE>
-int launch2(const VtResampleParams &P, cudaStream_t st)
+template <int INTERP, int RULE, int VPT>
+int launch3(const VtResampleParams &P, cudaStream_t st)
 {
+    constexpr int TZ = 2 * VPT;
     VtBrickStaging G;
     memset(&G, 0, sizeof G);
-    if (!brick_dims(P, INTERP, G.bw, G.bh, G.bd)) return VT_ERR_UNSUPPORTED;
-    tune_brick(P, G);  // (linear too: a rotation that sends a warp's x run down the brick's z axis is 8-way conflicted untuned)
+    if (!brick_dims(P, INTERP, VPT, G.bw, G.bh, G.bd)) return VT_ERR_UNSUPPORTED;
+    tune_brick(P, G, VPT);  // (linear too: a rotation that sends a warp's x run down the brick's z axis is 8-way conflicted untuned)
     const unsigned long long gdim[3] = {(unsigned long long)P.s2, (unsigned long long)P.s1, (unsigned long long)P.s0};
     const unsigned long long gstr[2] = {(unsigned long long)P.src_row * 4, (unsigned long long)P.src_plane * 4};
     const unsigned box[3] = {(unsigned)G.bw, (unsigned)G.bh, (unsigned)G.bd};
@@ -462,23 +484,33 @@ int launch2(const VtResampleParams &P, cudaStream_t st)
     VT_CUDA(cudaGetDevice(&attr_dev));
     std::atomic<bool> &attr_set = attr_set_dev[attr_dev & 63];
     if (!attr_set.load(std::memory_order_acquire)) {
-        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     128 + MAX_BRICK_BYTES));
-        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     128 + MAX_BRICK_BYTES));
-        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     128 + MAX_BRICK_BYTES));
+        const int mx = 128 + max_brick_bytes(VPT);
+        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 0, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 1, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        VT_CUDA(cudaFuncSetAttribute(vt_brick_kernel<INTERP, RULE, 2, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         attr_set.store(true, std::memory_order_release);
     }
     {
         VtProf prof(VT_K_BRICK_LINEAR + INTERP, st);
-        if (P.flags & VT_INTERNAL_PROJECT) vt_brick_kernel<INTERP, RULE, 2><<<grid, NT, smem, st>>>(P, G);
-        else if (P.flags & VT_OOB_ZERO) vt_brick_kernel<INTERP, RULE, 1><<<grid, NT, smem, st>>>(P, G);
-        else vt_brick_kernel<INTERP, RULE, 0><<<grid, NT, smem, st>>>(P, G);
+        if (P.flags & VT_INTERNAL_PROJECT) vt_brick_kernel<INTERP, RULE, 2, VPT><<<grid, NT, smem, st>>>(P, G);
+        else if (P.flags & VT_OOB_ZERO) vt_brick_kernel<INTERP, RULE, 1, VPT><<<grid, NT, smem, st>>>(P, G);
+        else vt_brick_kernel<INTERP, RULE, 0, VPT><<<grid, NT, smem, st>>>(P, G);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
     return VT_OK;
+}
+
+// tile depth (see the constants at the top: the deep tile is a measurement knob)
+template <int INTERP, int RULE>
+int launch2(const VtResampleParams &P, cudaStream_t st)
+{
+    static const int force = getenv("VT_BRICK_VPT") ? atoi(getenv("VT_BRICK_VPT")) : 0;  // tuning knob: 4 / 8
+    int bw, bh, bd;
+    const bool deep_fits = brick_dims(P, INTERP, 8, bw, bh, bd) && (P.z_end - P.z_begin) >= 16;
+    const bool deep = force == 8 && deep_fits;
+    if (deep) return launch3<INTERP, RULE, 8>(P, st);
+    return launch3<INTERP, RULE, 4>(P, st);
 }
 
 template <int INTERP>
@@ -493,7 +525,7 @@ int launch1(const VtResampleParams &P, cudaStream_t st)
 int vt_brick_supported(const VtResampleParams &P, int interp)
 {
     int bw, bh, bd;
-    return brick_dims(P, interp, bw, bh, bd) ? 1 : 0;
+    return brick_dims(P, interp, 4, bw, bh, bd) ? 1 : 0;
 }
 
 int vt_launch_brick(const VtResampleParams &P, int interp, cudaStream_t st)

@@ -113,6 +113,16 @@ class StaticVolume:
             z4[axis] = buf
         return buf
 
+    def plan(self, matrices):
+        """Which kernel family `affine` / `affine_many` would run for these matrices on this volume (introspection):
+        {'family': 'slice4', 'axis': m} for matrices that leave axis m alone, else 'brick' / 'gather' (or the texture
+        family once the volume has switched to it)."""
+        m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
+        p = _native.launch_plan(self._coeffs.data_ptr(), self.shape, self.shape, m, self._interp, resident=True)
+        if p['family'] != 'slice4' and getattr(self, '_tex', None) not in (None, False):
+            p = {'family': 'texture'}
+        return p
+
     def _launch(self, dst_ptr, m, flags, stream, z_range=None):
         """One launch set for the matrices `m` (K, 4, 4) on the resident volume.
 
