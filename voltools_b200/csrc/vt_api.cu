@@ -114,13 +114,14 @@ VtProf::~VtProf()
     g_prof_recs.push_back(r);
 }
 
-int vt_encode_tmap_3d(void *tmap, const void *base, const unsigned long long dims[3], const unsigned long long strides[2],
-                      const unsigned box[3])
+int vt_encode_tmap_nd(void *tmap, const void *base, int rank, const unsigned long long *dims, const unsigned long long *strides,
+                      const unsigned *box)
 {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static encode_fn fn = nullptr;
+    if (rank < 3 || rank > 5) return VT_ERR_INVALID_ARG;
     if (!fn) {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -128,14 +129,24 @@ int vt_encode_tmap_3d(void *tmap, const void *base, const unsigned long long dim
         if (!p || q != cudaDriverEntryPointSuccess) return VT_ERR_UNSUPPORTED;
         fn = (encode_fn)p;
     }
-    const cuuint64_t gdim[3] = {dims[0], dims[1], dims[2]};
-    const cuuint64_t gstr[2] = {strides[0], strides[1]};
-    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult cr = fn((CUtensorMap *)tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstr, bx, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; i++) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        estr[i] = 1;
+        if (i + 1 < rank) gstr[i] = strides[i];
+    }
+    const CUresult cr = fn((CUtensorMap *)tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)base, gdim, gstr, bx,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return cr == CUDA_SUCCESS ? VT_OK : 2000 + (int)cr;
+}
+
+int vt_encode_tmap_3d(void *tmap, const void *base, const unsigned long long dims[3], const unsigned long long strides[2],
+                      const unsigned box[3])
+{
+    return vt_encode_tmap_nd(tmap, base, 3, dims, strides, box);
 }
 
 namespace {

@@ -44,6 +44,9 @@ void vt_count_launch(int n = 1);
 // has no link-time dependency on libcuda (it must load on machines without a driver).
 int vt_encode_tmap_3d(void *tmap, const void *base, const unsigned long long dims[3], const unsigned long long strides[2],
                       const unsigned box[3]);
+// the same for rank 3..5 (dims / box: rank entries, strides: rank - 1 entries in bytes)
+int vt_encode_tmap_nd(void *tmap, const void *base, int rank, const unsigned long long *dims, const unsigned long long *strides,
+                      const unsigned *box);
 
 // ---------------------------------------------------------------------------------------------------
 // per-kernel device timing (vt_profile_* in the C ABI): every launch site wraps its <<<>>> in a VtProf,
@@ -214,6 +217,20 @@ __device__ __forceinline__ void vt_tma_load_3d(unsigned smem_dst, const void *tm
         "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// 4-D tiled box STORE shared -> global (bulk async group); elements outside the tensor are not written
+__device__ __forceinline__ void vt_tma_store_4d(const void *tmap, unsigned smem_src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(tmap),
+                 "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void vt_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void vt_bulk_wait_read()  // at most N groups still READING shared memory
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void vt_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void vt_tma_prefetch_desc(const void *tmap)
 {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");

@@ -64,6 +64,7 @@ struct Z4Params {
     long long dst_batch_stride;
     long long os_slow, os_fast, os_m;  // output element strides of the tile's slow / fast axes and of the march axis
     int o_fast;                        // extent of the fast tile axis
+    int o_slow, o_m;                   // full extents of the slow tile axis and of the march axis
     int slow_b, slow_e;                // range of the slow tile axis to produce
     int m_b, m_e;                      // range of the march axis to produce
     int s_y, s_x, s_m;                 // source extents: in-plane rows, in-plane columns, march axis
@@ -73,12 +74,15 @@ struct Z4Params {
     int tiles_fast;
     int march;                         // the march axis (0..2): selects the slots of the texture-weight rule
     int vec_store;                     // march axis contiguous in the output and 16-byte alignable: STG.128 quads
+    int tma_store;                     // ... and staged through shared memory + cp.async.bulk.tensor stores (UTMASTG)
     Z4Mat mats[VT_MAX_BATCH];
 };
 
 struct Z4Maps {
     CUtensorMap map[NPITCH];
+    CUtensorMap omap;  // output tensor (x, a1, a0, matrix) with an 8 x 16 x 16 x 1 box: the TMA store path of march axis 2
 };
+constexpr int OTILE_BYTES = TS * TS * 32;  // one staged output tile: two 16-byte quads (a whole 32-byte sector) per column
 
 // The reference's coordinate recipe (voltools/transforms.py:264-274 as compiled: t = a1*M1; t = fma(a0,M0,t);
 // t = fma(a2,M2,t); t = M3 + t; p = t + 0.5) for a source row whose coefficient of the march index is zero: that term
@@ -461,14 +465,39 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
         }
     };
 
+    // TMA store path (march axis 2, barrier ring): every thread parks its aligned quads in a shared-memory tile laid out
+    // as the box (x: 8, a1: 16, a0: 16) -- two consecutive steps fill a column's 32-byte sector --; after the next
+    // block-wide barrier one thread hands the tile to the TMA engine (cp.async.bulk.tensor store).  256 whole sectors
+    // leave as one bulk operation instead of sixteen STG.128 instructions that each touch 32 different cache lines with
+    // half a sector.  Only for tiles every column of which may be written (OOB_SKIP: all columns inside the source
+    // in-plane); two tiles alternate.
+    const unsigned otile_s = ring_s + NSTAGE * stage_bytes;
+    bool tile_ok = false;
+    if (!LOOSE && P.tma_store) {
+        const bool mine = OOB_ZERO ? true : (inplane || !live);
+        tile_ok = __syncthreads_and(mine ? 1 : 0) != 0 && as0 + TS <= P.slow_e;
+    }
+    int pending_zq = 0, pending_buf = -1, obuf = 0;  // a tile completed in the previous step, not yet handed over
+    bool half = false;                                // the even quad of the current tile is in place
+    auto flush_tile = [&]() {                         // after a block-wide barrier
+        if (pending_buf >= 0 && tid == 0) {
+            vt_fence_proxy_async();
+            vt_tma_store_4d(&G.omap, otile_s + (unsigned)pending_buf * OTILE_BYTES, pending_zq, af0, as0, mat);
+            vt_bulk_commit();
+        }
+        pending_buf = -1;
+    };
+
     auto stage_step = [&](auto cur_c, int gg) {
         constexpr unsigned CUR = decltype(cur_c)::value;
         constexpr unsigned FILL = (CUR + NSTAGE - 1) % NSTAGE;
         const unsigned ring = ring_s + CUR * stage_bytes;
         vt_mbar_wait(bars_s + 8u * CUR, phase);
         if constexpr (!LOOSE) {
+            if (tile_ok && tid == 0) vt_bulk_wait_read<1>();  // the tile this step may overwrite has been read
             __syncthreads();  // everyone is done with the stage consumed in the previous step: refill it
             if (tid == 0 && gg + NSTAGE - 1 <= g_last) load_group(gg + NSTAGE - 1, FILL);
+            if (tile_ok) flush_tile();
         }
         float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (inplane) {
@@ -519,7 +548,35 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
                 case 2: v[0] = prev[2]; v[1] = prev[3]; v[2] = r[0]; v[3] = r[1]; break;
                 default: v[0] = prev[1]; v[1] = prev[2]; v[2] = prev[3]; v[3] = r[0]; break;
             }
-            emit_quad(4 * gg - T::AFTER - tm - qshift, v);
+            const int zq = 4 * gg - T::AFTER - tm - qshift;
+            // an even quad (x a multiple of 8) opens a tile if its partner, the next step's quad, can be staged too
+            const int odd = (zq >> 2) & 1;
+            const int z8 = zq - 4 * odd;  // the sector: outputs z8 .. z8+7
+            const bool sector_ok = tile_ok && z8 >= zc0 && z8 + 7 < zc1 &&
+                                   (OOB_ZERO || (z8 + tm >= 0 && z8 + 7 + tm < P.s_m)) && 4 * g_last + 3 - T::AFTER - tm >= z8 + 7;
+            if (sector_ok && (odd ? half : true)) {  // uniform
+                float4 q = make_float4(v[0], v[1], v[2], v[3]);
+                if (OOB_ZERO) {  // values past the ends of the source along the march axis are zeros
+                    if ((unsigned)(zq + tm) >= (unsigned)P.s_m) q.x = 0.0f;
+                    if ((unsigned)(zq + 1 + tm) >= (unsigned)P.s_m) q.y = 0.0f;
+                    if ((unsigned)(zq + 2 + tm) >= (unsigned)P.s_m) q.z = 0.0f;
+                    if ((unsigned)(zq + 3 + tm) >= (unsigned)P.s_m) q.w = 0.0f;
+                }
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(otile_s + (unsigned)obuf * OTILE_BYTES +
+                                                                              32u * (unsigned)(ty * TS + tx) + 16u * odd),
+                             "f"(q.x), "f"(q.y), "f"(q.z), "f"(q.w)
+                             : "memory");
+                if (odd) {
+                    pending_zq = z8;
+                    pending_buf = obuf;
+                    obuf ^= 1;
+                    half = false;
+                } else {
+                    half = true;
+                }
+            } else {
+                emit_quad(zq, v);
+            }
 #pragma unroll
             for (int p = 0; p < 4; p++) prev[p] = r[p];
         } else {
@@ -564,6 +621,11 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
             if (++g > g_last) break;
         }
         phase ^= 1u;
+    }
+    if (tile_ok) {  // the last staged tile
+        __syncthreads();
+        flush_tile();
+        if (tid == 0) vt_bulk_wait_read<0>();  // shared memory must outlive the engine's reads
     }
     if (P.vec_store && qshift) {  // the values of the last, incomplete quad
         float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -744,7 +806,8 @@ int plan_z4(Z4Params &P, int sms, const float ext_y[], const float ext_x[], Z4Pl
         int bs = 0, bp = 0;
         for (int pi = 0; pi < NPITCH; pi++)
             for (int s = 0; s < N_SHAPES; s++) {
-                const float pen = 0.012f * (float)pi + (s == 2 ? 0.02f : (s == 3 ? 0.06f : 0.0f));
+                // (8x1 patches make a warp store 8 rows x 16 bytes: half sectors, measured ~2x slower stores)
+                const float pen = 0.012f * (float)pi + (s == 2 ? 0.02f : (s == 3 ? 0.30f : 0.0f));
                 const float c = C.wf[(L.bw0 + pi) & 7][s] + pen;
                 if (c < best) {
                     best = c;
@@ -819,6 +882,16 @@ int launch2(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
         rc = vt_encode_tmap_3d(&G.map[pi], d_src4, gdim, gstr, box);
         if (rc) return rc;
     }
+    if (P.tma_store) {
+        // output as a 4-D tensor (x, a1, a0, matrix); the box is what a CTA produces per step for march axis 2
+        const unsigned long long odim[4] = {(unsigned long long)P.o_m, (unsigned long long)P.o_fast, (unsigned long long)P.o_slow,
+                                            (unsigned long long)P.n_mats};
+        const unsigned long long ostr[3] = {(unsigned long long)P.os_fast * 4, (unsigned long long)P.os_slow * 4,
+                                            (unsigned long long)(P.n_mats > 1 ? P.dst_batch_stride : P.os_slow * P.o_slow) * 4};
+        const unsigned obox[4] = {8u, (unsigned)TS, (unsigned)TS, 1u};
+        rc = vt_encode_tmap_nd(&G.omap, P.dst, 4, odim, ostr, obox);
+        if (rc) P.tma_store = 0;  // (strides the engine cannot take: the STG.128 path writes the same values)
+    }
     if (getenv("VT_Z4_DEBUG"))
         fprintf(stderr, "z4 interp %d: box %d x %d, mat0 shape %d pitch +%d, wavefronts %.3f, chunks %d x %d\n", INTERP, L.bw0,
                 L.bh, P.mats[0].shape, P.mats[0].pitch_idx, L.cost, L.chunks, L.m_chunk);
@@ -829,15 +902,15 @@ int launch2(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
     constexpr int RESIDENT = INTERP == VT_CUBIC_TEX ? 2 : 3;
     static const int force_stages = getenv("VT_Z4_STAGES") ? atoi(getenv("VT_Z4_STAGES")) : 0;  // tuning knobs
     static const int force_sync = getenv("VT_Z4_LOOSE") ? atoi(getenv("VT_Z4_LOOSE")) : -1;
-    int nstage = ((size_t)SMEM_HEADER + 4u * (size_t)stage_bytes) * RESIDENT <= (size_t)220 * 1024 ? 4 : 3;
+    int nstage = ((size_t)SMEM_HEADER + 4u * (size_t)stage_bytes + 2 * OTILE_BYTES) * RESIDENT <= (size_t)220 * 1024 ? 4 : 3;
     if (force_stages == 3 || force_stages == 4) nstage = force_stages;
     const bool loose = force_sync >= 0 ? force_sync != 0 : Z4_DEFAULT_LOOSE;
-    const size_t smem = SMEM_HEADER + (size_t)nstage * stage_bytes;
+    const size_t smem = SMEM_HEADER + (size_t)nstage * stage_bytes + (P.tma_store ? 2 * OTILE_BYTES : 0);
     // the attribute is per device and per function: one flag per device (a process may drive several GPUs)
     static std::atomic<bool> attr_set_dev[64];
     std::atomic<bool> &attr_set = attr_set_dev[dev & 63];
     if (!attr_set.load(std::memory_order_acquire)) {
-        const int mx = SMEM_HEADER + 4 * STAGE_BYTES_MAX;
+        const int mx = SMEM_HEADER + 4 * STAGE_BYTES_MAX + 2 * OTILE_BYTES;
 #define VT_Z4_ATTR(Z, N, LS) \
     VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, Z, N, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
         VT_Z4_ATTR(true, 3, false); VT_Z4_ATTR(false, 3, false); VT_Z4_ATTR(true, 4, false); VT_Z4_ATTR(false, 4, false);
@@ -875,6 +948,8 @@ void fill_z4(const VtResampleParams &P, int m, Z4Params &Q, float ext_y[], float
     Q.os_fast = ostr[R.fast];
     Q.os_m = ostr[m];
     Q.o_fast = odim[R.fast];
+    Q.o_slow = odim[R.slow];
+    Q.o_m = odim[m];
     // the C ABI's z-range restricts output axis 0: the march axis for m = 0, the slow tile axis otherwise
     Q.slow_b = m == 0 ? 0 : P.z_begin;
     Q.slow_e = m == 0 ? odim[R.slow] : P.z_end;
@@ -888,6 +963,7 @@ void fill_z4(const VtResampleParams &P, int m, Z4Params &Q, float ext_y[], float
     Q.march = m;
     Q.vec_store = (m == 2 && (P.o2 % 4) == 0 && (P.dst_batch_stride % 4) == 0 && ((uintptr_t)P.dst % 16) == 0 &&
                    !getenv("VT_Z4_NO_VEC")) ? 1 : 0;
+    Q.tma_store = (Q.vec_store && (P.o2 % 8) == 0 && !getenv("VT_Z4_NO_TMA_STORE")) ? 1 : 0;
     Q.tiles_fast = (Q.o_fast + TS - 1) / TS;
     for (int k = 0; k < P.n_mats; k++) {
         const VtMat &M = P.mats[k];

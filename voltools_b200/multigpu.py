@@ -552,12 +552,18 @@ def _scatter_prefilter_exchange(engine, dist, group, src, volume, interpolation,
         raw_slab = engine.empty((xy1 - xy0, d1, d2))
         if xy1 > xy0:
             ops.append(dist.P2POp(dist.irecv, raw_slab, _global_rank(dist, group, src), group))
-    for w in (dist.batch_isend_irecv(ops) if ops else []):
-        w.wait()
-    # 2) every rank prefilters its own slab straight into its place in the full-size buffer
+    works = dist.batch_isend_irecv(ops) if ops else []
+    if rank != src:
+        for w in works:
+            w.wait()
+    # 2) every rank prefilters its own slab straight into its place in the full-size buffer (the root while its sends
+    #    are still leaving: they only read `raw`)
     i0, i1 = split_slabs(d0, world, rank)
     if i1 > i0:
         engine.prefilter_slab(raw_slab, buffer, shape, interpolation, xy0, xy1, i0, i1)
+    if rank == src:
+        for w in works:
+            w.wait()
     del raw_slab
     # 3) pairwise exchange of what each output slab reads from each owner, all pairs in one group
     ops, sends, recvs = [], [], []
