@@ -362,7 +362,10 @@ def run_sweep(args, torch, vt, dev, barrier, reduce_max, with_e2e=True):
     traffic = None
     tfile = ROOT / 'profiles' / 'traffic.json'
     if dom and tfile.exists():
-        traffic = json.loads(tfile.read_text()).get(dom, {}).get('dram_bytes_per_launch')
+        t = json.loads(tfile.read_text()).get(dom, {})
+        # measured per voxel on a 32-matrix launch of the same kernel and shape, scaled to this run's average launch
+        traffic = t['dram_bytes_per_voxel'] * kernels[dom]['voxels_per_launch'] if 'dram_bytes_per_voxel' in t \
+            else t.get('dram_bytes_per_launch')
     roofline = None
     if dom:
         inb = float(np.mean([inbounds_fraction(shape, m) for m in mats[::6]]))

@@ -215,3 +215,51 @@ def test_slice_planner_decisions_without_a_gpu():
     # rows that are not multiples of 16 bytes: per-element cp.async staging, a pitch per matrix in 32..40
     odd = N.slice_plan((40, 50, 61), rot(50, 30), N.LINEAR, src_strides=(61, 50 * 61))
     assert not odd['tma'] and 32 <= odd['pitches'][0] <= 40
+
+
+def test_slice4_planner_decisions_without_a_gpu():
+    """vt_z4_axis_of / vt_z4_plan are host-only: which axis a batch of matrices leaves alone, and the per-matrix
+    quarter-warp shape / pitch class the slice4 family picks from its bank simulation."""
+    import voltools_b200 as vt
+    from voltools_b200 import _native as N
+    shape = (256, 256, 256)
+    c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+    tm = vt.utils.transform_matrix
+    # the march axis: rotations about axis 0 ('rzxz' middle angle), 1 ('ryzy' first angle), 2 ('rzxz' first angle)
+    assert N.z4_axis(shape, shape, tm(rotation=(0, 30, 0), rotation_order='rzxz', center=c), N.CUBIC_TEX) == 0
+    assert N.z4_axis(shape, shape, tm(rotation=(30, 0, 0), rotation_order='ryzy', center=c), N.CUBIC_TEX) == 1
+    assert N.z4_axis(shape, shape, tm(rotation=(25, 0, 0), rotation_order='rzxz', center=c), N.CUBIC_TEX) == 2  # the example's
+    assert N.z4_axis(shape, shape, np.identity(4, dtype=np.float32), N.LINEAR) == 0                             # any: lowest
+    assert N.z4_axis(shape, shape, tm(rotation=(10, 20, 30), center=c), N.LINEAR) == -1
+    assert N.z4_axis(shape, shape, tm(rotation=(0, 30, 0), center=c, translation=(0.5, 0, 0)), N.LINEAR) == -1  # fractional shift
+    assert N.z4_axis(shape, shape, tm(rotation=(0, 30, 0), center=c, translation=(3, 0.5, -2)), N.LINEAR) == 0  # integer shift
+    # a batch must agree on one axis; a batch of more than VT_MAX_BATCH matrices is checked chunk by chunk
+    sweep = [tm(rotation=(0, a, 0), rotation_order='rzxz', center=c) for a in range(180)]
+    assert N.z4_axis(shape, shape, sweep, N.CUBIC_TEX) == 0
+    assert N.z4_axis(shape, shape, sweep + [tm(rotation=(25, 0, 0), rotation_order='rzxz', center=c)], N.CUBIC_TEX) == -1
+    assert N.launch_plan(None, shape, shape, sweep[45], N.CUBIC_TEX) == {'family': 'slice4', 'axis': 0}
+    assert N.launch_plan(None, shape, shape, sweep[45], N.CUBIC_TEX, resident=False, filtered=False)['family'] == 'slice'
+    assert N.launch_plan(None, shape, shape, sweep[45], N.CUBIC_TEX, resident=False, filtered=True)['family'] == 'slice4'
+    # strong minification does not fit the 16 x 16 tile's footprint box: not this family
+    assert N.z4_axis(shape, shape, tm(scale=(1.0, 2.5, 2.5), center=c), N.LINEAR) == -1
+    # the plan: 0 and 90 degrees are conflict free with 1 x 8 patches; 45 degrees is the worst case (~1.4 wavefronts per
+    # quarter-warp load instead of the ~2 of a full warp on the plain layout); box = footprint, at most 7 texels wider
+    for axis, order, rot in ((0, 'rzxz', lambda a: (0, a, 0)), (1, 'ryzy', lambda a: (a, 0, 0)), (2, 'rzxz', lambda a: (a, 0, 0))):
+        for angle in (0, 90):
+            p = N.z4_plan(shape, tm(rotation=rot(angle), rotation_order=order, center=c), N.CUBIC_TEX, axis)
+            assert p['wavefronts'][0] <= 1.01 and p['box_w'] <= 23, (axis, angle, p)
+        p45 = N.z4_plan(shape, tm(rotation=rot(45), rotation_order=order, center=c), N.CUBIC_SIMPLE, axis)
+        assert 1.2 <= p45['wavefronts'][0] <= 1.6 and 26 <= p45['box_w'] <= 28 and p45['box_w'] <= p45['pitches'][0] <= p45['box_w'] + 7
+    ps = N.z4_plan(shape, sweep[:32], N.CUBIC_TEX, 0)
+    assert len(ps['shapes']) == 32 and all(0 <= s <= 3 for s in ps['shapes']) and ps['chunks'] == 1 and ps['m_chunk'] == 256
+    assert N.z4_plan(shape, sweep[:32], N.CUBIC_TEX, 0) == ps                     # deterministic (memoised tables)
+    wf = [w for b in range(0, 180, 32) for w in N.z4_plan(shape, sweep[b:b + 32], N.CUBIC_TEX, 0)['wavefronts']]
+    assert np.mean(wf) <= 1.3 and max(wf) <= 1.8                                  # over the whole sweep
+    # a general matrix is refused
+    assert N.z4_plan(shape, tm(rotation=(10, 20, 30), center=c), N.LINEAR, 0) is None
+    # one large volume alone: the march is cut into chunks so that the grid fills the GPU
+    big = N.z4_plan((512, 512, 512), tm(rotation=(0, 45, 0), center=np.divide(np.subtract((512,) * 3, 1), 2, dtype=np.float32)),
+                    N.CUBIC_TEX, 0)
+    assert big['chunks'] >= 2 and big['m_chunk'] % 4 == 0
+    # sizes of the layout: the march axis rounded up to a multiple of four
+    assert N.z4_bytes((250, 30, 40), 0) == 252 * 30 * 40 * 4 and N.z4_bytes((250, 30, 41), 2) == 250 * 30 * 44 * 4

@@ -349,8 +349,10 @@ int vt_affine_plan(int s0, int s1, int s2, int o0, int o1, int o2, const void *d
     if (!family || !h_mats || n_mats < 1) return VT_ERR_INVALID_ARG;
     VtResampleParams P;
     float dummy;
-    int rc = fill_params(P, (const float *)d_src, s0, s1, s2, s2, (long long)s1 * s2, &dummy, o0, o1, o2, 0, flags, 0, o0);
+    int rc = fill_params(P, d_src ? (const float *)d_src : &dummy, s0, s1, s2, s2, (long long)s1 * s2, &dummy, o0, o1, o2, 0,
+                         flags, 0, o0);
     if (rc) return rc;
+    if (!d_src) P.src = nullptr;  // (only inspected for its alignment: a null pointer counts as aligned)
     copy_mats(P, h_mats, 0, n_mats < VT_MAX_BATCH ? n_mats : VT_MAX_BATCH);
     const int f = choose_family(P, interp, flags);
     if (f < 0) return VT_ERR_UNSUPPORTED;

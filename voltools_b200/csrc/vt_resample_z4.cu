@@ -47,9 +47,8 @@ constexpr int NT = TS * TS;   // threads per CTA, one column each
 constexpr int BH_MAX = 32;    // max footprint rows (texels)
 constexpr int BW_MAX = 40;    // max box width (texels): footprint <= 33 + 7 pitch classes
 constexpr int STAGE_BYTES_MAX = BH_MAX * BW_MAX * 16;  // one ring stage: a footprint of four planes (<= 20 KB)
-constexpr int SMEM_HEADER = 128;  // "full" mbarriers at 0, "empty" mbarriers at 32, refill counters at 64
+constexpr int SMEM_HEADER = 128;  // the ring stages' "full" mbarriers
 constexpr int NPITCH = 8;     // tensor maps per launch: box widths bw0 .. bw0+7 (pitch mod 8 is what matters)
-constexpr bool Z4_DEFAULT_LOOSE = false;  // ring without a block-wide barrier: measured SLOWER
 constexpr int N_SHAPES = 4;   // quarter-warp shapes 1x8, 2x4, 4x2, 8x1 (rows x columns of the tile)
 
 struct Z4Mat {
@@ -72,6 +71,7 @@ struct Z4Params {
     int prod_on_fast;                  // which in-plane index the recipe multiplies first (see z4_coord)
     int bw0, bh;                       // box width of map 0 (map k: bw0 + k) and box height, texels
     int tiles_fast;
+    int tsy;                           // rows of a tile: 16 (256-thread CTAs) or 8 (128-thread CTAs)
     int march;                         // the march axis (0..2): selects the slots of the texture-weight rule
     int vec_store;                     // march axis contiguous in the output and 16-byte alignable: STG.128 quads
     int tma_store;                     // ... and staged through shared memory + cp.async.bulk.tensor stores (UTMASTG)
@@ -82,7 +82,7 @@ struct Z4Maps {
     CUtensorMap map[NPITCH];
     CUtensorMap omap;  // output tensor (x, a1, a0, matrix) with an 8 x 16 x 16 x 1 box: the TMA store path of march axis 2
 };
-constexpr int OTILE_BYTES = TS * TS * 32;  // one staged output tile: two 16-byte quads (a whole 32-byte sector) per column
+constexpr int OTILE_BYTES = TS * TS * 32;  // one staged output tile (16-row tiles): two 16-byte quads = a 32-byte sector per column
 
 // The reference's coordinate recipe (voltools/transforms.py:264-274 as compiled: t = a1*M1; t = fma(a0,M0,t);
 // t = fma(a2,M2,t); t = M3 + t; p = t + 0.5) for a source row whose coefficient of the march index is zero: that term
@@ -325,21 +325,19 @@ struct Taps4<VT_CUBIC_TEX> {
 
 __host__ __device__ __forceinline__ int floordiv4(int v) { return v >> 2; }  // arithmetic shift: floor for negatives
 
-__device__ __forceinline__ unsigned atom_inc_shared(unsigned addr)
+// One block-wide barrier per step: everyone is done with the stage consumed in the previous step, thread 0 refills it.
+// (A ring without the barrier -- every warp waits on the stage's "full" mbarrier, arrives on an "empty" one, and the
+// last warp out of a stage refills it -- was built and measured SLOWER: cubic_tex 219 vs 264, cubic_simple 279 vs 300
+// Gvox/s at 256^3; the elected-lane bookkeeping of every warp and step costs more than the barrier it removes.)
+// TSY: rows of the tile (16 or 8).  8-row tiles = 128-thread CTAs, twice as many per SM: the same number of warps, but
+// barriers that tie 4 warps instead of 8 and CTAs that drift apart more (knob VT_Z4_TSY, measured in DESIGN.md).
+template <int INTERP>
+__host__ __device__ constexpr int z4_resident(int tsy)
 {
-    unsigned old;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
-    return old;
+    return (INTERP == VT_CUBIC_TEX ? 2 : 3) * (TS / tsy);
 }
-
-// LOOSE = false: one block-wide barrier per step (everyone is done with the previous stage -> thread 0 refills it).
-// LOOSE = true:  no block-wide barrier in the march.  Every warp waits for its stage on the "full" mbarrier, arrives on
-//                the stage's "empty" mbarrier when it has read it and bumps a counter; the warp whose bump is the
-//                eighth -- the LAST one to finish the stage -- refills it.  Nobody ever blocks on "empty" (the refiller's
-//                wait on it returns at once: it only orders the refill after the other warps' reads), so warps drift up
-//                to NSTAGE - 1 stages apart instead of meeting every step.
-template <int INTERP, int RULE, bool OOB_ZERO, int NSTAGE, bool LOOSE>
-__global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
+template <int INTERP, int RULE, bool OOB_ZERO, int NSTAGE, int TSY>
+__global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
     vt_z4_kernel(const __grid_constant__ Z4Params P, const __grid_constant__ Z4Maps G, int m_chunk, unsigned stage_bytes)
 {
     // [SMEM_HEADER: mbarriers, counters][NSTAGE stages of stage_bytes]
@@ -356,8 +354,8 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
     const int pof = P.prod_on_fast;
     const int zc0 = P.m_b + blockIdx.y * m_chunk;
     const int zc1 = min(zc0 + m_chunk, P.m_e);
-    const int as0 = P.slow_b + tile_y * TS, af0 = tile_x * TS;
-    const int as1 = min(as0 + TS, P.slow_e) - 1, af1 = min(af0 + TS, P.o_fast) - 1;
+    const int as0 = P.slow_b + tile_y * TSY, af0 = tile_x * TS;
+    const int as1 = min(as0 + TSY, P.slow_e) - 1, af1 = min(af0 + TS, P.o_fast) - 1;
 
     // footprint of the tile: extremes are at the corners (the float recipe is monotone in either index)
     float y_min, y_max, x_min, x_max;
@@ -383,11 +381,7 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
     if (tid == 0) {
         vt_tma_prefetch_desc(&G.map[pidx]);
 #pragma unroll
-        for (int i = 0; i < NSTAGE; i++) {
-            vt_mbar_init(bars_s + 8u * i, 1);
-            vt_mbar_init(bars_s + 32u + 8u * i, NT / 32);  // one arrival per warp
-            ((unsigned *)(smem_raw + 64))[i] = 0u;
-        }
+        for (int i = 0; i < NSTAGE; i++) vt_mbar_init(bars_s + 8u * i, 1);
         vt_mbar_fence_init();
     }
     __syncthreads();
@@ -415,7 +409,7 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
         // groups / rows / columns outside the source arrive as zeros (= the texture's border mode)
         vt_tma_load_3d(ring_s + st * stage_bytes, &G.map[pidx], bar, 4 * xlo, ylo, gg);
     };
-    constexpr int AHEAD = LOOSE ? NSTAGE : NSTAGE - 1;  // groups in flight after the prologue
+    constexpr int AHEAD = NSTAGE - 1;  // groups in flight after the prologue
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < AHEAD; i++)
@@ -473,9 +467,9 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
     // in-plane); two tiles alternate.
     const unsigned otile_s = ring_s + NSTAGE * stage_bytes;
     bool tile_ok = false;
-    if (!LOOSE && P.tma_store) {
+    if (P.tma_store) {
         const bool mine = OOB_ZERO ? true : (inplane || !live);
-        tile_ok = __syncthreads_and(mine ? 1 : 0) != 0 && as0 + TS <= P.slow_e;
+        tile_ok = __syncthreads_and(mine ? 1 : 0) != 0 && as0 + TSY <= P.slow_e;
     }
     int pending_zq = 0, pending_buf = -1, obuf = 0;  // a tile completed in the previous step, not yet handed over
     bool half = false;                                // the even quad of the current tile is in place
@@ -493,12 +487,10 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
         constexpr unsigned FILL = (CUR + NSTAGE - 1) % NSTAGE;
         const unsigned ring = ring_s + CUR * stage_bytes;
         vt_mbar_wait(bars_s + 8u * CUR, phase);
-        if constexpr (!LOOSE) {
-            if (tile_ok && tid == 0) vt_bulk_wait_read<1>();  // the tile this step may overwrite has been read
-            __syncthreads();  // everyone is done with the stage consumed in the previous step: refill it
-            if (tid == 0 && gg + NSTAGE - 1 <= g_last) load_group(gg + NSTAGE - 1, FILL);
-            if (tile_ok) flush_tile();
-        }
+        if (tile_ok && tid == 0) vt_bulk_wait_read<1>();  // the tile this step may overwrite has been read
+        __syncthreads();  // everyone is done with the stage consumed in the previous step: refill it
+        if (tid == 0 && gg + NSTAGE - 1 <= g_last) load_group(gg + NSTAGE - 1, FILL);
+        if (tile_ok) flush_tile();
         float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (inplane) {
             if constexpr (INTERP == VT_LINEAR) {
@@ -522,18 +514,6 @@ __global__ void __launch_bounds__(NT, INTERP == VT_CUBIC_TEX ? 2 : 3)
                     s3 = s2;
                     s2 = qa[p];
                     s1 = qb[p];
-                }
-            }
-        }
-        if constexpr (LOOSE) {
-            // this warp is done reading stage CUR (its loads have landed in registers: the sums above depend on them)
-            __syncwarp();
-            if ((tid & 31) == 0) {
-                vt_mbar_arrive(bars_s + 32u + 8u * CUR);
-                const unsigned old = atom_inc_shared(bars_s + 64u + 4u * CUR);
-                if ((old & (NT / 32 - 1)) == NT / 32 - 1 && gg + NSTAGE <= g_last) {  // the last warp out refills
-                    vt_mbar_wait(bars_s + 32u + 8u * CUR, phase);
-                    load_group(gg + NSTAGE, CUR);
                 }
             }
         }
@@ -709,14 +689,14 @@ static inline int z4_origin(float cs, float cf, float cc, int as, int af)
 {
     return (int)floor((double)cc + (double)as * cs + (double)af * cf);  // floor(p - 0.5), p = ... + 0.5
 }
-const Z4Conflicts &z4_conflicts(const Z4Mat &M, int pof)
+const Z4Conflicts &z4_conflicts(const Z4Mat &M, int pof, int tsy)
 {
     constexpr int MEMO = 2048, WAYS = 4;
     static thread_local Z4Conflicts memo[MEMO];
     static thread_local unsigned victim = 0;
-    const float key[8] = {M.ys, M.yf, M.yc, M.xs, M.xf, M.xc, (float)pof, 1.0f};
+    const float key[8] = {M.ys, M.yf, M.yc, M.xs, M.xf, M.xc, (float)pof, (float)tsy};
     unsigned h = 2166136261u;
-    for (int i = 0; i < 7; i++) {
+    for (int i = 0; i < 8; i++) {
         unsigned u;
         memcpy(&u, &key[i], 4);
         h = (h ^ u) * 16777619u;
@@ -745,7 +725,7 @@ const Z4Conflicts &z4_conflicts(const Z4Mat &M, int pof)
             }
         for (int s = 0; s < N_SHAPES; s++)
             for (int qi = 0; qi < NQ; qi++) {
-                const int q = (5 * qi + 1 + smp) & (NT / 8 - 1);  // a sample of the tile's 32 quarter warps
+                const int q = (5 * qi + 1 + smp) & (2 * tsy - 1);  // a sample of the tile's quarter warps
                 int yy[8], xx[8], n = 0;
                 for (int l = 0; l < 8; l++) {
                     int ty, tx;
@@ -801,7 +781,7 @@ int plan_z4(Z4Params &P, int sms, const float ext_y[], const float ext_x[], Z4Pl
     const char *force_s = getenv("VT_Z4_SHAPE"), *force_p = getenv("VT_Z4_PITCH");  // tuning knobs
     float total = 0.0f;
     for (int k = 0; k < P.n_mats; k++) {
-        const Z4Conflicts &C = z4_conflicts(P.mats[k], P.prod_on_fast);
+        const Z4Conflicts &C = z4_conflicts(P.mats[k], P.prod_on_fast, P.tsy);
         float best = 1e30f;
         int bs = 0, bp = 0;
         for (int pi = 0; pi < NPITCH; pi++)
@@ -826,9 +806,9 @@ int plan_z4(Z4Params &P, int sms, const float ext_y[], const float ext_x[], Z4Pl
     // waves of (SMs x resident CTAs).  Long marches over large planes lose the L2 reuse between neighbouring tiles
     // (see vt_resample_slice.cu): cap a march at 2 GB of source planes.
     const int nm = P.m_e - P.m_b;
-    const int tiles = ((P.slow_e - P.slow_b + TS - 1) / TS) * P.tiles_fast;
+    const int tiles = ((P.slow_e - P.slow_b + P.tsy - 1) / P.tsy) * P.tiles_fast;
     constexpr int WARM = T::BEFORE + T::AFTER + 3;  // + up to 3 planes of group misalignment
-    constexpr int RESIDENT = INTERP == VT_CUBIC_TEX ? 2 : 3;
+    const int RESIDENT = z4_resident<INTERP>(P.tsy);
     constexpr int STARTUP = 12;
     const long long slots = (long long)sms * RESIDENT, per_chunk = (long long)tiles * P.n_mats;
     const long long plane_bytes = (long long)P.s_y * P.s_x * 4;
@@ -860,8 +840,8 @@ int plan_z4(Z4Params &P, int sms, const float ext_y[], const float ext_x[], Z4Pl
     return VT_OK;
 }
 
-template <int INTERP, int RULE>
-int launch2(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[], const float ext_x[], cudaStream_t st)
+template <int INTERP, int RULE, int TSY>
+int launch3(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[], const float ext_x[], cudaStream_t st)
 {
     int sms = 148, dev = 0;
     VT_CUDA(cudaGetDevice(&dev));
@@ -888,45 +868,41 @@ int launch2(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
                                             (unsigned long long)P.n_mats};
         const unsigned long long ostr[3] = {(unsigned long long)P.os_fast * 4, (unsigned long long)P.os_slow * 4,
                                             (unsigned long long)(P.n_mats > 1 ? P.dst_batch_stride : P.os_slow * P.o_slow) * 4};
-        const unsigned obox[4] = {8u, (unsigned)TS, (unsigned)TS, 1u};
+        const unsigned obox[4] = {8u, (unsigned)TS, (unsigned)TSY, 1u};
         rc = vt_encode_tmap_nd(&G.omap, P.dst, 4, odim, ostr, obox);
         if (rc) P.tma_store = 0;  // (strides the engine cannot take: the STG.128 path writes the same values)
     }
     if (getenv("VT_Z4_DEBUG"))
         fprintf(stderr, "z4 interp %d: box %d x %d, mat0 shape %d pitch +%d, wavefronts %.3f, chunks %d x %d\n", INTERP, L.bw0,
                 L.bh, P.mats[0].shape, P.mats[0].pitch_idx, L.cost, L.chunks, L.m_chunk);
-    const int tiles = ((P.slow_e - P.slow_b + TS - 1) / TS) * P.tiles_fast;
+    const int tiles = ((P.slow_e - P.slow_b + TSY - 1) / TSY) * P.tiles_fast;
     dim3 grid(tiles, L.chunks, P.n_mats);
     // ring: stages sized for this launch's box; four stages when the resident CTAs still fit, else three
     const unsigned stage_bytes = ((unsigned)(16 * (L.bw0 + NPITCH - 1) * L.bh) + 127u) & ~127u;
-    constexpr int RESIDENT = INTERP == VT_CUBIC_TEX ? 2 : 3;
-    static const int force_stages = getenv("VT_Z4_STAGES") ? atoi(getenv("VT_Z4_STAGES")) : 0;  // tuning knobs
-    static const int force_sync = getenv("VT_Z4_LOOSE") ? atoi(getenv("VT_Z4_LOOSE")) : -1;
-    int nstage = ((size_t)SMEM_HEADER + 4u * (size_t)stage_bytes + 2 * OTILE_BYTES) * RESIDENT <= (size_t)220 * 1024 ? 4 : 3;
+    constexpr int RESIDENT = z4_resident<INTERP>(TSY);
+    static const int force_stages = getenv("VT_Z4_STAGES") ? atoi(getenv("VT_Z4_STAGES")) : 0;  // tuning knob
+    const size_t otile = P.tma_store ? 2 * OTILE_BYTES : 0;
+    int nstage = ((size_t)SMEM_HEADER + 4u * (size_t)stage_bytes + otile) * RESIDENT <= (size_t)220 * 1024 ? 4 : 3;
     if (force_stages == 3 || force_stages == 4) nstage = force_stages;
-    const bool loose = force_sync >= 0 ? force_sync != 0 : Z4_DEFAULT_LOOSE;
-    const size_t smem = SMEM_HEADER + (size_t)nstage * stage_bytes + (P.tma_store ? 2 * OTILE_BYTES : 0);
+    const size_t smem = SMEM_HEADER + (size_t)nstage * stage_bytes + otile;
     // the attribute is per device and per function: one flag per device (a process may drive several GPUs)
     static std::atomic<bool> attr_set_dev[64];
     std::atomic<bool> &attr_set = attr_set_dev[dev & 63];
     if (!attr_set.load(std::memory_order_acquire)) {
         const int mx = SMEM_HEADER + 4 * STAGE_BYTES_MAX + 2 * OTILE_BYTES;
-#define VT_Z4_ATTR(Z, N, LS) \
-    VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, Z, N, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
-        VT_Z4_ATTR(true, 3, false); VT_Z4_ATTR(false, 3, false); VT_Z4_ATTR(true, 4, false); VT_Z4_ATTR(false, 4, false);
-        VT_Z4_ATTR(true, 3, true); VT_Z4_ATTR(false, 3, true); VT_Z4_ATTR(true, 4, true); VT_Z4_ATTR(false, 4, true);
+#define VT_Z4_ATTR(Z, N) \
+    VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, Z, N, TSY>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
+        VT_Z4_ATTR(true, 3); VT_Z4_ATTR(false, 3); VT_Z4_ATTR(true, 4); VT_Z4_ATTR(false, 4);
 #undef VT_Z4_ATTR
         attr_set.store(true, std::memory_order_release);
     }
     {
         VtProf prof(VT_K_Z4_LINEAR + INTERP, st);
-#define VT_Z4_GO(Z, N, LS) vt_z4_kernel<INTERP, RULE, Z, N, LS><<<grid, NT, smem, st>>>(P, G, L.m_chunk, stage_bytes)
+#define VT_Z4_GO(Z, N) vt_z4_kernel<INTERP, RULE, Z, N, TSY><<<grid, TS * TSY, smem, st>>>(P, G, L.m_chunk, stage_bytes)
         if (oob_zero) {
-            if (nstage == 4) { if (loose) VT_Z4_GO(true, 4, true); else VT_Z4_GO(true, 4, false); }
-            else { if (loose) VT_Z4_GO(true, 3, true); else VT_Z4_GO(true, 3, false); }
+            if (nstage == 4) VT_Z4_GO(true, 4); else VT_Z4_GO(true, 3);
         } else {
-            if (nstage == 4) { if (loose) VT_Z4_GO(false, 4, true); else VT_Z4_GO(false, 4, false); }
-            else { if (loose) VT_Z4_GO(false, 3, true); else VT_Z4_GO(false, 3, false); }
+            if (nstage == 4) VT_Z4_GO(false, 4); else VT_Z4_GO(false, 3);
         }
 #undef VT_Z4_GO
     }
@@ -935,8 +911,25 @@ int launch2(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
     return VT_OK;
 }
 
+template <int INTERP, int RULE>
+int launch2(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[], const float ext_x[], cudaStream_t st)
+{
+    if (P.tsy == 8) return launch3<INTERP, RULE, 8>(P, d_src4, oob_zero, ext_y, ext_x, st);
+    return launch3<INTERP, RULE, 16>(P, d_src4, oob_zero, ext_y, ext_x, st);
+}
+
+// rows of a tile for this interpolator (knob VT_Z4_TSY = 8 / 16)
+int z4_tile_rows(int interp)
+{
+    static const int force = getenv("VT_Z4_TSY") ? atoi(getenv("VT_Z4_TSY")) : 0;
+    if (force == 8 || force == 16) return force;
+    // measured (profiles/r02g_z4_tile_rows.log): 8-row tiles +4-5 % for the cubic kernels (sweep 343 vs 329 Gvox/s), the
+    // linear kernel, bound by L2 -> shared traffic, loses 2-4 % to the larger footprint overlap
+    return interp == VT_LINEAR ? 16 : 8;
+}
+
 // VtResampleParams (logical source dims, output, z-range, matrices) -> Z4Params for march axis m
-void fill_z4(const VtResampleParams &P, int m, Z4Params &Q, float ext_y[], float ext_x[])
+void fill_z4(const VtResampleParams &P, int m, int interp, Z4Params &Q, float ext_y[], float ext_x[])
 {
     const AxisRoles R = roles(m);
     const int sdim[3] = {P.s0, P.s1, P.s2}, odim[3] = {P.o0, P.o1, P.o2};
@@ -965,14 +958,15 @@ void fill_z4(const VtResampleParams &P, int m, Z4Params &Q, float ext_y[], float
                    !getenv("VT_Z4_NO_VEC")) ? 1 : 0;
     Q.tma_store = (Q.vec_store && (P.o2 % 8) == 0 && !getenv("VT_Z4_NO_TMA_STORE")) ? 1 : 0;
     Q.tiles_fast = (Q.o_fast + TS - 1) / TS;
+    Q.tsy = z4_tile_rows(interp);
     for (int k = 0; k < P.n_mats; k++) {
         const VtMat &M = P.mats[k];
         Z4Mat &Z = Q.mats[k];
         Z.ys = M.r[R.ay][R.slow]; Z.yf = M.r[R.ay][R.fast]; Z.yc = M.r[R.ay][3];
         Z.xs = M.r[R.ax][R.slow]; Z.xf = M.r[R.ax][R.fast]; Z.xc = M.r[R.ax][3];
         Z.tm = (int)M.r[m][3];
-        ext_y[k] = (fabsf(Z.ys) + fabsf(Z.yf)) * (float)(TS - 1);
-        ext_x[k] = (fabsf(Z.xs) + fabsf(Z.xf)) * (float)(TS - 1);
+        ext_y[k] = fabsf(Z.ys) * (float)(Q.tsy - 1) + fabsf(Z.yf) * (float)(TS - 1);
+        ext_x[k] = fabsf(Z.xs) * (float)(Q.tsy - 1) + fabsf(Z.xf) * (float)(TS - 1);
     }
 }
 
@@ -981,7 +975,7 @@ int launch1(const VtResampleParams &P, const float *d_src4, int m, cudaStream_t 
 {
     Z4Params Q;
     float ext_y[VT_MAX_BATCH], ext_x[VT_MAX_BATCH];
-    fill_z4(P, m, Q, ext_y, ext_x);
+    fill_z4(P, m, INTERP, Q, ext_y, ext_x);
     const bool zero = (P.flags & VT_OOB_ZERO) != 0;
     if (INTERP != VT_CUBIC_SIMPLE && (P.flags & VT_WEIGHTS_EXACT)) return launch2<INTERP, 2>(Q, d_src4, zero, ext_y, ext_x, st);
     return launch2<INTERP, 0>(Q, d_src4, zero, ext_y, ext_x, st);
@@ -1046,7 +1040,7 @@ int vt_z4_plan_impl(const VtResampleParams &P, int axis, int interp, int sms, in
 {
     Z4Params Q;
     float ext_y[VT_MAX_BATCH], ext_x[VT_MAX_BATCH];
-    fill_z4(P, axis, Q, ext_y, ext_x);
+    fill_z4(P, axis, interp, Q, ext_y, ext_x);
     Z4Plan L;
     int rc;
     switch (interp) {
@@ -1063,7 +1057,7 @@ int vt_z4_plan_impl(const VtResampleParams &P, int axis, int interp, int sms, in
     for (int k = 0; k < P.n_mats; k++) {
         if (shapes) shapes[k] = Q.mats[k].shape;
         if (pitches) pitches[k] = L.bw0 + Q.mats[k].pitch_idx;
-        if (wavefronts) wavefronts[k] = z4_conflicts(Q.mats[k], Q.prod_on_fast).wf[(L.bw0 + Q.mats[k].pitch_idx) & 7][Q.mats[k].shape];
+        if (wavefronts) wavefronts[k] = z4_conflicts(Q.mats[k], Q.prod_on_fast, Q.tsy).wf[(L.bw0 + Q.mats[k].pitch_idx) & 7][Q.mats[k].shape];
     }
     return VT_OK;
 }
