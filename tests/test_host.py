@@ -249,7 +249,8 @@ def test_slice4_planner_decisions_without_a_gpu():
             p = N.z4_plan(shape, tm(rotation=rot(angle), rotation_order=order, center=c), N.CUBIC_TEX, axis)
             assert p['wavefronts'][0] <= 1.01 and p['box_w'] <= 23, (axis, angle, p)
         p45 = N.z4_plan(shape, tm(rotation=rot(45), rotation_order=order, center=c), N.CUBIC_SIMPLE, axis)
-        assert 1.2 <= p45['wavefronts'][0] <= 1.6 and 26 <= p45['box_w'] <= 28 and p45['box_w'] <= p45['pitches'][0] <= p45['box_w'] + 7
+        # (cubic kernels: 8-row tiles, footprint 0.707 * (7 + 15) + 6 = 21 texels; 16-row tiles: 27)
+        assert 1.2 <= p45['wavefronts'][0] <= 1.6 and 21 <= p45['box_w'] <= 28 and p45['box_w'] <= p45['pitches'][0] <= p45['box_w'] + 7
     ps = N.z4_plan(shape, sweep[:32], N.CUBIC_TEX, 0)
     assert len(ps['shapes']) == 32 and all(0 <= s <= 3 for s in ps['shapes']) and ps['chunks'] == 1 and ps['m_chunk'] == 256
     assert N.z4_plan(shape, sweep[:32], N.CUBIC_TEX, 0) == ps                     # deterministic (memoised tables)
