@@ -328,11 +328,19 @@ def run_sweep(args, torch, vt, dev, barrier, reduce_max, with_e2e=True):
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
+    # nvidia-smi (100 ms period) needs samples under this load: ~0.6 s of steps before the timed region.  The step holds a
+    # collective, so EVERY rank must run the same number of them: the count comes from a max-reduced time, never from a
+    # rank's own clock.
+    barrier()
+    t_probe = time.perf_counter()
+    step()
+    torch.cuda.synchronize()
+    step_s = reduce_max(time.perf_counter() - t_probe)
+    n_load = int(min(200, max(2, 0.6 / max(step_s, 1e-4))))
     clocks = clock_sampler(torch, dev)
-    t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.6:  # nvidia-smi (100 ms period) needs samples under this load
+    for _ in range(n_load):
         step()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
     l0 = _native.launch_count()
     sec = reduce_max(timed(torch, step, args.steps, 0, barrier))
     launches = _native.launch_count() - l0
@@ -658,7 +666,9 @@ def main():
     torch.cuda.set_device(dev)
     import torch.distributed as dist
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{dev}'))
+        import datetime
+        # (a mismatched collective must fail in minutes, not hold N GPUs for the watchdog's default 10)
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{dev}'), timeout=datetime.timedelta(seconds=180))
 
         def barrier():
             dist.barrier()

@@ -1,4 +1,5 @@
 """Compile voltools_b200/csrc/*.cu into voltools_b200/libvoltools_b200.so for sm_100a (in-tree)."""
+import os
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -16,7 +17,8 @@ def _compile(src, verbose):
     deps = [src, HERE / 'vt_common.cuh', PKG.parent / 'include' / 'voltools_b200.h']
     if obj.exists() and all(obj.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return obj, ''
-    r = subprocess.run(['nvcc', *NVCC_FLAGS, '-c', '-o', str(obj), str(src)], capture_output=True, text=True)
+    extra = os.environ.get('VT_NVCC_EXTRA', '').split()  # tuning experiments: extra -D flags
+    r = subprocess.run(['nvcc', *NVCC_FLAGS, *extra, '-c', '-o', str(obj), str(src)], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'nvcc failed on {src.name}:\n{r.stdout}\n{r.stderr}')
     return obj, r.stderr

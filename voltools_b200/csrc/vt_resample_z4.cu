@@ -331,10 +331,13 @@ __host__ __device__ __forceinline__ int floordiv4(int v) { return v >> 2; }  // 
 // Gvox/s at 256^3; the elected-lane bookkeeping of every warp and step costs more than the barrier it removes.)
 // TSY: rows of the tile (16 or 8).  8-row tiles = 128-thread CTAs, twice as many per SM: the same number of warps, but
 // barriers that tie 4 warps instead of 8 and CTAs that drift apart more (knob VT_Z4_TSY, measured in DESIGN.md).
+#ifndef VT_Z4_CT8_RESIDENT
+#define VT_Z4_CT8_RESIDENT 4  // resident 128-thread CTAs per SM the cubic_tex kernel is compiled for (register cap 65536 / 128 / N)
+#endif
 template <int INTERP>
 __host__ __device__ constexpr int z4_resident(int tsy)
 {
-    return (INTERP == VT_CUBIC_TEX ? 2 : 3) * (TS / tsy);
+    return INTERP == VT_CUBIC_TEX ? (tsy == 8 ? VT_Z4_CT8_RESIDENT : 2) : 3 * (TS / tsy);
 }
 template <int INTERP, int RULE, bool OOB_ZERO, int NSTAGE, int TSY>
 __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
