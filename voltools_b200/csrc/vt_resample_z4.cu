@@ -339,7 +339,8 @@ __host__ __device__ constexpr int z4_resident(int tsy)
 {
     return INTERP == VT_CUBIC_TEX ? (tsy == 8 ? VT_Z4_CT8_RESIDENT : 2) : 3 * (TS / tsy);
 }
-template <int INTERP, int RULE, bool OOB_ZERO, int NSTAGE, int TSY>
+// VEC: the march axis is the contiguous output axis (march 2): quads + TMA stores (compiled out otherwise).
+template <int INTERP, int RULE, bool OOB_ZERO, int NSTAGE, int TSY, bool VEC>
 __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
     vt_z4_kernel(const __grid_constant__ Z4Params P, const __grid_constant__ Z4Maps G, int m_chunk, unsigned stage_bytes)
 {
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
     // in-plane); two tiles alternate.
     const unsigned otile_s = ring_s + NSTAGE * stage_bytes;
     bool tile_ok = false;
-    if (P.tma_store) {
+    if (VEC && P.tma_store) {
         const bool mine = OOB_ZERO ? true : (inplane || !live);
         tile_ok = __syncthreads_and(mine ? 1 : 0) != 0 && as0 + TSY <= P.slow_e;
     }
@@ -490,10 +491,10 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
         constexpr unsigned FILL = (CUR + NSTAGE - 1) % NSTAGE;
         const unsigned ring = ring_s + CUR * stage_bytes;
         vt_mbar_wait(bars_s + 8u * CUR, phase);
-        if (tile_ok && tid == 0) vt_bulk_wait_read<1>();  // the tile this step may overwrite has been read
+        if (VEC && tile_ok && tid == 0) vt_bulk_wait_read<1>();  // the tile this step may overwrite has been read
         __syncthreads();  // everyone is done with the stage consumed in the previous step: refill it
         if (tid == 0 && gg + NSTAGE - 1 <= g_last) load_group(gg + NSTAGE - 1, FILL);
-        if (tile_ok) flush_tile();
+        if (VEC && tile_ok) flush_tile();
         float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (inplane) {
             if constexpr (INTERP == VT_LINEAR) {
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
                 }
             }
         }
-        if (P.vec_store) {
+        if constexpr (VEC) {
             // The march axis is the contiguous output axis (march 2): a thread's four values are neighbours in memory.
             // Re-cut them into 16-byte aligned quads -- `qa` values of a quad come from the previous step -- and store
             // each quad with one STG.128 (elements outside the chunk / the source fall back to scalar stores).
@@ -605,12 +606,12 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
         }
         phase ^= 1u;
     }
-    if (tile_ok) {  // the last staged tile
+    if (VEC && tile_ok) {  // the last staged tile
         __syncthreads();
         flush_tile();
         if (tid == 0) vt_bulk_wait_read<0>();  // shared memory must outlive the engine's reads
     }
-    if (P.vec_store && qshift) {  // the values of the last, incomplete quad
+    if (VEC && qshift) {  // the values of the last, incomplete quad
         float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         switch (qshift) {  // uniform
             case 1: v[0] = prev[3]; break;
@@ -894,14 +895,19 @@ int launch3(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
     if (!attr_set.load(std::memory_order_acquire)) {
         const int mx = SMEM_HEADER + 4 * STAGE_BYTES_MAX + 2 * OTILE_BYTES;
 #define VT_Z4_ATTR(Z, N) \
-    VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, Z, N, TSY>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
+    VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, Z, N, TSY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)); \
+    VT_CUDA(cudaFuncSetAttribute(vt_z4_kernel<INTERP, RULE, Z, N, TSY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
         VT_Z4_ATTR(true, 3); VT_Z4_ATTR(false, 3); VT_Z4_ATTR(true, 4); VT_Z4_ATTR(false, 4);
 #undef VT_Z4_ATTR
         attr_set.store(true, std::memory_order_release);
     }
     {
         VtProf prof(VT_K_Z4_LINEAR + INTERP, st);
-#define VT_Z4_GO(Z, N) vt_z4_kernel<INTERP, RULE, Z, N, TSY><<<grid, TS * TSY, smem, st>>>(P, G, L.m_chunk, stage_bytes)
+#define VT_Z4_GO(Z, N)                                                                                        \
+    do {                                                                                                      \
+        if (P.vec_store) vt_z4_kernel<INTERP, RULE, Z, N, TSY, true><<<grid, TS * TSY, smem, st>>>(P, G, L.m_chunk, stage_bytes); \
+        else vt_z4_kernel<INTERP, RULE, Z, N, TSY, false><<<grid, TS * TSY, smem, st>>>(P, G, L.m_chunk, stage_bytes);           \
+    } while (0)
         if (oob_zero) {
             if (nstage == 4) VT_Z4_GO(true, 4); else VT_Z4_GO(true, 3);
         } else {
