@@ -424,19 +424,17 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
     if (inplane) taps.template init<RULE>(py, px, ylo, xlo, pitch, P.march);
     float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // sliding window of per-plane sums
     unsigned phase = 0;
-    // Output addressing in 32-bit element offsets from the matrix's output volume (the host admits output volumes of
-    // (o0 + 8) * o1 * o2 < 2^31 voxels to this family): one IMAD.WIDE per store instead of 64-bit pointer chains rebuilt from the parameter bank.
-    float *const mbase = P.dst + (size_t)mat * P.dst_batch_stride;
-    const int osm = (int)P.os_m;
-    // offset of this column at the output plane that input plane 4g is the LAST tap plane of (may start below zero)
-    int doff = a_s * (int)P.os_slow + a_f * (int)P.os_fast + (4 * g - T::AFTER - tm) * osm;
+    const long long osm = P.os_m;
+    // output pointer of this column at the output plane that input plane 4g is the LAST tap plane of
+    float *dstp = P.dst + (size_t)mat * P.dst_batch_stride + (long long)a_s * P.os_slow + (long long)a_f * P.os_fast +
+                  (long long)(4 * g - T::AFTER - tm) * P.os_m;
 
     // vector-store path (march axis = contiguous output axis)
     float prev[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     // a step's first output index is 4*gg - AFTER - tm: how many values of an aligned output quad come from the
     // previous step
     const int qshift = (4 - ((T::AFTER + tm) & 3)) & 3;
-    float *const dcol = mbase + (long long)(a_s * (int)P.os_slow + a_f * (int)P.os_fast);
+    float *const dcol = P.dst + (size_t)mat * P.dst_batch_stride + (long long)a_s * P.os_slow + (long long)a_f * P.os_fast;
     auto emit_quad = [&](int zq, const float (&v)[4]) {  // outputs zq .. zq+3 (zq a multiple of 4) of this column
         const bool all_in = zq >= zc0 && zq + 3 < zc1;                             // uniform
         const bool all_src = zq + tm >= 0 && zq + 3 + tm < P.s_m;                 // uniform
@@ -571,8 +569,12 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
             // (r[] is zero for columns outside the source in-plane)
             if (zo0 >= zc0 && zo0 + 3 < zc1 && zi0 >= 0 && zi0 + 3 < P.s_m) {  // uniform: a step in the interior
                 if (OOB_ZERO ? live : inplane) {
+                    float *d = dstp;
 #pragma unroll
-                    for (int p = 0; p < 4; p++) mbase[doff + p * osm] = r[p];
+                    for (int p = 0; p < 4; p++) {
+                        *d = r[p];
+                        d += osm;
+                    }
                 }
             } else {
 #pragma unroll
@@ -581,15 +583,15 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
                     if (zo >= zc0 && zo < zc1) {  // uniform: past the warm-up planes, inside the chunk
                         const bool ok = inplane && (unsigned)zi < (unsigned)P.s_m;  // 0 <= p_m < s_m with p_m = zi + 0.5
                         if (OOB_ZERO) {
-                            if (live) mbase[doff + p * osm] = ok ? r[p] : 0.0f;
+                            if (live) dstp[(long long)p * osm] = ok ? r[p] : 0.0f;
                         } else if (ok) {
-                            mbase[doff + p * osm] = r[p];
+                            dstp[(long long)p * osm] = r[p];
                         }
                     }
                 }
             }
         }
-        doff += 4 * osm;
+        dstp += 4 * osm;
     };
     for (;;) {
         stage_step(std::integral_constant<unsigned, 0>{}, g);
@@ -992,22 +994,24 @@ int launch1(const VtResampleParams &P, const float *d_src4, int m, cudaStream_t 
 
 // the axis (0, 1, 2) every matrix of the batch leaves alone in the way this family needs, or -1.  Axis 0 first: it is
 // the one whose layout the prefilter can write directly.
-bool vt_z4_axis_accepts(const VtResampleParams &P, int axis);
 int vt_z4_axis(const VtResampleParams &P, int interp)
 {
     (void)interp;
     const int sdim[3] = {P.s0, P.s1, P.s2};
-    (void)sdim;
-    for (int m = 0; m < 3; m++)
-        if (vt_z4_axis_accepts(P, m)) return m;
+    const long long ostr_lim = 0x7fffffffLL;
+    if ((long long)P.o1 * P.o2 > ostr_lim) return -1;
+    for (int m = 0; m < 3; m++) {
+        bool ok = true;
+        for (int k = 0; k < P.n_mats && ok; k++) ok = z4_mat_ok(P.mats[k], m, sdim);
+        if (ok) return m;
+    }
     return -1;
 }
 
 bool vt_z4_axis_accepts(const VtResampleParams &P, int axis)
 {
     const int sdim[3] = {P.s0, P.s1, P.s2};
-    // (32-bit element offsets inside an output volume, with room for the march's warm-up steps below / past it)
-    if (((long long)P.o0 + 8) * P.o1 * P.o2 > 0x7fffffffLL || axis < 0 || axis > 2) return false;
+    if ((long long)P.o1 * P.o2 > 0x7fffffffLL || axis < 0 || axis > 2) return false;
     for (int k = 0; k < P.n_mats; k++)
         if (!z4_mat_ok(P.mats[k], axis, sdim)) return false;
     return true;
