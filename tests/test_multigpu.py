@@ -278,3 +278,28 @@ def test_sweep_and_zslab_two_ranks_gloo():
             # the all-reduced projection is complete and identical on every rank
             assert np.allclose(z['whole'], want.astype(np.float64).sum(axis=0), rtol=0, atol=1e-5 * shape[0])
         assert sorted(seen) == list(range(len(tilts)))
+
+
+def test_world_of_one_needs_no_process_group():
+    """Without torch.distributed initialised every entry point degenerates to its single-GPU form (no collective)."""
+    import torch.distributed as dist
+    assert not dist.is_initialized()
+    shape = (13, 16, 18)
+    vol = np.random.default_rng(42).random(shape, dtype=np.float32)
+    c = np.divide(np.subtract(shape, 1), 2, dtype=np.float32)
+    eng = OracleEngine()
+    mats = [transform_matrix(rotation=(0, a, 0), center=c) for a in (0, 40, 95)]
+    out, idx = multigpu.sweep(vol, mats, 'filt_bspline', engine=eng)
+    assert idx == [0, 1, 2]
+    for o, m in zip(out.numpy(), mats):
+        assert np.array_equal(o, oracle.affine(vol, m, 'filt_bspline'))
+    m = transform_matrix(rotation=(20, 30, 40), translation=(1, -2, 0.5), center=c)
+    info = {}
+    slab, (z0, z1) = multigpu.zslab_affine(vol, m, 'bspline_simple', engine=eng, shape=shape, timings=info)
+    assert (z0, z1) == (0, 13) and info['info']['path'] == 'broadcast'
+    assert np.array_equal(slab.numpy(), oracle.affine(vol, m, 'bspline_simple'))
+    assert multigpu.gather_slabs(slab) is slab
+    buf, width = multigpu.prepare_and_broadcast(eng, vol, 'filt_bspline', shape=shape)
+    assert width == 18 and np.array_equal(buf.numpy(), oracle.prefilter(vol))
+    whole = multigpu.zslab_project(vol, m, 'bspline_simple', engine=eng)
+    assert np.allclose(whole.numpy(), oracle.affine(vol, m, 'bspline_simple').astype(np.float64).sum(axis=0), atol=1e-4)
