@@ -92,6 +92,15 @@ class ClockSampler:
         except OSError:
             pass
 
+    def rows(self):
+        """Samples delivered so far."""
+        if self.p is None:
+            return 1 << 30  # no nvidia-smi here: nothing to wait for
+        try:
+            return sum(1 for r in Path(self.f.name).read_text().splitlines() if r.count(',') >= 6)
+        except OSError:
+            return 0
+
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.p is None:
@@ -336,11 +345,14 @@ def run_sweep(args, torch, vt, dev, barrier, reduce_max, with_e2e=True):
     step()
     torch.cuda.synchronize()
     step_s = reduce_max(time.perf_counter() - t_probe)
-    n_load = int(min(200, max(2, 0.6 / max(step_s, 1e-4))))
+    n_load = int(min(400, max(2, 0.4 / max(step_s, 1e-4))))
     clocks = clock_sampler(torch, dev)
-    for _ in range(n_load):
-        step()
-    torch.cuda.synchronize()
+    for _ in range(8):  # chunks of ~0.4 s until the sampler has delivered a few rows (nvidia-smi can take a second to start)
+        for _ in range(n_load):
+            step()
+        torch.cuda.synchronize()
+        if reduce_max(0.0 if clocks.rows() >= 3 else 1.0) == 0.0:  # collective: every rank leaves the loop together
+            break
     l0 = _native.launch_count()
     sec = reduce_max(timed(torch, step, args.steps, 0, barrier))
     launches = _native.launch_count() - l0
