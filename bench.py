@@ -433,37 +433,77 @@ def sweep_e2e(args, torch, vt, dev, barrier, reduce_max, shape, interp, mats, mi
         h_vol = h_vol.numpy()
     eng = multigpu.CudaEngine(dev)
     check = {}
+    my_mats = np.stack([mats[i] for i in mine]) if len(mine) else np.zeros((0, 4, 4), np.float32)
+    try:   # the rank's results land here, step after step (page-locked once, like the pinned input volume)
+        h_out = vt.pinned_empty((len(mine),) + tuple(shape))
+    except RuntimeError as e:
+        h_out = None
+        print(f'[bench] no page-locked result buffer ({e}); e2e falls back to per-angle calls', file=sys.stderr)
 
-    def step():
+    def resident():
         if world > 1:
             buf, width = multigpu.prepare_and_broadcast(eng, h_vol, interp, src=0, shape=shape)
-            sv = vt.StaticVolume.from_coefficients(buf, interp, width)
-        else:
-            sv = vt.StaticVolume(h_vol, interpolation=interp, device=f'gpu:{dev}')
+            return vt.StaticVolume.from_coefficients(buf, interp, width)
+        return vt.StaticVolume(h_vol, interpolation=interp, device=f'gpu:{dev}')
+
+    def step_batched():
+        sv = resident()
+        sv.affine_many(my_mats, output=h_out)   # returns when the last result is in host memory
+
+    def step_per_call():
+        sv = resident()
         for k, i in enumerate(mine):
             res = sv.affine(mats[i])  # numpy (pinned staging inside the library)
             if k == len(mine) // 2:
                 check['res'], check['k'] = res, k
 
-    steps = max(1, min(args.steps, 3))
-    step()
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    def timed(step):
+        steps = max(1, min(args.steps, 3))
         step()
-    torch.cuda.synchronize()
-    sec = reduce_max(time.perf_counter() - t0)
-    barrier()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        sec = reduce_max(time.perf_counter() - t0)
+        barrier()
+        return steps, sec
+
+    vox = len(mats) * n ** 3
+    steps, sec = timed(step_per_call)
     if 'res' in check:  # the host path must agree with the device path
         err = float((torch.from_numpy(check['res']).to(f'cuda:{dev}') - out_dev[check['k']]).abs().max())
         assert err <= 1e-5 * 16, f'host path differs from device path: {err}'
-    vox = len(mats) * n ** 3
+    per_call = {'value': vox * steps / sec / 1e9, 'ms_per_step': sec / steps * 1e3,
+                'call': "StaticVolume(host volume, 'filt_bspline') then sv.affine(m) -> numpy for each of the rank's angles "
+                        '(the reference README loop: one synchronous result at a time)'}
+    call, phases = per_call['call'], None
+    if h_out is not None:
+        steps, sec = timed(step_batched)
+        for k in sorted({0, len(mine) // 2, len(mine) - 1} if len(mine) else ()):
+            err = float((torch.from_numpy(h_out[k]).to(f'cuda:{dev}') - out_dev[k]).abs().max())
+            assert err <= 1e-5 * 16, f'host results differ from device results: {err} (angle {mine[k]})'
+        call = ("StaticVolume(host volume, 'filt_bspline').affine_many(matrices, output=page-locked numpy array): the "
+                "rank's results stream to host memory while the next kernels run")
+        # one more (untimed) step, phase by phase, on this rank
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sv = resident()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        sv.affine_many(my_mats, output=h_out)
+        t2 = time.perf_counter()
+        phases = {'resident_volume_ms': (t1 - t0) * 1e3, 'affine_many_to_host_ms': (t2 - t1) * 1e3,
+                  'd2h_GBps_rank0': len(mine) * n ** 3 * 4 / max(t2 - t1, 1e-9) / 1e9}
+        barrier()
     return {'value': vox * steps / sec / 1e9, 'unit': METRIC, 'h2d_bytes_per_step': n ** 3 * 4,
             'd2h_bytes_per_step': vox * 4, 'steps': steps, 'ms_per_step': sec / steps * 1e3,
-            'call': "StaticVolume(host volume, 'filt_bspline') then sv.affine(m) -> numpy for each of the rank's angles "
-                    '(H2D of the volume and D2H of every output volume inside the timed region; wall clock, max over ranks)',
-            'bound': 'PCIe D2H: 180 x 64 MiB per step'}
+            'call': call + ' (H2D of the volume, prefilter, broadcast and D2H of every output volume inside the timed '
+                           'region; wall clock, max over ranks)',
+            'per_call': per_call, 'phases': phases,
+            'bound': 'PCIe D2H: 180 x 64 MiB per step (raw pinned copies on this host: 57 GB/s for one GPU, 127 GB/s '
+                     'for four at once -- tools/e2e_probe.py)'}
 
 
 def random_rotation_mats(vt, n, count):

@@ -738,3 +738,36 @@ def test_second_device_in_one_process(vt):
         out = sv.affine_many([mats['rot45'], mats['full_affine']])
         assert out.device.index == 1
         assert _err(out[1].cpu().numpy(), oracle.affine(vol, mats['full_affine'], mode), r) <= TOL[mode]
+
+
+@pytest.mark.parametrize('pinned', [True, False])
+def test_affine_many_into_host_memory(vt, pinned, monkeypatch):
+    """affine_many(output=<numpy array>): K results stream into host memory through the three-chunk ring (K `.get()`s of
+    volume.py:99 overlapped with the kernels): identical to the device results, ring slots reused, ragged last chunk."""
+    import torch
+    shape = (24, 28, 32)
+    vol = np.random.default_rng(11).random(shape, dtype=np.float32)
+    sv = vt.StaticVolume(vol, interpolation='filt_bspline', device='gpu:0')
+    c = _center(shape)
+    mats = [vt.utils.transform_matrix(rotation=(0, 9 * a, 0), rotation_order='rzxz', center=c) for a in range(11)]
+    want = sv.affine_many(mats).cpu().numpy()
+    monkeypatch.setattr(vt.StaticVolume, 'HOST_CHUNK_BYTES', 2 * 4 * int(np.prod(shape)))   # 2 volumes per chunk: 6 chunks
+    out = vt.pinned_empty((len(mats),) + shape) if pinned else np.empty((len(mats),) + shape, np.float32)
+    assert torch.from_numpy(out).is_pinned() == pinned
+    out[:] = 7.0
+    assert sv.affine_many(mats, output=out) is None
+    assert np.array_equal(out, want)
+    for a, m in enumerate(mats[:3]):
+        assert np.array_equal(out[a], sv.affine(m))
+    with pytest.raises(ValueError):
+        sv.affine_many(mats, output=np.empty((3,) + shape, np.float32))
+    with pytest.raises(ValueError):
+        sv.affine_many(mats, output=np.empty((len(mats),) + shape, np.float64))
+    # a registered (not allocator-owned) pinned array: the > 1 GiB route of pinned_empty, forced small
+    from voltools_b200 import _native
+    monkeypatch.setattr(_native, 'PINNED_CACHE_LIMIT', 0)
+    big = vt.pinned_empty((len(mats),) + shape)
+    assert torch.from_numpy(big).is_pinned()
+    sv.affine_many(mats, output=big)
+    assert np.array_equal(big, want)
+    del big

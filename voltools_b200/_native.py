@@ -385,11 +385,31 @@ class HostContext:
             pass
 
 
+PINNED_CACHE_LIMIT = 1 << 30
+
+
 def pinned_empty(shape):
-    """A float32 numpy array backed by page-locked memory from torch's caching host allocator (the block returns to the
-    cache when the array is garbage-collected): device copies into / out of it are asynchronous and run at link speed."""
+    """A float32 numpy array in page-locked memory: device copies into / out of it are asynchronous and run at link
+    speed.  Up to 1 GiB it comes from torch's caching host allocator (the block returns to the cache when the array is
+    garbage-collected); larger arrays -- the host side of `StaticVolume.affine_many(output=...)` for a whole sweep -- are
+    ordinary numpy memory registered with the driver at its exact size (the caching allocator rounds up to a power of
+    two) and unregistered when the array dies."""
     import torch
-    return torch.empty(tuple(int(v) for v in shape), dtype=torch.float32, pin_memory=True).numpy()
+    shape = tuple(int(v) for v in shape)
+    n = 4
+    for v in shape:
+        n *= v
+    if n <= PINNED_CACHE_LIMIT:
+        return torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
+    import weakref
+    torch.cuda.init()
+    rt = torch.cuda.cudart()
+    a = np.empty(shape, dtype=np.float32)
+    err = rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+    if int(err) != 0:
+        raise RuntimeError(f'cudaHostRegister of {a.nbytes} bytes failed: error {int(err)}')
+    weakref.finalize(a, rt.cudaHostUnregister, a.ctypes.data)
+    return a
 
 
 def as_pinned(a):

@@ -185,11 +185,18 @@ class StaticVolume:
 
         output: None -> returns a new torch CUDA tensor of shape (K, *shape), zero where out of bounds;
                 a (K, *shape) device array -> written in place (out-of-bounds voxels untouched unless
-                zero_fill=True), returns None.
+                zero_fill=True), returns None;
+                a (K, *shape) float32 C-contiguous NUMPY array -> the K results land in host memory (K `.get()`s of
+                volume.py:99, pipelined: the kernels of chunk c+1 run while chunk c crosses PCIe), every voxel
+                overwritten (zero where out of bounds), returns None.  Give it page-locked memory
+                (`voltools_b200.pinned_empty`) and the copies run at link rate; a pageable array is filled through
+                two pinned staging buffers and a host memcpy.
         """
         torch = _torch()
         m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 4, 4)
         k = len(m)
+        if isinstance(output, np.ndarray):
+            return self._affine_many_host(m, output)
         with torch.cuda.device(self._dev):
             stream = _stream(self._dev)
             if output is None:
@@ -203,6 +210,64 @@ class StaticVolume:
                 flags = _native.OOB_ZERO if zero_fill else _native.OOB_SKIP
             self._launch(ptr, m, flags, stream)
         return out_t
+
+    HOST_CHUNK_BYTES = 128 << 20   # device staging per chunk of the host-output pipeline (three in flight)
+
+    def _affine_many_host(self, m, out):
+        """K results into the host array `out`: a ring of three device chunks; the kernels write chunk c on the
+        caller's stream, a copy stream ships it while the kernels of chunk c+1 run."""
+        torch = _torch()
+        k = len(m)
+        if out.shape != (k,) + self.shape or out.dtype != np.float32 or not out.flags['C_CONTIGUOUS'] \
+                or not out.flags['WRITEABLE']:
+            raise ValueError(f'output must be a writeable C-contiguous float32 array of shape {(k,) + self.shape}')
+        if k == 0:
+            return None
+        host_t = torch.from_numpy(out)
+        pinned = host_t.is_pinned()
+        vol_bytes = 4 * int(np.prod(self.shape))
+        per = int(max(1, min(k, self.HOST_CHUNK_BYTES // max(vol_bytes, 1))))
+        n_chunks = -(-k // per)
+        with torch.cuda.device(self._dev):
+            cur = torch.cuda.current_stream(self._dev)
+            cp = getattr(self, '_copy_stream', None)
+            if cp is None:
+                cp = self._copy_stream = torch.cuda.Stream(device=self._dev)
+            slots = [torch.empty((per,) + self.shape, dtype=torch.float32, device=f'cuda:{self._dev}')
+                     for _ in range(min(3, n_chunks))]
+            slot_free = [None] * len(slots)
+            stage = [] if pinned else [torch.empty((per,) + self.shape, dtype=torch.float32, pin_memory=True)
+                                       for _ in range(min(2, n_chunks))]
+            pending = []   # pageable destination: (copy-done event, staging index, k0, k1)
+
+            def drain_one():
+                ev, si, a, b = pending.pop(0)
+                ev.synchronize()
+                np.copyto(out[a:b], stage[si][:b - a].numpy())
+
+            for c in range(n_chunks):
+                k0, k1 = c * per, min(k, (c + 1) * per)
+                s = c % len(slots)
+                if slot_free[s] is not None:
+                    cur.wait_event(slot_free[s])
+                self._launch(slots[s].data_ptr(), m[k0:k1], _native.OOB_ZERO, cur.cuda_stream)
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                cp.wait_event(ready)
+                if not pinned and len(pending) == len(stage):
+                    drain_one()
+                with torch.cuda.stream(cp):
+                    dst = host_t[k0:k1] if pinned else stage[c % len(stage)][:k1 - k0]
+                    dst.copy_(slots[s][:k1 - k0], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(cp)
+                slot_free[s] = done
+                if not pinned:
+                    pending.append((done, c % len(stage), k0, k1))
+            while pending:
+                drain_one()
+            cp.synchronize()   # the ring and `out` are safe to reuse / read from here on
+        return None
 
     # -- rotate-and-project (examples/projections.py:20-26: `transform(...).sum(axis=0)`, fused) ----------
     def _project(self, ptr, m, z_range, stream):
