@@ -217,6 +217,23 @@ __device__ __forceinline__ void vt_tma_load_3d(unsigned smem_dst, const void *tm
         "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy): evict_last keeps a volume that every matrix of a launch
+// re-reads resident while the outputs stream through the cache
+__device__ __forceinline__ unsigned long long vt_l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void vt_tma_load_3d_hint(unsigned smem_dst, const void *tmap, unsigned bar, int c0, int c1, int c2,
+                                                    unsigned long long policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::
+            "r"(smem_dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
 // 4-D tiled box STORE shared -> global (bulk async group); elements outside the tensor are not written
 __device__ __forceinline__ void vt_tma_store_4d(const void *tmap, unsigned smem_src, int c0, int c1, int c2, int c3)
 {

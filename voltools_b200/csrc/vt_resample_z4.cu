@@ -331,6 +331,9 @@ __host__ __device__ __forceinline__ int floordiv4(int v) { return v >> 2; }  // 
 // Gvox/s at 256^3; the elected-lane bookkeeping of every warp and step costs more than the barrier it removes.)
 // TSY: rows of the tile (16 or 8).  8-row tiles = 128-thread CTAs, twice as many per SM: the same number of warps, but
 // barriers that tie 4 warps instead of 8 and CTAs that drift apart more (knob VT_Z4_TSY, measured in DESIGN.md).
+#ifndef VT_Z4_L2_HINTS
+#define VT_Z4_L2_HINTS 0   // bit 0: TMA loads with L2 evict_last; bit 1: streaming output stores (A/B: tools/z4_l2_ab.sh)
+#endif
 #ifndef VT_Z4_CT8_RESIDENT
 #define VT_Z4_CT8_RESIDENT 4  // resident 128-thread CTAs per SM the cubic_tex kernel is compiled for (register cap 65536 / 128 / N)
 #endif
@@ -406,12 +409,19 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
     int g = floordiv4(q_first);
     const unsigned tx_bytes = 16u * (unsigned)(pitch * P.bh);
 
+#if VT_Z4_L2_HINTS & 1
+    const unsigned long long l2_keep = vt_l2_policy_evict_last();
+#endif
     // one elected thread: stage group gg into ring stage st
     auto load_group = [&](int gg, unsigned st) {
         const unsigned bar = bars_s + 8u * st;
         vt_mbar_expect_tx(bar, tx_bytes);
         // groups / rows / columns outside the source arrive as zeros (= the texture's border mode)
+#if VT_Z4_L2_HINTS & 1
+        vt_tma_load_3d_hint(ring_s + st * stage_bytes, &G.map[pidx], bar, 4 * xlo, ylo, gg, l2_keep);
+#else
         vt_tma_load_3d(ring_s + st * stage_bytes, &G.map[pidx], bar, 4 * xlo, ylo, gg);
+#endif
     };
     constexpr int AHEAD = NSTAGE - 1;  // groups in flight after the prologue
     if (tid == 0) {
@@ -572,7 +582,11 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
                     float *d = dstp;
 #pragma unroll
                     for (int p = 0; p < 4; p++) {
+#if VT_Z4_L2_HINTS & 2
+                        __stcs(d, r[p]);  // streaming (evict-first) store: the outputs must not push the volume out of L2
+#else
                         *d = r[p];
+#endif
                         d += osm;
                     }
                 }
