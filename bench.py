@@ -396,8 +396,8 @@ def run_sweep(args, torch, vt, dev, barrier, reduce_max, with_e2e=True):
                     'step_frac': 8.0 * vox_step * args.steps / sec / 1e9 / peak / world,
                     'note': 'achieved = 8 B/voxel (4 B compulsory read + 4 B write) x voxels per launch / average launch '
                             'duration on rank 0; out-of-bounds voxels (1 - inbounds_fraction) are counted although they are '
-                            'neither read nor written; the 64 MiB coefficient volume is L2-resident across a sweep, so the '
-                            'real HBM traffic is the 4 B/voxel of writes; step_frac = the same for the whole step per GPU',
+                            'neither read nor written; ncu sees the algorithmic bytes at DRAM (the 64 MiB volume is fetched '
+                            'about once per matrix, 4 B/voxel of writes); step_frac = the same for the whole step per GPU',
                     'kernels': kernels}
 
     line = {
@@ -406,7 +406,7 @@ def run_sweep(args, torch, vt, dev, barrier, reduce_max, with_e2e=True):
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': cfg['name'].replace('256^3', f'{n}^3'), 'voxels_per_step': vox_step,
                    'parallelism': f'dp{world} over the matrix batch',
-                   'l2': 'outputs (180 x 64 MiB per step) exceed L2; the 64 MiB coefficient volume is L2-resident by design',
+                   'l2': 'outputs (180 x 64 MiB per step) exceed L2 and stream through it; no flush between steps is needed',
                    'call': "StaticVolume(vol, 'filt_bspline').affine_many(matrices, output=device array) -- eager calls, "
                            'no CUDA graph', 'timing': 'CUDA events around K steps, barrier + synchronize on both sides, '
                                                       'max over ranks'},
