@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 5
+#define VT_ABI_VERSION 6
 
 /* status codes: 0 ok; 1..99 library errors; 1000+e = cudaError_t e; 2000+e = CUresult e */
 #define VT_OK 0
@@ -89,6 +89,13 @@ int vt_prefilter_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, i
  */
 int vt_prefilter_strided_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride,
                              long long dst_plane_stride, int variant, int device, void *stream);
+
+/*
+ * The unfiltered counterpart: a dense (d0,d1,d2) volume copied into rows of dst_row_stride elements (pad columns zero),
+ * plane stride d1*dst_row_stride -- the layout vt_affine_strided_f32 can stage with TMA for any d2.  One 8 B/voxel pass;
+ * the reference pays the same pass for its CUDA-array copy (voltools/transforms.py:197-199, voltools/volume.py:46-48).
+ */
+int vt_pad_rows_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride, int device, void *stream);
 
 /*
  * Same with a caller-owned device workspace of vt_prefilter_workspace_bytes(...) bytes (distinct from d_src and

@@ -115,7 +115,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f'{name} declared in the header but not exported'
     lib.vt_abi_version.restype = ctypes.c_int
-    assert lib.vt_abi_version() == 5
+    assert lib.vt_abi_version() == 6
     lib.vt_error_string.restype = ctypes.c_char_p
     assert lib.vt_error_string(0) == b'ok'
     assert lib.vt_error_string(2) != b'ok'

@@ -85,7 +85,8 @@ def lib():
         L.vt_profile_kernel_name.restype = ctypes.c_char_p
         L.vt_profile_kernel_name.argtypes = [_i]
         L.vt_profile_read.argtypes = [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
-        if L.vt_abi_version() != 5:
+        L.vt_pad_rows_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, _i, _vp]
+        if L.vt_abi_version() != 6:
             raise RuntimeError('libvoltools_b200.so ABI version mismatch')
         _lib = L
     return _lib
@@ -158,6 +159,11 @@ def prefilter(src_ptr, shape, device=-1, stream=0, variant=0, dst_ptr=None, dst_
     del ws
 
 
+def pad_rows(src_ptr, shape, dst_ptr, row, device=-1, stream=0):
+    """Dense volume -> rows padded to `row` elements (vt_pad_rows_f32)."""
+    check(lib().vt_pad_rows_f32(src_ptr, dst_ptr, int(shape[0]), int(shape[1]), int(shape[2]), int(row), device, stream))
+
+
 def prefilter_planes(src_ptr, ws_ptr, dst_ptr, shape, dst_strides, xy_range, z_range, device=-1, stream=0):
     """Streaming prefilter step (vt_prefilter_planes_f32): XY passes of sample planes xy_range into the workspace,
     Z pass of coefficient planes z_range from the workspace into dst."""
@@ -184,17 +190,21 @@ def affine(src_ptr, src_shape, dst_ptr, dst_shape, matrices, interp, flags=0, ba
 import os as _os
 
 
-def z4_wanted(interp, resident, axis=0, filtered=False):
+def z4_wanted(interp, resident, axis=0, filtered=False, width=None):
     """Policy: does a launch whose matrices leave `axis` alone go to the slice4 kernels?  A resident volume always
     (the Z4 copy is packed once and kept).  A one-shot call pays a pack pass (8 B/voxel) unless the prefilter writes
     the layout directly (filt_*, axis 0): measured at 512^3 the pass is paid back whenever
     the alternative is the general-matrix kernels (axes 1 and 2: 2-6x), and for axis 0 only with the prefilter
     (pack + slice4 221 / 236 Gvox/s against 250 / 280 for the plain-layout slice kernels, bspline / bspline_simple).
+    A one-shot volume whose rows are not a multiple of 16 bytes (width 250: the reference's benchmark size) needs a
+    copy pass before ANY TMA-staged kernel can read it; the pack pass is that copy, so it goes to slice4 as well.
     VT_Z4=0/1 forces it off/on (A/B measurements)."""
     force = _os.environ.get('VT_Z4')
     if force is not None:
         return force != '0'
     if resident or axis != 0:
+        return True
+    if width is not None and padded_row(width) != int(width):
         return True
     return bool(filtered)
 
@@ -306,7 +316,7 @@ def launch_plan(src_ptr, src_shape, dst_shape, matrices, interp, resident=True, 
     the slice4 kernels before asking the plain-layout planner): {'family': 'slice4', 'axis': m} or
     {'family': 'slice' | 'brick' | 'gather'}."""
     axis = z4_axis(src_shape, dst_shape, matrices, interp)
-    if axis >= 0 and z4_wanted(interp, resident, axis, filtered):
+    if axis >= 0 and z4_wanted(interp, resident, axis, filtered, width=src_shape[2]):
         return {'family': 'slice4', 'axis': axis}
     return {'family': affine_plan(src_ptr, src_shape, dst_shape, matrices, interp)}
 

@@ -73,7 +73,7 @@ const char *const g_prof_names[VT_K_COUNT] = {
     "prefilter_x", "prefilter_y", "prefilter_z", "prefilter_fused", "gather_linear", "gather_cubic_tex",
     "gather_cubic_simple", "brick_linear", "brick_cubic_tex", "brick_cubic_simple", "slice_linear",
     "slice_cubic_tex", "slice_cubic_simple", "tex_linear", "tex_cubic", "plane_sum", "project_2d", "z4_linear",
-    "z4_cubic_tex", "z4_cubic_simple", "pack_z4"};
+    "z4_cubic_tex", "z4_cubic_simple", "pack_z4", "pad_rows"};
 
 void prof_drain_locked()
 {
@@ -428,6 +428,27 @@ int vt_pack_z4_f32(const float *d_src, int s0, int s1, int s2, long long src_row
     DeviceGuard g(device);
     if (g.status) return g.status;
     return vt_pack_z4_impl(d_src, s0, s1, s2, src_row_stride, src_plane_stride, d_dst4, axis, (cudaStream_t)stream);
+}
+
+__global__ void vt_pad_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int row, size_t rows);
+
+int vt_pad_rows_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride, int device, void *stream)
+{
+    if (!d_src || !d_dst || d_src == d_dst || d0 < 1 || d1 < 1 || d2 < 1 || dst_row_stride < d2) return VT_ERR_INVALID_ARG;
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_row_stride > 0x7fffffffLL) return VT_ERR_INVALID_ARG;
+    const size_t rows = (size_t)d0 * d1;
+    const size_t n = rows * (size_t)dst_row_stride;
+    const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
+    {
+        VtProf prof(VT_K_PAD_ROWS, st);
+        vt_pad_rows_kernel<<<blocks, 256, 0, st>>>(d_src, d_dst, d2, (int)dst_row_stride, rows);
+    }
+    vt_count_launch();
+    VT_CUDA(cudaGetLastError());
+    return VT_OK;
 }
 
 int vt_prefilter_z4_f32(const float *d_src, float *d_dst4, int d0, int d1, int d2, void *d_workspace, size_t workspace_bytes,

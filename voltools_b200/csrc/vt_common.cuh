@@ -74,6 +74,7 @@ enum VtKernelId {
     VT_K_Z4_CUBIC_TEX,
     VT_K_Z4_CUBIC_SIMPLE,
     VT_K_PACK_Z4,
+    VT_K_PAD_ROWS,
     VT_K_COUNT
 };
 struct VtProf {

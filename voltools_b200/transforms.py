@@ -279,7 +279,7 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
             # axis 0, otherwise one pack pass (the reference pays the same pass for its CUDA-array copy,
             # transforms.py:197-199).
             axis = _native.z4_axis(shape, shape, m, interp)
-            if axis >= 0 and _native.z4_wanted(interp, False, axis, needs_prefilter):
+            if axis >= 0 and _native.z4_wanted(interp, False, axis, needs_prefilter, width=shape[2]):
                 z4_t = torch.empty(_native.z4_bytes(shape, axis) // 4, dtype=torch.float32, device=f'cuda:{dev}')
                 if needs_prefilter:
                     ws_t = torch.empty(shape, dtype=torch.float32, device=f'cuda:{dev}')
@@ -307,7 +307,7 @@ def affine(volume, transform_m: np.ndarray, interpolation: str = 'linear', resha
                     src_t, src_ptr = coef_t, coef_t.data_ptr()
                 elif row != shape[2]:
                     pad_t = torch.empty((shape[0], shape[1], row), dtype=torch.float32, device=f'cuda:{dev}')
-                    pad_t[:, :, :shape[2]].copy_(src_t)
+                    _native.pad_rows(src_ptr, shape, pad_t.data_ptr(), row, device=dev, stream=stream)
                     src_t, src_ptr = pad_t, pad_t.data_ptr()
                 _native.affine(src_ptr, shape, dst_ptr, shape, m, interp, flags, device=dev, stream=stream,
                                src_strides=src_strides)

@@ -59,9 +59,10 @@ class StaticVolume:
                 _native.prefilter(raw.data_ptr(), self.shape, self._dev, _stream(self._dev),
                                   dst_ptr=self._coeffs.data_ptr(), dst_strides=self._strides)
             elif row != self.shape[2]:
-                self._coeffs = torch.zeros((self.shape[0], self.shape[1], row), dtype=torch.float32,
+                self._coeffs = torch.empty((self.shape[0], self.shape[1], row), dtype=torch.float32,
                                            device=f'cuda:{self._dev}')
-                self._coeffs[:, :, :self.shape[2]].copy_(raw)
+                _native.pad_rows(raw.data_ptr(), self.shape, self._coeffs.data_ptr(), row, device=self._dev,
+                                 stream=_stream(self._dev))
             del raw
 
     # -- resident buffer access (used by the multi-GPU layer) -------------------------------------------
