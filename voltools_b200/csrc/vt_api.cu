@@ -431,6 +431,7 @@ int vt_pack_z4_f32(const float *d_src, int s0, int s1, int s2, long long src_row
 }
 
 __global__ void vt_pad_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int row, size_t rows);
+static inline unsigned pad_rows_blocks(size_t rows);
 
 int vt_pad_rows_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, long long dst_row_stride, int device, void *stream)
 {
@@ -440,11 +441,9 @@ int vt_pad_rows_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, lo
     cudaStream_t st = (cudaStream_t)stream;
     if (dst_row_stride > 0x7fffffffLL) return VT_ERR_INVALID_ARG;
     const size_t rows = (size_t)d0 * d1;
-    const size_t n = rows * (size_t)dst_row_stride;
-    const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
     {
         VtProf prof(VT_K_PAD_ROWS, st);
-        vt_pad_rows_kernel<<<blocks, 256, 0, st>>>(d_src, d_dst, d2, (int)dst_row_stride, rows);
+        vt_pad_rows_kernel<<<pad_rows_blocks(rows), dim3(64, 4), 0, st>>>(d_src, d_dst, d2, (int)dst_row_stride, rows);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
@@ -761,16 +760,25 @@ int vt_host_ctx_destroy(vt_host_ctx *c)
     return VT_OK;
 }
 
-// dense rows -> rows padded to `row` floats (pad columns zero); one thread per destination element
-__global__ void vt_pad_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int row, size_t rows)
+// dense rows -> rows padded to `row` floats (pad columns zero); blockDim = (64, 4): threadIdx.y picks a row, the 64 lanes
+// walk along it (no per-element division: the one-thread-per-element version was instruction bound)
+__global__ void __launch_bounds__(256) vt_pad_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int row,
+                                                          size_t rows)
 {
-    const size_t n = rows * (size_t)row;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / (unsigned)row;
-        const int x = (int)(i - r * (unsigned)row);
-        dst[i] = x < w ? src[r * (size_t)w + x] : 0.0f;
+    for (size_t r = (size_t)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (size_t)gridDim.x * blockDim.y) {
+        const float *s = src + r * (size_t)w;
+        float *d = dst + r * (size_t)row;
+        for (int x0 = threadIdx.x; x0 < row; x0 += 4 * 64) {  // four loads in flight per thread
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = x0 + 64 * k < w ? __ldg(s + x0 + 64 * k) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (x0 + 64 * k < row) d[x0 + 64 * k] = v[k];
+        }
     }
 }
+static inline unsigned pad_rows_blocks(size_t rows) { return (unsigned)((rows + 3) / 4 < 148 * 128 ? (rows + 3) / 4 : 148 * 128); }
 
 static int ensure(float **p, size_t *cap, size_t bytes)
 {
@@ -915,9 +923,7 @@ static int host_affine_impl(vt_host_ctx *c, const float *h_src, int s0, int s1, 
             ready = z_done;
         } else if (pad) {
             const size_t rows = (size_t)(h1 - h0) * s1;
-            const size_t n = rows * (size_t)row;
-            const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-            vt_pad_rows_kernel<<<blocks, 256, 0, c->st_k>>>(c->d_src + (size_t)h0 * plane_in, c->d_coef + (size_t)h0 * plane,
+            vt_pad_rows_kernel<<<pad_rows_blocks(rows), dim3(64, 4), 0, c->st_k>>>(c->d_src + (size_t)h0 * plane_in, c->d_coef + (size_t)h0 * plane,
                                                            s2, (int)row, rows);
             vt_count_launch();
             VT_CUDA(cudaGetLastError());
