@@ -73,6 +73,7 @@ struct Z4Params {
     int tiles_fast;
     int tsy;                           // rows of a tile: 16 (256-thread CTAs) or 8 (128-thread CTAs)
     int march;                         // the march axis (0..2): selects the slots of the texture-weight rule
+    int mat_fastest;                   // block order: 1 = the matrix index varies fastest (blockIdx.x = tile * n_mats + mat)
     int vec_store;                     // march axis contiguous in the output and 16-byte alignable: STG.128 quads
     int tma_store;                     // ... and staged through shared memory + cp.async.bulk.tensor stores (UTMASTG)
     Z4Mat mats[VT_MAX_BATCH];
@@ -352,8 +353,13 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
     using T = Taps4<INTERP>;
     static_assert(NSTAGE == 3 || NSTAGE == 4, "the ring loop is unrolled for 3 or 4 stages");
     const int tid = threadIdx.x;
-    const int tile_y = blockIdx.x / P.tiles_fast, tile_x = blockIdx.x - tile_y * P.tiles_fast;
-    const int mat = blockIdx.z;
+    // Block order.  Tile-fastest (the default: one matrix per wave of CTAs) or matrix-fastest (the same output tile of all
+    // matrices side by side: their footprints overlap, DRAM reads of a 32-matrix launch at 256^3 drop from 1.91 to 1.09 GB).
+    // Measured: no gain for the cubic kernels (shared-memory bound), and `linear` loses 8 % (neighbouring tiles of one
+    // output volume no longer write the two halves of a cache line at the same time) -- profiles/r02w_z4_block_order.log.
+    const int tile = P.mat_fastest ? (int)blockIdx.x / P.n_mats : (int)blockIdx.x;
+    const int mat = P.mat_fastest ? (int)blockIdx.x - tile * P.n_mats : (int)blockIdx.z;
+    const int tile_y = tile / P.tiles_fast, tile_x = tile - tile_y * P.tiles_fast;
     const Z4Mat &M = P.mats[mat];
     const int pidx = M.pitch_idx;
     const int pitch = P.bw0 + pidx;
@@ -894,7 +900,10 @@ int launch3(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
         fprintf(stderr, "z4 interp %d: box %d x %d, mat0 shape %d pitch +%d, wavefronts %.3f, chunks %d x %d\n", INTERP, L.bw0,
                 L.bh, P.mats[0].shape, P.mats[0].pitch_idx, L.cost, L.chunks, L.m_chunk);
     const int tiles = ((P.slow_e - P.slow_b + TSY - 1) / TSY) * P.tiles_fast;
-    dim3 grid(tiles, L.chunks, P.n_mats);
+    static const int order_env = getenv("VT_Z4_ORDER") ? atoi(getenv("VT_Z4_ORDER")) : -1;  // A/B knob: 0 tile-, 1 matrix-fastest
+    P.mat_fastest = order_env > 0 && P.n_mats > 1;
+    if ((long long)tiles * P.n_mats > 0x7fffffffLL) P.mat_fastest = 0;
+    dim3 grid(P.mat_fastest ? tiles * P.n_mats : tiles, L.chunks, P.mat_fastest ? 1 : P.n_mats);
     // ring: stages sized for this launch's box; four stages when the resident CTAs still fit, else three
     const unsigned stage_bytes = ((unsigned)(16 * (L.bw0 + NPITCH - 1) * L.bh) + 127u) & ~127u;
     constexpr int RESIDENT = z4_resident<INTERP>(TSY);
