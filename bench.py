@@ -471,6 +471,19 @@ def sweep_e2e(args, torch, vt, dev, barrier, reduce_max, shape, interp, mats, mi
         return steps, sec
 
     vox = len(mats) * n ** 3
+    raw = None
+    if h_out is not None and len(mine):   # the link itself, right now: plain copies of one device volume into h_out
+        d_one = torch.empty(shape, device=f'cuda:{dev}')
+        h_t = torch.from_numpy(h_out)
+        reps = min(len(mine), 16)
+        for timed_pass in (False, True):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for k in range(reps):
+                h_t[k].copy_(d_one, non_blocking=True)
+            torch.cuda.synchronize()
+            raw = reps * n ** 3 * 4 / (time.perf_counter() - t0) / 1e9
+        del d_one, h_t
     steps, sec = timed(step_per_call)
     if 'res' in check:  # the host path must agree with the device path
         err = float((torch.from_numpy(check['res']).to(f'cuda:{dev}') - out_dev[check['k']]).abs().max())
@@ -494,7 +507,8 @@ def sweep_e2e(args, torch, vt, dev, barrier, reduce_max, shape, interp, mats, mi
         t1 = time.perf_counter()
         sv.affine_many(my_mats, output=h_out)
         t2 = time.perf_counter()
-        phases = {'resident_volume_ms': (t1 - t0) * 1e3, 'affine_many_to_host_ms': (t2 - t1) * 1e3,
+        phases = {'raw_d2h_GBps_rank0_before': raw, 'resident_volume_ms': (t1 - t0) * 1e3,
+                  'affine_many_to_host_ms': (t2 - t1) * 1e3,
                   'd2h_GBps_rank0': len(mine) * n ** 3 * 4 / max(t2 - t1, 1e-9) / 1e9}
         barrier()
     return {'value': vox * steps / sec / 1e9, 'unit': METRIC, 'h2d_bytes_per_step': n ** 3 * 4,
