@@ -216,6 +216,12 @@ int choose_family(const VtResampleParams &P, int interp, unsigned flags)
 
 }  // namespace
 
+bool vt_pdl_enabled()
+{
+    static const bool on = !(getenv("VT_PDL") && atoi(getenv("VT_PDL")) == 0);
+    return on;
+}
+
 extern "C" {
 
 int vt_abi_version(void) { return VT_ABI_VERSION; }
@@ -443,7 +449,8 @@ int vt_pad_rows_f32(const float *d_src, float *d_dst, int d0, int d1, int d2, lo
     const size_t rows = (size_t)d0 * d1;
     {
         VtProf prof(VT_K_PAD_ROWS, st);
-        vt_pad_rows_kernel<<<pad_rows_blocks(rows), dim3(64, 4), 0, st>>>(d_src, d_dst, d2, (int)dst_row_stride, rows);
+        VT_CUDA(vt_launch_pdl(vt_pad_rows_kernel, dim3(pad_rows_blocks(rows)), dim3(64, 4), 0, st, d_src, d_dst, d2,
+                              (int)dst_row_stride, rows));
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
@@ -765,6 +772,7 @@ int vt_host_ctx_destroy(vt_host_ctx *c)
 __global__ void __launch_bounds__(256) vt_pad_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int row,
                                                           size_t rows)
 {
+    vt_pdl_wait();
     for (size_t r = (size_t)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (size_t)gridDim.x * blockDim.y) {
         const float *s = src + r * (size_t)w;
         float *d = dst + r * (size_t)row;

@@ -77,6 +77,35 @@ enum VtKernelId {
     VT_K_PAD_ROWS,
     VT_K_COUNT
 };
+// ---------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the kernels of a one-shot call (xy prefilter -> z prefilter -> pack -> slice4) are each
+// 30-70 us at the reference's benchmark sizes, so the launch gap between them is a visible share.  Launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization a kernel's CTAs become resident while the previous kernel of the
+// stream drains; vt_pdl_wait() at the very top of the kernel then blocks until that kernel has completed and its
+// writes are visible -- stream order as before, minus the launch latency.  VT_PDL=0 turns the attribute off.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void vt_pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool vt_pdl_enabled();  // vt_api.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t vt_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = vt_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct VtProf {
     int id;
     cudaStream_t st;

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(NT) prefilter_xy_kernel(const float *__restric
     constexpr int L = NT / RB;   // chunks (X-pass lanes) per row
     constexpr int P = L * SEG;   // tile row pitch in floats (= NT)
     extern __shared__ __align__(16) float smem[];  // NBUF tiles [RB][P]
+    vt_pdl_wait();
     const int z = z_first + blockIdx.z;
     const int x0 = blockIdx.x * x_strip, x1 = min(x0 + x_strip, W);  // columns written by this CTA
     const int xa = max(x0 - HX, 0), xb = min(x1 + HX, W);            // columns staged (X warm-up on both sides)
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(Z_THREADS) prefilter_z_kernel(const V *src, V 
     using O = ZOps<V>;
     constexpr size_t VW = sizeof(V) / sizeof(float);
     float4 *d4 = (float4 *)dst;
+    vt_pdl_wait();
     const size_t fcols = cols * VW;  // float columns per plane
     const size_t col = (size_t)blockIdx.x * Z_THREADS + threadIdx.x;
     if (col >= cols) return;
@@ -494,8 +496,8 @@ int launch_xy(const float *d_src, float *d_dst, int D, int H, int W, long long d
     // per device, so not cached in a static: a process may drive several GPUs
     VT_CUDA(cudaFuncSetAttribute(prefilter_xy_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VtProf prof(VT_K_PREFILTER_FUSED, st);
-    prefilter_xy_kernel<NT><<<dim3(strips, chunks, nz), NT, smem, st>>>(d_src, d_dst, H, W, dst_row, dst_plane, y_chunk,
-                                                                       x_strip, z0);
+    VT_CUDA(vt_launch_pdl(prefilter_xy_kernel<NT>, dim3(strips, chunks, nz), dim3(NT), smem, st, d_src, d_dst, H, W, dst_row,
+                          dst_plane, y_chunk, x_strip, z0));
     return VT_OK;
 }
 
@@ -563,16 +565,20 @@ static int z_range_impl(const float *d_src, float *d_dst, int d0, size_t cols, i
     {
         VtProf prof(VT_K_PREFILTER_Z, st);
         const dim3 grid((unsigned)bx, chunks);
+        cudaError_t e;
         if (pack && z4out)
-            prefilter_z_kernel<vt_f2, true><<<grid, Z_THREADS, 0, st>>>((const vt_f2 *)d_src, (vt_f2 *)d_dst, d_avail, vcols,
-                                                                        z_chunk, z0, z1);
+            e = vt_launch_pdl(prefilter_z_kernel<vt_f2, true>, grid, dim3(Z_THREADS), 0, st, (const vt_f2 *)d_src, (vt_f2 *)d_dst,
+                              d_avail, vcols, z_chunk, z0, z1);
         else if (pack)
-            prefilter_z_kernel<vt_f2, false><<<grid, Z_THREADS, 0, st>>>((const vt_f2 *)d_src, (vt_f2 *)d_dst, d_avail, vcols,
-                                                                         z_chunk, z0, z1);
+            e = vt_launch_pdl(prefilter_z_kernel<vt_f2, false>, grid, dim3(Z_THREADS), 0, st, (const vt_f2 *)d_src, (vt_f2 *)d_dst,
+                              d_avail, vcols, z_chunk, z0, z1);
         else if (z4out)
-            prefilter_z_kernel<float, true><<<grid, Z_THREADS, 0, st>>>(d_src, d_dst, d_avail, cols, z_chunk, z0, z1);
+            e = vt_launch_pdl(prefilter_z_kernel<float, true>, grid, dim3(Z_THREADS), 0, st, d_src, d_dst, d_avail, cols, z_chunk,
+                              z0, z1);
         else
-            prefilter_z_kernel<float, false><<<grid, Z_THREADS, 0, st>>>(d_src, d_dst, d_avail, cols, z_chunk, z0, z1);
+            e = vt_launch_pdl(prefilter_z_kernel<float, false>, grid, dim3(Z_THREADS), 0, st, d_src, d_dst, d_avail, cols, z_chunk,
+                              z0, z1);
+        VT_CUDA(e);
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());

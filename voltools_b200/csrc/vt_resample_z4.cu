@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(TS * TSY, z4_resident<INTERP>(TSY))
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using T = Taps4<INTERP>;
     static_assert(NSTAGE == 3 || NSTAGE == 4, "the ring loop is unrolled for 3 or 4 stages");
+    vt_pdl_wait();
     const int tid = threadIdx.x;
     // Block order.  Tile-fastest (the default: one matrix per wave of CTAs) or matrix-fastest (the same output tile of all
     // matrices side by side: their footprints overlap, DRAM reads of a 32-matrix launch at 256^3 drop from 1.91 to 1.09 GB).
@@ -652,6 +653,7 @@ __global__ void __launch_bounds__(256)
     vt_pack_z4_kernel(const float *__restrict__ src, float4 *__restrict__ dst, int dm, int dy, int dx, long long sm,
                       long long sy, long long sx)
 {
+    vt_pdl_wait();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, g = blockIdx.z;
     if (x >= dx) return;
@@ -924,12 +926,17 @@ int launch3(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
 #undef VT_Z4_ATTR
         attr_set.store(true, std::memory_order_release);
     }
+    cudaError_t launch_err = cudaSuccess;
     {
         VtProf prof(VT_K_Z4_LINEAR + INTERP, st);
 #define VT_Z4_GO(Z, N)                                                                                        \
     do {                                                                                                      \
-        if (P.vec_store) vt_z4_kernel<INTERP, RULE, Z, N, TSY, true><<<grid, TS * TSY, smem, st>>>(P, G, L.m_chunk, stage_bytes); \
-        else vt_z4_kernel<INTERP, RULE, Z, N, TSY, false><<<grid, TS * TSY, smem, st>>>(P, G, L.m_chunk, stage_bytes);           \
+        if (P.vec_store)                                                                                      \
+            launch_err = vt_launch_pdl(vt_z4_kernel<INTERP, RULE, Z, N, TSY, true>, grid, dim3(TS * TSY), smem, st, P, G,         \
+                                       L.m_chunk, stage_bytes);                                               \
+        else                                                                                                  \
+            launch_err = vt_launch_pdl(vt_z4_kernel<INTERP, RULE, Z, N, TSY, false>, grid, dim3(TS * TSY), smem, st, P, G,        \
+                                       L.m_chunk, stage_bytes);                                               \
     } while (0)
         if (oob_zero) {
             if (nstage == 4) VT_Z4_GO(true, 4); else VT_Z4_GO(true, 3);
@@ -939,6 +946,7 @@ int launch3(Z4Params &P, const float *d_src4, bool oob_zero, const float ext_y[]
 #undef VT_Z4_GO
     }
     vt_count_launch();
+    VT_CUDA(launch_err);
     VT_CUDA(cudaGetLastError());
     return VT_OK;
 }
@@ -1058,8 +1066,8 @@ int vt_pack_z4_impl(const float *d_src, int s0, int s1, int s2, long long row, l
     dim3 grid((d[R.ax] + 255) / 256, d[R.ay], groups);
     {
         VtProf prof(VT_K_PACK_Z4, st);
-        vt_pack_z4_kernel<<<grid, 256, 0, st>>>(d_src, (float4 *)d_dst4, d[axis], d[R.ay], d[R.ax], str[axis], str[R.ay],
-                                                str[R.ax]);
+        VT_CUDA(vt_launch_pdl(vt_pack_z4_kernel, grid, dim3(256), 0, st, d_src, (float4 *)d_dst4, d[axis], d[R.ay], d[R.ax],
+                              str[axis], str[R.ay], str[R.ax]));
     }
     vt_count_launch();
     VT_CUDA(cudaGetLastError());
