@@ -115,7 +115,9 @@ def test_c_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f'{name} declared in the header but not exported'
     lib.vt_abi_version.restype = ctypes.c_int
-    assert lib.vt_abi_version() == 6
+    from voltools_b200 import _native
+    version = int(re.search(r'#define\s+VT_ABI_VERSION\s+(\d+)', header).group(1))
+    assert lib.vt_abi_version() == version == _native.ABI_VERSION
     lib.vt_error_string.restype = ctypes.c_char_p
     assert lib.vt_error_string(0) == b'ok'
     assert lib.vt_error_string(2) != b'ok'

@@ -16,6 +16,7 @@ WEIGHTS_TEX_HW, WEIGHTS_EXACT = 0x0, 0x4
 KERNEL_AUTO, KERNEL_GATHER, KERNEL_BRICK, KERNEL_SLICE = 0x00, 0x10, 0x20, 0x30
 STAGE_CP_ASYNC = 0x100
 MAX_BATCH = 32
+ABI_VERSION = 6   # include/voltools_b200.h VT_ABI_VERSION
 
 # interpolation name -> (device function, needs prefilter)      voltools/transforms.py:11-17
 INTERPOLATIONS = {
@@ -86,8 +87,8 @@ def lib():
         L.vt_profile_kernel_name.argtypes = [_i]
         L.vt_profile_read.argtypes = [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
         L.vt_pad_rows_f32.argtypes = [_vp, _vp, _i, _i, _i, ctypes.c_longlong, _i, _vp]
-        if L.vt_abi_version() != 6:
-            raise RuntimeError('libvoltools_b200.so ABI version mismatch')
+        if L.vt_abi_version() != ABI_VERSION:
+            raise RuntimeError(f'libvoltools_b200.so ABI version {L.vt_abi_version()} != {ABI_VERSION}: rebuild it')
         _lib = L
     return _lib
 
