@@ -266,3 +266,24 @@ def test_slice4_planner_decisions_without_a_gpu():
     assert big['chunks'] >= 2 and big['m_chunk'] % 4 == 0
     # sizes of the layout: the march axis rounded up to a multiple of four
     assert N.z4_bytes((250, 30, 40), 0) == 252 * 30 * 40 * 4 and N.z4_bytes((250, 30, 41), 2) == 250 * 30 * 44 * 4
+
+
+def test_slice4_routing_policy(monkeypatch):
+    """_native.z4_wanted / launch_plan: which one-shot launches pay the Z4 pack pass.  Resident
+    volumes and axes 1 / 2 always; axis 0 only when the prefilter writes the layout (filt_*) or when the rows are not a
+    multiple of 16 bytes (250^3: the pack replaces the pad copy every TMA-staged kernel would need)."""
+    import voltools_b200 as vt
+    from voltools_b200 import _native as N
+    monkeypatch.delenv('VT_Z4', raising=False)
+    assert N.z4_wanted(N.CUBIC_TEX, True)
+    assert N.z4_wanted(N.LINEAR, False, axis=2)
+    assert not N.z4_wanted(N.LINEAR, False, axis=0, filtered=False, width=256)
+    assert N.z4_wanted(N.LINEAR, False, axis=0, filtered=True, width=256)
+    assert N.z4_wanted(N.LINEAR, False, axis=0, filtered=False, width=250)
+    assert N.padded_row(250) == 252 and N.padded_row(256) == 256
+    for n, family in ((250, 'slice4'), (256, 'slice')):
+        shape = (n, n, n)
+        m = vt.utils.transform_matrix(rotation=(0, 45, 0), rotation_order='rzxz', center=np.divide(np.subtract(shape, 1), 2, dtype=np.float32))
+        assert N.launch_plan(None, shape, shape, m, N.LINEAR, resident=False)['family'] == family
+    monkeypatch.setenv('VT_Z4', '0')
+    assert not N.z4_wanted(N.CUBIC_TEX, True)
