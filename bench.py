@@ -491,14 +491,16 @@ def sweep_e2e(args, torch, vt, dev, barrier, reduce_max, shape, interp, mats, mi
     per_call = {'value': vox * steps / sec / 1e9, 'ms_per_step': sec / steps * 1e3,
                 'call': "StaticVolume(host volume, 'filt_bspline') then sv.affine(m) -> numpy for each of the rank's angles "
                         '(the reference README loop: one synchronous result at a time)'}
-    call, phases = per_call['call'], None
-    if h_out is not None:
-        steps, sec = timed(step_batched)
+    phases, batched = None, None
+    # (collective decision: a rank without its page-locked buffer must not leave the others alone in a barrier)
+    if reduce_max(0.0 if h_out is not None else 1.0) == 0.0:
+        steps_b, sec_b = timed(step_batched)
         for k in sorted({0, len(mine) // 2, len(mine) - 1} if len(mine) else ()):
             err = float((torch.from_numpy(h_out[k]).to(f'cuda:{dev}') - out_dev[k]).abs().max())
             assert err <= 1e-5 * 16, f'host results differ from device results: {err} (angle {mine[k]})'
-        call = ("StaticVolume(host volume, 'filt_bspline').affine_many(matrices, output=page-locked numpy array): the "
-                "rank's results stream to host memory while the next kernels run")
+        batched = {'value': vox * steps_b / sec_b / 1e9, 'ms_per_step': sec_b / steps_b * 1e3,
+                   'call': "StaticVolume(host volume, 'filt_bspline').affine_many(matrices, output=page-locked numpy "
+                           "array): the rank's results stream to host memory while the next kernels run"}
         # one more (untimed) step, phase by phase, on this rank
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -511,11 +513,14 @@ def sweep_e2e(args, torch, vt, dev, barrier, reduce_max, shape, interp, mats, mi
                   'affine_many_to_host_ms': (t2 - t1) * 1e3,
                   'd2h_GBps_rank0': len(mine) * n ** 3 * 4 / max(t2 - t1, 1e-9) / 1e9}
         barrier()
-    return {'value': vox * steps / sec / 1e9, 'unit': METRIC, 'h2d_bytes_per_step': n ** 3 * 4,
-            'd2h_bytes_per_step': vox * 4, 'steps': steps, 'ms_per_step': sec / steps * 1e3,
-            'call': call + ' (H2D of the volume, prefilter, broadcast and D2H of every output volume inside the timed '
-                           'region; wall clock, max over ranks)',
-            'per_call': per_call, 'phases': phases,
+    # both forms are public-API calls for the same job with host buffers on both ends; the line's e2e is the faster one
+    # (one GPU: the batched form, by the overlap; several GPUs sharing the host's PCIe root: whichever the link favours)
+    best = batched if batched is not None and batched['value'] >= per_call['value'] else per_call
+    return {'value': best['value'], 'unit': METRIC, 'h2d_bytes_per_step': n ** 3 * 4,
+            'd2h_bytes_per_step': vox * 4, 'steps': steps, 'ms_per_step': best['ms_per_step'],
+            'call': best['call'] + ' (H2D of the volume, prefilter, broadcast and D2H of every output volume inside the '
+                                   'timed region; wall clock, max over ranks)',
+            'per_call': per_call, 'batched': batched, 'phases': phases,
             'bound': 'PCIe D2H: 180 x 64 MiB per step (raw pinned copies on this host: 57 GB/s for one GPU, 127 GB/s '
                      'for four at once -- tools/e2e_probe.py)'}
 
