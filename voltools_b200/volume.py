@@ -246,28 +246,32 @@ class StaticVolume:
                 ev.synchronize()
                 np.copyto(out[a:b], stage[si][:b - a].numpy())
 
-            for c in range(n_chunks):
-                k0, k1 = c * per, min(k, (c + 1) * per)
-                s = c % len(slots)
-                if slot_free[s] is not None:
-                    cur.wait_event(slot_free[s])
-                self._launch(slots[s].data_ptr(), m[k0:k1], _native.OOB_ZERO, cur.cuda_stream)
-                ready = torch.cuda.Event()
-                ready.record(cur)
-                cp.wait_event(ready)
-                if not pinned and len(pending) == len(stage):
+            try:
+                for c in range(n_chunks):
+                    k0, k1 = c * per, min(k, (c + 1) * per)
+                    s = c % len(slots)
+                    if slot_free[s] is not None:
+                        cur.wait_event(slot_free[s])
+                    self._launch(slots[s].data_ptr(), m[k0:k1], _native.OOB_ZERO, cur.cuda_stream)
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    cp.wait_event(ready)
+                    if not pinned and len(pending) == len(stage):
+                        drain_one()
+                    with torch.cuda.stream(cp):
+                        dst = host_t[k0:k1] if pinned else stage[c % len(stage)][:k1 - k0]
+                        dst.copy_(slots[s][:k1 - k0], non_blocking=True)
+                        done = torch.cuda.Event()
+                        done.record(cp)
+                    slot_free[s] = done
+                    if not pinned:
+                        pending.append((done, c % len(stage), k0, k1))
+                while pending:
                     drain_one()
-                with torch.cuda.stream(cp):
-                    dst = host_t[k0:k1] if pinned else stage[c % len(stage)][:k1 - k0]
-                    dst.copy_(slots[s][:k1 - k0], non_blocking=True)
-                    done = torch.cuda.Event()
-                    done.record(cp)
-                slot_free[s] = done
-                if not pinned:
-                    pending.append((done, c % len(stage), k0, k1))
-            while pending:
-                drain_one()
-            cp.synchronize()   # the ring and `out` are safe to reuse / read from here on
+            finally:
+                # also on an error path: no copy into `out` (or out of the ring) may still be running when the caller
+                # gets control back and is free to release either
+                cp.synchronize()
         return None
 
     # -- rotate-and-project (examples/projections.py:20-26: `transform(...).sum(axis=0)`, fused) ----------
