@@ -248,7 +248,7 @@ def reference_arm(args, cfg):
     procs = max(1, min(os.cpu_count() or 1, 32))
     t_probe, _ = _ref_worker((0, (16, n, n), cfg['interpolation'], _sweep_kw(45)))
     per_plane = t_probe / 16
-    budget = 150.0 / (args.steps + args.warmup)
+    budget = float(os.environ.get('VT_BENCH_REF_BUDGET_S', 150.0)) / (args.steps + args.warmup)  # CPU seconds per step
     planes = int(max(8, min(n, budget / per_plane)))
     shape = (planes, n, n)
     jobs = [(1000, shape, cfg['interpolation'], _sweep_kw((i * cfg['angles']) // procs)) for i in range(procs)]
